@@ -1,0 +1,229 @@
+// common.cuh — shared device helpers for the sm_100a posterior-update kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+
+#include "bde_b200.h"
+
+namespace bde {
+
+// ----------------------------------------------------------------------------
+// launch helpers
+// ----------------------------------------------------------------------------
+#define BDE_RETURN_IF_CUDA(expr)                       \
+    do {                                               \
+        cudaError_t _e = (expr);                       \
+        if (_e != cudaSuccess) return static_cast<int>(_e); \
+    } while (0)
+
+#define BDE_CHECK_LAUNCH()                             \
+    do {                                               \
+        cudaError_t _e = cudaGetLastError();           \
+        if (_e != cudaSuccess) return static_cast<int>(_e); \
+    } while (0)
+
+inline int sm_count_cached() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;
+    }
+    return cached[dev];
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ----------------------------------------------------------------------------
+// packed FP32x2 (Blackwell FADD2 / FMUL2 / FFMA2): two fp32 lanes in one 64-bit reg
+// ----------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// scalar-broadcast multiply-add: ptxas folds pack2(s, s) into the FFMA2 ".F32" operand form
+__device__ __forceinline__ f32x2 fma2s(float s, f32x2 b, f32x2 c) { return fma2(pack2(s, s), b, c); }
+
+// ----------------------------------------------------------------------------
+// 128-bit streaming global access (read-once / write-once data: keep it out of L1)
+// ----------------------------------------------------------------------------
+struct __align__(16) V4 {
+    f32x2 lo, hi;  // columns (0,1) and (2,3)
+};
+
+__device__ __forceinline__ V4 ldg_stream_v4(const float* p) {
+    V4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+    return v;
+}
+// cached variant (several warps of one CTA re-read the same lines)
+__device__ __forceinline__ V4 ldg_cached_v4(const float* p) {
+    V4 v;
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream_v4(float* p, V4 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(v.lo), "l"(v.hi) : "memory");
+}
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+// plain (coherent) 128-bit load for buffers that the same kernel also writes
+__device__ __forceinline__ float4 ld_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// reductions
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic grid-wide fp64 sum of `count` values per CTA.
+//   cta_vals: this CTA's values in shared memory (count doubles), valid after __syncthreads.
+//   ws layout: [0] ticket (unsigned, padded to 16 B), then gridDim.x*count doubles.
+// Returns true in every thread of the LAST CTA to arrive, after which
+// total[k] = sum over CTAs in blockIdx order is available in `total` (shared, count doubles).
+// The ticket is reset so the workspace can be reused by the next launch.
+__device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int count, void* ws, double* total) {
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
+    double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    __shared__ bool is_last;
+    for (int k = tid; k < count; k += nthreads) parts[(size_t)blockIdx.x * count + k] = cta_vals[k];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int prev = atomicAdd(ticket, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return false;
+    __threadfence();
+    for (int k = tid; k < count; k += nthreads) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&parts[(size_t)b * count + k]);
+        total[k] = s;
+    }
+    if (tid == 0) *ticket = 0u;
+    __syncthreads();
+    return true;
+}
+
+inline size_t grid_reduce_ws_bytes(int max_ctas, int count) { return 16 + sizeof(double) * (size_t)max_ctas * count; }
+
+// ----------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011) + Box-Muller.  counter = (q_lo, q_hi, sid_lo, sid_hi)
+// with q = global element index / 4; key = 64-bit seed.  One call -> 4 normals for
+// elements 4q .. 4q+3.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned int hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const unsigned int hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+__device__ __forceinline__ float u01_open(unsigned int r) {
+    // (r>>8) * 2^-24 + 2^-25  in (0, 1]
+    return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+}
+
+__device__ __forceinline__ void box_muller(unsigned int r0, unsigned int r1, float& z0, float& z1) {
+    const float u = u01_open(r0);
+    const float ang2 = static_cast<float>(r1 >> 8) * 1.1920928955078125e-07f;  // 2*u2 in [0, 2)
+    const float rad = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif(ang2, &s, &c);
+    z0 = rad * c;
+    z1 = rad * s;
+}
+
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream_id, uint64_t quad) {
+    const uint4 ctr = make_uint4(static_cast<unsigned int>(quad), static_cast<unsigned int>(quad >> 32),
+                                 static_cast<unsigned int>(stream_id), static_cast<unsigned int>(stream_id >> 32));
+    const uint2 key = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
+    const uint4 r = philox4x32_10(ctr, key);
+    float4 z;
+    box_muller(r.x, r.y, z.x, z.y);
+    box_muller(r.z, r.w, z.z, z.w);
+    return z;
+}
+
+// torch's softplus (beta=1, threshold=20) and its derivative factor, util.py:181-183
+__device__ __forceinline__ float softplus_ref(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float softplus_grad_ref(float x) {
+    if (x > 20.0f) return 1.0f;
+    const float z = expf(x);
+    return __fdiv_rn(z, __fadd_rn(z, 1.0f));
+}
+
+// ----------------------------------------------------------------------------
+// elementwise launch geometry: each thread handles one float4 per pass, grid-stride
+// ----------------------------------------------------------------------------
+struct EwGrid {
+    int blocks;
+    int threads;
+};
+inline EwGrid ew_grid(int64_t n_elems, int threads, int ctas_per_sm) {
+    const int64_t quads = (n_elems + 3) / 4;
+    int64_t want = (quads + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count_cached() * ctas_per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    return EwGrid{static_cast<int>(want), threads};
+}
+
+}  // namespace bde

@@ -1,0 +1,186 @@
+// ivon.cu — iVON posterior sampling, gradient accumulation and Hessian-EMA update.
+// Reference arithmetic: src/algos/ivorn.py:66-89 (update), :102-115 (sample), :120-127.
+// Each fp32 operation of the reference is reproduced in the same order with explicit
+// round-to-nearest intrinsics (no FMA contraction), python-side scalars are folded in
+// double and rounded to fp32 exactly where eager PyTorch rounds them.
+#include "elementwise.cuh"
+
+namespace bde {
+
+// K5 ------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kEwThreads)
+ivon_sample_kernel(const float* __restrict__ mean, const float* __restrict__ prec, float* __restrict__ delta_sum,
+                   float* __restrict__ theta, int64_t D, float n_eff, int first, int deterministic,
+                   const float* __restrict__ eps, uint64_t seed, uint64_t stream_id, int64_t quad0) {
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 m = load_quad<VEC, true>(mean, b, D);
+        float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!deterministic) {
+            const float4 p = load_quad<VEC, true>(prec, b, D);
+            float4 e;
+            if (eps)
+                e = load_quad<VEC, true>(eps, b, D);
+            else
+                e = philox_normal4(seed, stream_id, static_cast<uint64_t>(quad0 + q));
+            // ivorn.py:108  delta = 1 / (N * precision.clamp(min=1e-4)).sqrt() * normal
+            auto f = [&](float pv, float ev) {
+                const float r = __fsqrt_rn(__fmul_rn(n_eff, fmaxf(pv, 1e-4f)));
+                return __fmul_rn(__fdiv_rn(1.0f, r), ev);
+            };
+            dl = BDE_LANES(f(p.x, e.x), f(p.y, e.y), f(p.z, e.z), f(p.w, e.w));
+        }
+        const float4 th = BDE_LANES(__fadd_rn(m.x, dl.x), __fadd_rn(m.y, dl.y), __fadd_rn(m.z, dl.z), __fadd_rn(m.w, dl.w));
+        store_quad<VEC>(theta, b, D, th);
+        float4 ds = dl;
+        if (!first) {
+            const float4 o = load_quad<VEC, false>(delta_sum, b, D);
+            ds = BDE_LANES(__fadd_rn(o.x, dl.x), __fadd_rn(o.y, dl.y), __fadd_rn(o.z, dl.z), __fadd_rn(o.w, dl.w));
+        }
+        store_quad<VEC>(delta_sum, b, D, ds);
+    }
+}
+
+// K6 ------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kEwThreads)
+ivon_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ grad, int64_t D, int first) {
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        float4 g = load_quad<VEC, true>(grad, b, D);
+        if (!first) {
+            const float4 a = load_quad<VEC, false>(acc, b, D);
+            g = BDE_LANES(__fadd_rn(a.x, g.x), __fadd_rn(a.y, g.y), __fadd_rn(a.z, g.z), __fadd_rn(a.w, g.w));
+        }
+        store_quad<VEC>(acc, b, D, g);
+    }
+}
+
+// K7 ------------------------------------------------------------------------------------
+struct IvonScalars {
+    float S;        // mc_samples
+    float delta0;   // tempering * prior_prec / N_eff
+    float beta1;
+    float omb1;     // 1 - beta1
+    float n_eff;
+    float damping;
+    float bc1;      // 1 - beta1**t
+    float bc2;      // 1 - beta2**t
+    float lr;
+    float omb2;     // 1 - beta2
+    float c2;       // 0.5 * (1 - beta2)**2
+};
+
+__device__ __forceinline__ void ivon_update_one(const IvonScalars& c, float acc, float dsum, float& mean, float& mom,
+                                                float& prec) {
+    const float gradient = __fdiv_rn(acc, c.S);                                                // :79
+    const float g_mu = __fadd_rn(__fmul_rn(c.delta0, mean), gradient);                          // :80
+    const float m_new = __fadd_rn(__fmul_rn(c.beta1, mom), __fmul_rn(c.omb1, g_mu));            // :81
+    float t = __fmul_rn(c.n_eff, prec);                                                         // :82
+    t = __fmul_rn(t, dsum);
+    t = __fdiv_rn(t, c.S);
+    t = __fmul_rn(t, gradient);
+    float g_s = __fadd_rn(__fsub_rn(c.delta0, prec), t);
+    g_s = __fadd_rn(g_s, c.damping);
+    const float cm = __fdiv_rn(m_new, c.bc1);                                                   // :84
+    const float cp = __fdiv_rn(prec, c.bc2);                                                    // :85 (old precision)
+    const float mean_new = __fsub_rn(mean, __fdiv_rn(__fmul_rn(c.lr, cm), cp));                 // :88
+    float u = __fmul_rn(c.c2, g_s);                                                             // :89
+    u = __fdiv_rn(u, prec);
+    u = __fadd_rn(c.omb2, u);
+    u = __fmul_rn(u, g_s);
+    const float prec_new = __fadd_rn(prec, u);
+    mean = mean_new;
+    mom = m_new;
+    prec = prec_new;
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kEwThreads)
+ivon_update_kernel(const float* __restrict__ acc_grad, const float* __restrict__ delta_sum, float* __restrict__ mean,
+                   float* __restrict__ momentum, float* __restrict__ prec, int64_t D, IvonScalars c) {
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 a = load_quad<VEC, true>(acc_grad, b, D);
+        const float4 ds = load_quad<VEC, true>(delta_sum, b, D);
+        float4 m = load_quad<VEC, false>(mean, b, D);
+        float4 mo = load_quad<VEC, false>(momentum, b, D);
+        float4 p = load_quad<VEC, false>(prec, b, D);
+        ivon_update_one(c, a.x, ds.x, m.x, mo.x, p.x);
+        ivon_update_one(c, a.y, ds.y, m.y, mo.y, p.y);
+        ivon_update_one(c, a.z, ds.z, m.z, mo.z, p.z);
+        ivon_update_one(c, a.w, ds.w, m.w, mo.w, p.w);
+        store_quad<VEC>(mean, b, D, m);
+        store_quad<VEC>(momentum, b, D, mo);
+        store_quad<VEC>(prec, b, D, p);
+    }
+}
+
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_ivon_sample(const float* mean, const float* prec, float* delta_sum, float* theta, int64_t D,
+                               double n_eff, int first, int deterministic, const float* eps, uint64_t seed,
+                               uint64_t stream_id, int64_t elem0, bde_stream_t stream) {
+    if (!mean || !prec || !delta_sum || !theta || D < 0 || elem0 < 0 || (elem0 & 3)) return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const bool vec = aligned16(mean) && aligned16(prec) && aligned16(delta_sum) && aligned16(theta) &&
+                     (!eps || aligned16(eps));
+    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float nf = static_cast<float>(n_eff);
+    if (vec)
+        ivon_sample_kernel<true><<<g.blocks, g.threads, 0, st>>>(mean, prec, delta_sum, theta, D, nf, first,
+                                                                 deterministic, eps, seed, stream_id, elem0 >> 2);
+    else
+        ivon_sample_kernel<false><<<g.blocks, g.threads, 0, st>>>(mean, prec, delta_sum, theta, D, nf, first,
+                                                                  deterministic, eps, seed, stream_id, elem0 >> 2);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+extern "C" int bde_ivon_accumulate(float* acc, const float* grad, int64_t D, int first, bde_stream_t stream) {
+    if (!acc || !grad || D < 0) return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const bool vec = aligned16(acc) && aligned16(grad);
+    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec)
+        ivon_accumulate_kernel<true><<<g.blocks, g.threads, 0, st>>>(acc, grad, D, first);
+    else
+        ivon_accumulate_kernel<false><<<g.blocks, g.threads, 0, st>>>(acc, grad, D, first);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+extern "C" int bde_ivon_update(const float* acc_grad, const float* delta_sum, float* mean, float* momentum,
+                               float* prec, int64_t D, int mc_samples, int64_t step, double lr, double beta1,
+                               double beta2, double prior_prec, double n_eff, double tempering, double damping,
+                               bde_stream_t stream) {
+    if (!acc_grad || !delta_sum || !mean || !momentum || !prec || D < 0 || mc_samples < 1 || step < 1)
+        return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    IvonScalars c;
+    c.S = static_cast<float>(mc_samples);
+    c.delta0 = static_cast<float>(tempering * prior_prec / n_eff);
+    c.beta1 = static_cast<float>(beta1);
+    c.omb1 = static_cast<float>(1.0 - beta1);
+    c.n_eff = static_cast<float>(n_eff);
+    c.damping = static_cast<float>(damping);
+    c.bc1 = static_cast<float>(1.0 - pow(beta1, static_cast<double>(step)));
+    c.bc2 = static_cast<float>(1.0 - pow(beta2, static_cast<double>(step)));
+    c.lr = static_cast<float>(lr);
+    c.omb2 = static_cast<float>(1.0 - beta2);
+    c.c2 = static_cast<float>(0.5 * (1.0 - beta2) * (1.0 - beta2));
+    const bool vec = aligned16(acc_grad) && aligned16(delta_sum) && aligned16(mean) && aligned16(momentum) && aligned16(prec);
+    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec)
+        ivon_update_kernel<true><<<g.blocks, g.threads, 0, st>>>(acc_grad, delta_sum, mean, momentum, prec, D, c);
+    else
+        ivon_update_kernel<false><<<g.blocks, g.threads, 0, st>>>(acc_grad, delta_sum, mean, momentum, prec, D, c);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}

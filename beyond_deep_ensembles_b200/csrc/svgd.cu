@@ -1,0 +1,218 @@
+// svgd.cu — SVGD posterior update on sm_100a: generic kernels, K1b, dispatch and C-ABI.
+// Kernel templates live in svgd_kernels.cuh; reference arithmetic: src/algos/svgd.py:14-32, :83-97.
+#include "svgd_kernels.cuh"
+
+namespace bde {
+
+// unaligned / generic fallback: one column per thread, runtime n, fp64 accumulate per thread
+__global__ void __launch_bounds__(256)
+svgd_pairdist_scalar_kernel(const float* __restrict__ X, int n, int64_t D, int64_t ld, double* __restrict__ dist,
+                            int accumulate, void* ws) {
+    extern __shared__ double sm[];  // [P] cta_vals, [P] total
+    const int P = pair_count(n);
+    double* cta_vals = sm;
+    double* total = sm + P;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) cta_vals[p] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    int p = 0;
+    for (int i = 0; i < n; ++i) {
+        for (int j = i + 1; j < n; ++j, ++p) {
+            double s = 0.0;
+            for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < D;
+                 c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+                const float d = __ldg(X + i * ld + c) - __ldg(X + j * ld + c);
+                s += static_cast<double>(d * d);
+            }
+            s = warp_sum(s);
+            if (lane == 0) atomicAdd(&cta_vals[p], s);  // order within a CTA: fp64, <=8 warps
+        }
+    }
+    __syncthreads();
+    if (!grid_reduce_fp64(cta_vals, P, ws, total)) return;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e - i * n;
+        double v = 0.0;
+        if (i != j) v = total[i < j ? pair_index(i, j, n) : pair_index(j, i, n)];
+        if (accumulate) v += dist[e];
+        dist[e] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) svgd_bandwidth_kernel(const double* __restrict__ dist, int n, BandwidthParams bp) {
+    __shared__ double sd[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    __shared__ double sk[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    bandwidth_device(dist, n, bp, sd, sk);
+}
+
+__global__ void __launch_bounds__(256)
+svgd_apply_scalar_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ out,
+                         const float* __restrict__ K, const float* __restrict__ A, int n, int64_t D, int64_t ldx,
+                         int64_t ldg, int64_t ldo) {
+    __shared__ float sK[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    __shared__ float sA[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        sK[e] = K[e];
+        sA[e] = A[e];
+    }
+    __syncthreads();
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < D;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float xs[BDE_MAX_PARTICLES], gs[BDE_MAX_PARTICLES];
+        for (int j = 0; j < n; ++j) {
+            xs[j] = __ldg(X + j * ldx + c);
+            gs[j] = __ldg(G + j * ldg + c);
+        }
+        for (int i = 0; i < n; ++i) {
+            float s = 0.0f;
+            for (int j = 0; j < n; ++j) {
+                s = fmaf(sK[i * n + j], gs[j], s);
+                s = fmaf(sA[i * n + j], xs[j], s);
+            }
+            out[i * ldo + c] = s;
+        }
+    }
+}
+
+// particle counts with a register-resident fast path (explicitly instantiated in svgd_inst_*.cu);
+// any other n <= BDE_MAX_PARTICLES runs the generic runtime-n kernels.
+#define BDE_FOR_EACH_N(X_) X_(2) X_(3) X_(4) X_(5) X_(6) X_(7) X_(8) X_(9) X_(10) X_(11) X_(12) X_(16) X_(20)
+
+#define X_(N_)                                                                                                     \
+    extern template int launch_pairdist<N_>(const float*, int64_t, int64_t, double*, int, void*, int,              \
+                                            const BandwidthParams&, cudaStream_t);                                 \
+    extern template int launch_apply<N_>(const float*, const float*, float*, const float*, const float*, int64_t, \
+                                         int64_t, int64_t, int64_t, cudaStream_t);
+BDE_FOR_EACH_N(X_)
+#undef X_
+
+static bool has_fast_path(int n) {
+    switch (n) {
+#define X_(N_) case N_:
+        BDE_FOR_EACH_N(X_)
+#undef X_
+        return true;
+        default:
+            return false;
+    }
+}
+
+static bool overlaps(const void* a, size_t abytes, const void* b, size_t bbytes) {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(a), b0 = reinterpret_cast<uintptr_t>(b);
+    return a0 < b0 + bbytes && b0 < a0 + abytes;
+}
+
+int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, int accumulate, void* ws,
+                  size_t ws_bytes, int fuse, const BandwidthParams& bp, cudaStream_t st) {
+    if (!X || !dist || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ld < D) return BDE_ERR_INVALID_ARG;
+    size_t need = 0;
+    bde_svgd_workspace_bytes(n, &need);
+    if (!ws || ws_bytes < need) return BDE_ERR_WORKSPACE;
+    if (n == 1) {
+        if (!accumulate) BDE_RETURN_IF_CUDA(cudaMemsetAsync(dist, 0, sizeof(double), st));
+        if (fuse) {
+            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp);
+            BDE_CHECK_LAUNCH();
+        }
+        return BDE_OK;
+    }
+    const bool vec_ok = aligned16(X) && (ld % 4 == 0);
+    if (!vec_ok || !has_fast_path(n)) {
+        const int P = pair_count(n);
+        int64_t want = (D + 255) / 256;
+        const int64_t cap = static_cast<int64_t>(sm_count_cached()) * 4;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        svgd_pairdist_scalar_kernel<<<static_cast<unsigned>(want), 256, 2 * P * sizeof(double), st>>>(X, n, D, ld, dist,
+                                                                                                  accumulate, ws);
+        BDE_CHECK_LAUNCH();
+        if (fuse) {
+            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp);
+            BDE_CHECK_LAUNCH();
+        }
+        return BDE_OK;
+    }
+    switch (n) {
+#define X_(N_) \
+    case N_:   \
+        return launch_pairdist<N_>(X, D, ld, dist, accumulate, ws, fuse, bp, st);
+        BDE_FOR_EACH_N(X_)
+#undef X_
+        default:
+            return BDE_ERR_UNSUPPORTED_N;
+    }
+}
+
+int apply_impl(const float* X, const float* G, float* out, const float* K, const float* A, int n, int64_t D,
+               int64_t ldx, int64_t ldg, int64_t ldo, cudaStream_t st) {
+    if (!X || !G || !out || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ldx < D || ldg < D || ldo < D)
+        return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const size_t span_x = sizeof(float) * (static_cast<size_t>(n - 1) * ldx + D);
+    const size_t span_g = sizeof(float) * (static_cast<size_t>(n - 1) * ldg + D);
+    const size_t span_o = sizeof(float) * (static_cast<size_t>(n - 1) * ldo + D);
+    if (overlaps(out, span_o, X, span_x) || overlaps(out, span_o, G, span_g)) return BDE_ERR_INVALID_ARG;
+    const bool vec_ok = aligned16(X) && aligned16(G) && aligned16(out) && (ldx % 4 == 0) && (ldg % 4 == 0) && (ldo % 4 == 0);
+    if (!vec_ok || !has_fast_path(n)) {
+        int64_t want = (D + 255) / 256;
+        const int64_t cap = static_cast<int64_t>(sm_count_cached()) * 4;
+        if (want > cap) want = cap;
+        svgd_apply_scalar_kernel<<<static_cast<unsigned>(want), 256, 0, st>>>(X, G, out, K, A, n, D, ldx, ldg, ldo);
+        BDE_CHECK_LAUNCH();
+        return BDE_OK;
+    }
+    switch (n) {
+#define X_(N_) \
+    case N_:   \
+        return launch_apply<N_>(X, G, out, K, A, D, ldx, ldg, ldo, st);
+            BDE_FOR_EACH_N(X_)
+#undef X_
+        default:
+            return BDE_ERR_UNSUPPORTED_N;
+    }
+}
+
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_svgd_workspace_bytes(int n, size_t* bytes) {
+    if (!bytes || n < 1 || n > BDE_MAX_PARTICLES) return BDE_ERR_INVALID_ARG;
+    const int P = pair_count(n) > 0 ? pair_count(n) : 1;
+    *bytes = grid_reduce_ws_bytes(kMaxCtasPairdist, P);
+    return BDE_OK;
+}
+
+extern "C" int bde_svgd_pairdist(const float* X, int n, int64_t D, int64_t ld, double* dist, int accumulate,
+                                 void* workspace, size_t workspace_bytes, bde_stream_t stream) {
+    BandwidthParams bp{};
+    return pairdist_impl(X, n, D, ld, dist, accumulate, workspace, workspace_bytes, 0, bp,
+                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bde_svgd_bandwidth(const double* dist, int n, double l2_reg, double kernel_grad_scale,
+                                  double dataset_size, double h_override, float* K, float* A, double* info,
+                                  int32_t* sel, bde_stream_t stream) {
+    if (!dist || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || !(dataset_size > 0.0)) return BDE_ERR_INVALID_ARG;
+    BandwidthParams bp{l2_reg, kernel_grad_scale, dataset_size, h_override, K, A, info, sel};
+    svgd_bandwidth_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, n, bp);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+extern "C" int bde_svgd_apply(const float* X, const float* G, float* out, const float* K, const float* A, int n,
+                              int64_t D, int64_t ld, bde_stream_t stream) {
+    return apply_impl(X, G, out, K, A, n, D, ld, ld, ld, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, int64_t ld, double l2_reg,
+                             double kernel_grad_scale, double dataset_size, double h_override, double* dist, float* K,
+                             float* A, double* info, int32_t* sel, void* workspace, size_t workspace_bytes,
+                             bde_stream_t stream) {
+    if (!K || !A || !(dataset_size > 0.0)) return BDE_ERR_INVALID_ARG;
+    BandwidthParams bp{l2_reg, kernel_grad_scale, dataset_size, h_override, K, A, info, sel};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = pairdist_impl(X, n, D, ld, dist, 0, workspace, workspace_bytes, 1, bp, st);
+    if (rc != BDE_OK) return rc;
+    return apply_impl(X, G, out, K, A, n, D, ld, ld, ld, st);
+}

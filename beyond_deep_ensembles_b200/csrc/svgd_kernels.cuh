@@ -1,0 +1,388 @@
+// svgd_kernels.cuh — SVGD posterior update on sm_100a (kernel templates).
+//
+//   K1  svgd_pairdist : one streaming pass over X[n, D]; all n(n-1)/2 squared pair
+//                       distances accumulated in packed-fp32 registers (FADD2/FFMA2),
+//                       flushed to fp64 per warp, combined over CTAs in fixed order.
+//   K1b svgd_bandwidth: n*n fp64 epilogue — median heuristic, RBF kernel K and the
+//                       fused coefficient matrix A.
+//   K2  svgd_apply    : out = K·G + A·X in one pass (FFMA2 with scalar-broadcast
+//                       coefficients from shared memory).
+//
+// Reference arithmetic: src/algos/svgd.py:14-32 (rbf) and :83-97 (step).
+#pragma once
+#include "common.cuh"
+#include "svgd_internal.h"
+
+namespace bde {
+
+constexpr int kPairTarget = 48;    // pair accumulators (x2 registers) per thread
+constexpr int kFlushIters = 128;   // fp32 -> fp64 flush period (columns*4 per thread)
+constexpr int kMaxCtasPairdist = 148 * 8 * 2;
+
+__host__ __device__ constexpr int pair_count(int n) { return n * (n - 1) / 2; }
+__host__ __device__ constexpr int pair_groups(int n) {
+    return pair_count(n) <= kPairTarget ? 1 : (pair_count(n) + kPairTarget - 1) / kPairTarget;
+}
+__host__ __device__ constexpr int pairs_per_group(int n) {
+    return pair_groups(n) == 0 ? 0 : (pair_count(n) + pair_groups(n) - 1) / pair_groups(n);
+}
+__host__ __device__ constexpr int pairdist_tpb(int n) {
+    // threads along columns; total CTA threads = tpb * groups
+    return pair_groups(n) <= 2 ? 128 : (pair_groups(n) <= 4 ? 64 : 32);
+}
+__host__ __device__ __forceinline__ constexpr int pair_index(int i, int j, int n) {  // i < j
+    return i * (2 * n - i - 1) / 2 + (j - i - 1);
+}
+
+// ---------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------
+template <int N, int G>
+__device__ __forceinline__ void pair_accumulate(const V4 (&v)[N], f32x2 (&acc)[pairs_per_group(N) > 0 ? pairs_per_group(N) : 1]) {
+    constexpr int PG = pairs_per_group(N);
+    constexpr int LO = G * PG;
+    constexpr int HI = (LO + PG < pair_count(N)) ? LO + PG : pair_count(N);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < N; ++j) {
+            const int p = pair_index(i, j, N);
+            if (p >= LO && p < HI) {
+                const f32x2 d0 = sub2(v[i].lo, v[j].lo);
+                const f32x2 d1 = sub2(v[i].hi, v[j].hi);
+                acc[p - LO] = fma2(d0, d0, acc[p - LO]);
+                acc[p - LO] = fma2(d1, d1, acc[p - LO]);
+            }
+        }
+    }
+}
+
+// fp32 lane pairs -> warp sum -> this warp's fp64 accumulators (lane k%32 owns pair k)
+template <int PG>
+__device__ __forceinline__ void flush_pairs(f32x2 (&acc)[PG > 0 ? PG : 1], double* __restrict__ wacc, int lane) {
+#pragma unroll
+    for (int k = 0; k < PG; ++k) {
+        float lo, hi;
+        unpack2(acc[k], lo, hi);
+        const float s = warp_sum(lo + hi);
+        if (lane == (k & 31)) wacc[k] += static_cast<double>(s);
+        acc[k] = 0ull;
+    }
+}
+
+template <int N, int G>
+__device__ __forceinline__ void pairdist_body(const float* __restrict__ X, int64_t D, int64_t ld,
+                                              double* __restrict__ wacc /* this warp's PG doubles */) {
+    constexpr int PG = pairs_per_group(N);
+    constexpr int NG = pair_groups(N);
+    constexpr int TPB = pairdist_tpb(N);
+    f32x2 acc[PG > 0 ? PG : 1];
+#pragma unroll
+    for (int k = 0; k < PG; ++k) acc[k] = 0ull;
+    const int lane = threadIdx.x & 31;
+
+
+    const int64_t nquads = D >> 2;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * TPB;
+    int iter = 0;
+    // block-uniform trip count so that the warp shuffles in flush() stay convergent
+    for (int64_t q0 = static_cast<int64_t>(blockIdx.x) * TPB; q0 < nquads; q0 += stride) {
+        const int64_t q = q0 + threadIdx.x;
+        V4 v[N];
+        if (q < nquads) {
+            const float* p = X + 4 * q;
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = (NG > 1) ? ldg_cached_v4(p + i * ld) : ldg_stream_v4(p + i * ld);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+        }
+        pair_accumulate<N, G>(v, acc);
+        if (++iter == kFlushIters) {
+            flush_pairs<PG>(acc, wacc, lane);
+            iter = 0;
+        }
+    }
+    // ragged tail: columns 4*nquads .. D-1, one per thread of CTA 0
+    if (blockIdx.x == 0) {
+        V4 v[N];
+        const int64_t c = 4 * nquads + threadIdx.x;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            v[i].lo = (threadIdx.x < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+            v[i].hi = 0ull;
+        }
+        pair_accumulate<N, G>(v, acc);
+    }
+    flush_pairs<PG>(acc, wacc, lane);
+}
+
+template <int N, int G>
+__device__ __forceinline__ void group_dispatch(int g, const float* X, int64_t D, int64_t ld, double* wacc) {
+    if (g == G) {
+        pairdist_body<N, G>(X, D, ld, wacc);
+    } else {
+        if constexpr (G + 1 < pair_groups(N)) group_dispatch<N, G + 1>(g, X, D, ld, wacc);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------
+// K1b
+// ---------------------------------------------------------------------------------
+// Block-cooperative; sd/sk are n*n doubles of shared scratch.  Mirrors svgd.py:15-21:
+// d = (sqrt(sum))^2 as torch.cdist(p=2)**2 does, torch.quantile(d, 0.5) over all n*n
+// entries (stable order statistic + lerp), h = sqrt(0.5*med/ln(n+1)) + 1e-8,
+// K = exp(-d / (2 h^2)); then A = (l2/2 + c) K - c diag(rowsum K), c = s/(N h^2).
+__device__ __forceinline__ void bandwidth_device(const double* dist, int n, const BandwidthParams& bp, double* sd, double* sk) {
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    const int nn = n * n;
+    __shared__ double s_sel[2];
+    __shared__ int s_idx[2];
+    __shared__ double s_h;
+
+    for (int e = tid; e < nn; e += nthreads) {
+        const double r = sqrt(dist[e]);
+        sd[e] = r * r;
+    }
+    __syncthreads();
+    const int pos_lo = (nn - 1) / 2;
+    const int pos_hi = nn / 2;
+    for (int e = tid; e < nn; e += nthreads) {
+        const double de = sd[e];
+        int rank = 0;
+        for (int k = 0; k < nn; ++k) {
+            const double dk = sd[k];
+            rank += (dk < de || (dk == de && k < e)) ? 1 : 0;
+        }
+        const int i = e / n, j = e - i * n;
+        const int canon = i <= j ? e : j * n + i;
+        if (rank == pos_lo) {
+            s_sel[0] = de;
+            s_idx[0] = canon;
+        }
+        if (rank == pos_hi) {
+            s_sel[1] = de;
+            s_idx[1] = canon;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double a = s_sel[0], b = s_sel[1];
+        const double w = 0.5 * (nn - 1) - pos_lo;
+        // torch lerp: w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
+        const double med = (w < 0.5) ? a + w * (b - a) : b - (b - a) * (1.0 - w);
+        double h = sqrt(0.5 * med / log(static_cast<double>(n) + 1.0)) + 1e-8;
+        if (bp.h_override > 0.0) h = bp.h_override;
+        s_h = h;
+        if (bp.info) {
+            bp.info[0] = h;
+            bp.info[1] = med;
+            bp.info[2] = a;
+            bp.info[3] = b;
+        }
+        if (bp.sel) {
+            bp.sel[0] = s_idx[0];
+            bp.sel[1] = s_idx[1];
+        }
+    }
+    __syncthreads();
+    const double h = s_h;
+    const double inv2h2 = 1.0 / (2.0 * h * h);
+    for (int e = tid; e < nn; e += nthreads) sk[e] = exp(-sd[e] * inv2h2);
+    __syncthreads();
+    const double c = bp.kernel_grad_scale / (bp.dataset_size * h * h);
+    const double half_l2 = 0.5 * bp.l2_reg;
+    for (int e = tid; e < nn; e += nthreads) {
+        const int i = e / n, j = e - i * n;
+        const double kij = sk[e];
+        double a;
+        if (i != j) {
+            a = (half_l2 + c) * kij;
+        } else {
+            double off = 0.0;  // rowsum without the diagonal: (l2/2 + c) K_ii - c rowsum = l2/2 K_ii - c off
+            for (int m = 0; m < n; ++m)
+                if (m != i) off += sk[i * n + m];
+            a = half_l2 * kij - c * off;
+        }
+        bp.K[e] = static_cast<float>(kij);
+        bp.A[e] = static_cast<float>(a);
+    }
+}
+
+
+template <int N>
+__global__ void __launch_bounds__(pairdist_tpb(N) * pair_groups(N))
+svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double* __restrict__ dist, int accumulate,
+                     void* ws, int fuse_bandwidth, BandwidthParams bp) {
+    constexpr int P = pair_count(N);
+    constexpr int PG = pairs_per_group(N);
+    constexpr int NG = pair_groups(N);
+    constexpr int TPB = pairdist_tpb(N);
+    constexpr int WPG = TPB / 32;  // warps per group
+    __shared__ double wacc[NG * WPG][PG];
+    __shared__ double cta_vals[P];
+    __shared__ double total[P];
+    __shared__ double sd[N * N];
+    __shared__ double sk[N * N];
+
+    const int g = threadIdx.y;
+    const int warp_in_group = threadIdx.x >> 5;
+    const int tid = threadIdx.x + threadIdx.y * TPB;
+    for (int k = tid; k < NG * WPG * PG; k += TPB * NG) (&wacc[0][0])[k] = 0.0;
+    __syncthreads();
+
+    group_dispatch<N, 0>(g, X, D, ld, wacc[g * WPG + warp_in_group]);
+    __syncthreads();
+
+    for (int p = tid; p < P; p += TPB * NG) {
+        const int grp = p / PG, k = p - grp * PG;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WPG; ++w) s += wacc[grp * WPG + w][k];
+        cta_vals[p] = s;
+    }
+    __syncthreads();
+
+    if (!grid_reduce_fp64(cta_vals, P, ws, total)) return;
+
+    // last CTA: symmetric n*n matrix, zero diagonal
+    for (int e = tid; e < N * N; e += TPB * NG) {
+        const int i = e / N, j = e - i * N;
+        double v = 0.0;
+        if (i != j) v = total[i < j ? pair_index(i, j, N) : pair_index(j, i, N)];
+        if (accumulate) v += dist[e];
+        dist[e] = v;
+    }
+    if (fuse_bandwidth) {
+        __syncthreads();
+        bandwidth_device(dist, N, bp, sd, sk);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// K2
+// ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : 8; }
+
+template <int N>
+__global__ void __launch_bounds__(128)
+svgd_apply_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ out,
+                  const float* __restrict__ K, const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg,
+                  int64_t ldo) {
+    constexpr int NP = (N + 3) & ~3;
+    constexpr int JC = apply_row_chunk(N);
+    // transposed coefficients: sKT[j][i] = K[i][j] so that the i-loop reads contiguous words
+    __shared__ __align__(16) float sKT[N][NP];
+    __shared__ __align__(16) float sAT[N][NP];
+    for (int e = threadIdx.x; e < N * NP; e += blockDim.x) {
+        const int j = e / NP, i = e - j * NP;
+        sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
+        sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
+    }
+    __syncthreads();
+
+    const int64_t nquads = D >> 2;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+        f32x2 acc[N][2];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i][0] = acc[i][1] = 0ull;
+        const float* xp = X + 4 * q;
+        const float* gp = G + 4 * q;
+#pragma unroll
+        for (int jc = 0; jc < N; jc += JC) {
+            V4 x[JC], g[JC];
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) {
+                if (jc + jj < N) {
+                    g[jj] = ldg_stream_v4(gp + (jc + jj) * ldg);
+                    x[jj] = ldg_stream_v4(xp + (jc + jj) * ldx);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < JC; ++jj) {
+                if (jc + jj < N) {
+                    const int j = jc + jj;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const float kij = sKT[j][i];
+                        const float aij = sAT[j][i];
+                        acc[i][0] = fma2s(kij, g[jj].lo, acc[i][0]);
+                        acc[i][1] = fma2s(kij, g[jj].hi, acc[i][1]);
+                        acc[i][0] = fma2s(aij, x[jj].lo, acc[i][0]);
+                        acc[i][1] = fma2s(aij, x[jj].hi, acc[i][1]);
+                    }
+                }
+            }
+        }
+        float* op = out + 4 * q;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            V4 o;
+            o.lo = acc[i][0];
+            o.hi = acc[i][1];
+            stg_stream_v4(op + i * ldo, o);
+        }
+    }
+    // ragged tail columns
+    if (blockIdx.x == 0 && threadIdx.x < (D & 3)) {
+        const int64_t c = 4 * nquads + threadIdx.x;
+        for (int i = 0; i < N; ++i) {
+            float s = 0.0f;
+            for (int j = 0; j < N; ++j) {
+                s = fmaf(sKT[j][i], __ldg(G + j * ldg + c), s);
+                s = fmaf(sAT[j][i], __ldg(X + j * ldx + c), s);
+            }
+            out[i * ldo + c] = s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------
+template <int N>
+int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int accumulate, void* ws, int fuse,
+                    const BandwidthParams& bp, cudaStream_t st) {
+    constexpr int TPB = pairdist_tpb(N);
+    constexpr int NG = pair_groups(N);
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int v = 0;
+        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_pairdist_kernel<N>, TPB * NG, 0));
+        ctas_per_sm = v > 0 ? v : 1;
+    }
+    const int64_t nquads = D >> 2;
+    int64_t want = (nquads + TPB - 1) / TPB;
+    int64_t cap = static_cast<int64_t>(sm_count_cached()) * ctas_per_sm;
+    if (cap > kMaxCtasPairdist) cap = kMaxCtasPairdist;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    svgd_pairdist_kernel<N><<<dim3(static_cast<unsigned>(want)), dim3(TPB, NG), 0, st>>>(X, D, ld, dist, accumulate, ws,
+                                                                                      fuse, bp);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+template <int N>
+int launch_apply(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
+                 int64_t ldg, int64_t ldo, cudaStream_t st) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int v = 0;
+        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N>, 128, 0));
+        ctas_per_sm = v > 0 ? v : 1;
+    }
+    const int64_t nquads = D >> 2;
+    int64_t want = (nquads + 127) / 128;
+    const int64_t cap = static_cast<int64_t>(sm_count_cached()) * ctas_per_sm;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    svgd_apply_kernel<N><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+}  // namespace bde

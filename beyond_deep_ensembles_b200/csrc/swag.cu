@@ -1,0 +1,137 @@
+// swag.cu — SWAG running moments / deviation ring buffer / low-rank + diagonal sampling.
+// Reference arithmetic: src/algos/swag.py:91-114 and torch LowRankMultivariateNormal.rsample.
+// Operation order and rounding follow the reference op by op (explicit *_rn intrinsics, no
+// FMA contraction) so that the update matches eager fp32 PyTorch.
+#include "elementwise.cuh"
+
+namespace bde {
+
+// K3 ------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kEwThreads)
+swag_update_kernel(const float* __restrict__ theta, float* __restrict__ mean, float* __restrict__ sq,
+                   float* __restrict__ dev_row, int64_t D, float fu, float fu1) {
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 t = load_quad<VEC, true>(theta, b, D);
+        const float4 m = load_quad<VEC, false>(mean, b, D);
+        const float4 s = load_quad<VEC, false>(sq, b, D);
+        // swag.py:101  mean = (updates*mean + params) / (updates + 1)
+        auto upd_mean = [&](float mv, float tv) { return __fdiv_rn(__fadd_rn(__fmul_rn(fu, mv), tv), fu1); };
+        // swag.py:102  sq = (updates*sq + params**2) / (updates + 1)
+        auto upd_sq = [&](float sv, float tv) { return __fdiv_rn(__fadd_rn(__fmul_rn(fu, sv), __fmul_rn(tv, tv)), fu1); };
+        const float4 mn = BDE_LANES(upd_mean(m.x, t.x), upd_mean(m.y, t.y), upd_mean(m.z, t.z), upd_mean(m.w, t.w));
+        const float4 sn = BDE_LANES(upd_sq(s.x, t.x), upd_sq(s.y, t.y), upd_sq(s.z, t.z), upd_sq(s.w, t.w));
+        // swag.py:104  deviations[:, -1] = params - mean_new
+        const float4 dv = BDE_LANES(__fsub_rn(t.x, mn.x), __fsub_rn(t.y, mn.y), __fsub_rn(t.z, mn.z), __fsub_rn(t.w, mn.w));
+        store_quad<VEC>(mean, b, D, mn);
+        store_quad<VEC>(sq, b, D, sn);
+        store_quad<VEC>(dev_row, b, D, dv);
+    }
+}
+
+// K4 ------------------------------------------------------------------------------------
+constexpr int kMaxSwagRank = 256;
+
+template <bool VEC, int KU>
+__global__ void __launch_bounds__(kEwThreads)
+swag_sample_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
+                   int head, int64_t D, int64_t ld, const float* __restrict__ eps_k, const float* __restrict__ eps_d,
+                   uint64_t seed, uint64_t stream_id, int64_t quad0, float inv_norm_den, float* __restrict__ theta) {
+    // zc[k] = z[k] / sqrt(2(K-1)) for the LOGICAL column k (0 = oldest); rowoff[k] = physical row offset
+    __shared__ float zc[kMaxSwagRank];
+    __shared__ int64_t rowoff[kMaxSwagRank];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float z;
+        if (eps_k) {
+            z = eps_k[k];
+        } else {
+            const float4 z4 = philox_normal4(seed, stream_id ^ 0x5741ull, static_cast<uint64_t>(k >> 2));
+            z = (k & 3) == 0 ? z4.x : (k & 3) == 1 ? z4.y : (k & 3) == 2 ? z4.z : z4.w;
+        }
+        zc[k] = __fdiv_rn(z, inv_norm_den);  // cov_factor = deviations / sqrt(2(K-1)), swag.py:113
+        rowoff[k] = static_cast<int64_t>((head + k) % K) * ld;
+    }
+    __syncthreads();
+
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 m = load_quad<VEC, true>(mean, b, D);
+        const float4 s = load_quad<VEC, true>(sq, b, D);
+        float4 low = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k0 = 0; k0 < K; k0 += KU) {
+            float4 d[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u)
+                if (k0 + u < K) d[u] = load_quad<VEC, true>(dev + rowoff[k0 + u], b, D);
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                if (k0 + u < K) {
+                    const float z = zc[k0 + u];
+                    low.x = fmaf(d[u].x, z, low.x);
+                    low.y = fmaf(d[u].y, z, low.y);
+                    low.z = fmaf(d[u].z, z, low.z);
+                    low.w = fmaf(d[u].w, z, low.w);
+                }
+            }
+        }
+        float4 e;
+        if (eps_d) {
+            e = load_quad<VEC, true>(eps_d, b, D);
+        } else {
+            e = philox_normal4(seed, stream_id, static_cast<uint64_t>(quad0 + q));
+        }
+        // swag.py:112  diag = 0.5 * (relu(sq - mean**2) + 1e-6);  rsample: loc + W@eps_W + diag.sqrt()*eps_D
+        auto fin = [&](float mv, float sv, float lv, float ev) {
+            float v = __fsub_rn(sv, __fmul_rn(mv, mv));
+            v = fmaxf(v, 0.0f);
+            v = __fmul_rn(0.5f, __fadd_rn(v, 1e-6f));
+            return __fadd_rn(__fadd_rn(mv, lv), __fmul_rn(__fsqrt_rn(v), ev));
+        };
+        const float4 o = BDE_LANES(fin(m.x, s.x, low.x, e.x), fin(m.y, s.y, low.y, e.y), fin(m.z, s.z, low.z, e.z),
+                                   fin(m.w, s.w, low.w, e.w));
+        store_quad<VEC>(theta, b, D, o);
+    }
+}
+
+}  // namespace bde
+
+using namespace bde;
+
+extern "C" int bde_swag_update(const float* theta, float* mean, float* sq, float* dev_row, int64_t D, int64_t updates,
+                               bde_stream_t stream) {
+    if (!theta || !mean || !sq || !dev_row || D < 0 || updates < 1) return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const bool vec = aligned16(theta) && aligned16(mean) && aligned16(sq) && aligned16(dev_row);
+    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
+    const float fu = static_cast<float>(updates), fu1 = static_cast<float>(updates + 1);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec)
+        swag_update_kernel<true><<<g.blocks, g.threads, 0, st>>>(theta, mean, sq, dev_row, D, fu, fu1);
+    else
+        swag_update_kernel<false><<<g.blocks, g.threads, 0, st>>>(theta, mean, sq, dev_row, D, fu, fu1);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
+extern "C" int bde_swag_sample(const float* mean, const float* sq, const float* dev, int K, int head, int64_t D,
+                               int64_t ld, const float* eps_k, const float* eps_d, uint64_t seed, uint64_t stream_id,
+                               int64_t elem0, float* theta, bde_stream_t stream) {
+    if (!mean || !sq || !dev || !theta || K < 1 || K > kMaxSwagRank || head < 0 || head >= K || D < 0 || ld < D ||
+        elem0 < 0 || (elem0 & 3))
+        return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const bool vec = aligned16(mean) && aligned16(sq) && aligned16(dev) && aligned16(theta) && (ld % 4 == 0) &&
+                     (!eps_d || aligned16(eps_d));
+    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
+    const float den = static_cast<float>(sqrt(2.0 * (K - 1)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (vec)
+        swag_sample_kernel<true, 5><<<g.blocks, g.threads, 0, st>>>(mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
+                                                                    stream_id, elem0 >> 2, den, theta);
+    else
+        swag_sample_kernel<false, 5><<<g.blocks, g.threads, 0, st>>>(mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
+                                                                     stream_id, elem0 >> 2, den, theta);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}

@@ -1,0 +1,224 @@
+/*
+ * bde_b200.h — C-ABI of the B200-native posterior-update kernels.
+ *
+ * This is the drop-in boundary of the hot path inside the reference's
+ * BayesianOptimizer.step (Feuermagier/Beyond_Deep_Ensembles, src/algos).  The
+ * reference has no FFI for this path (it is inline eager PyTorch), so each entry
+ * point below cites the reference lines whose arithmetic it replaces.  The Python
+ * host classes in beyond_deep_ensembles_b200/ (same names and constructor
+ * signatures as the reference's optimizers) call these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - functions never allocate, never synchronise and never throw; the caller
+ *     passes workspaces (sizes from the *_workspace_bytes queries, zero-filled
+ *     once when allocated — kernels leave them zeroed again);
+ *   - return value: 0 = ok, >0 = a cudaError_t, <0 = one of BDE_ERR_*;
+ *   - matrices are row-major fp32, `ld` = row stride in elements;
+ *   - Philox4x32-10 noise is keyed by (seed, stream_id) and counted by the GLOBAL
+ *     element index (`elem0` + local index) so results do not depend on how the
+ *     parameter dimension is sharded over GPUs.  `elem0` must be a multiple of 4.
+ *     When an `eps` pointer is non-NULL the injected noise is used instead.
+ */
+#ifndef BDE_B200_H
+#define BDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDE_OK 0
+#define BDE_ERR_INVALID_ARG (-1)
+#define BDE_ERR_ALIGNMENT (-2)
+#define BDE_ERR_WORKSPACE (-3)
+#define BDE_ERR_UNSUPPORTED_N (-4)
+
+#define BDE_MAX_PARTICLES 32
+
+typedef void* bde_stream_t;
+
+/* ---- library ------------------------------------------------------------- */
+int bde_version(void);
+const char* bde_error_string(int code);
+/* number of SMs of the current device (grid sizing is done inside the library) */
+int bde_device_sm_count(int* sm_count);
+
+/* ---- SVGD (reference: src/algos/svgd.py) ---------------------------------- */
+
+/* Workspace for bde_svgd_pairdist / bde_kl_* reductions (bytes). */
+int bde_svgd_workspace_bytes(int n, size_t* bytes);
+
+/*
+ * K1: partial squared pairwise distances of the n particle rows over the local D
+ * columns: dist[i*n+j] (+)= sum_c (X[i,c]-X[j,c])^2, symmetric, zero diagonal, fp64.
+ * Replaces torch.cdist(particles, particles, p=2)**2, svgd.py:15 (direct
+ * differences, fp32 per-thread partials combined in fp64, deterministic order).
+ * accumulate != 0 adds into dist (used when the columns arrive in chunks).
+ * Under D-sharding the caller sum-all-reduces `dist` (n*n doubles) across ranks.
+ */
+int bde_svgd_pairdist(const float* X, int n, int64_t D, int64_t ld, double* dist,
+                      int accumulate, void* workspace, size_t workspace_bytes,
+                      bde_stream_t stream);
+
+/*
+ * K1b: median-heuristic bandwidth, RBF kernel matrix and the fused coefficient
+ * matrix.  Replaces svgd.py:17-21 (quantile over all n*n entries with linear
+ * interpolation, h = sqrt(0.5*median/ln(n+1)) + 1e-8, K = exp(-d/(2h^2))) and folds
+ * svgd.py:23,31,86,89 into A = (l2_reg/2 + c) K - c diag(rowsum K),
+ * c = kernel_grad_scale / (dataset_size h^2), so that the new gradient of
+ * particle i is  sum_j K_ij g_j + sum_j A_ij x_j.
+ * h_override > 0 replaces the median heuristic (svgd.py:19-20).
+ * Outputs: K, A fp32 [n*n]; info fp64 [4] = {h, median, d_lo, d_hi};
+ * sel int32 [2] = flat indices i*n+j (i<=j) of the two order statistics used.
+ */
+int bde_svgd_bandwidth(const double* dist, int n, double l2_reg, double kernel_grad_scale,
+                       double dataset_size, double h_override, float* K, float* A,
+                       double* info, int32_t* sel, bde_stream_t stream);
+
+/*
+ * K2: out[i,:] = sum_j K[i,j] G[j,:] + sum_j A[i,j] X[j,:]  (one pass, FP32 FFMA2).
+ * Replaces svgd.py:86-97 (prior term, K@(-G), grad_kernel, scatter of -phi).
+ * `out` must not overlap X or G.
+ */
+int bde_svgd_apply(const float* X, const float* G, float* out, const float* K, const float* A,
+                   int n, int64_t D, int64_t ld, bde_stream_t stream);
+
+/*
+ * Single-GPU convenience: K1 + K1b + K2 on one stream (no collective in between).
+ */
+int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, int64_t ld,
+                  double l2_reg, double kernel_grad_scale, double dataset_size,
+                  double h_override, double* dist, float* K, float* A, double* info,
+                  int32_t* sel, void* workspace, size_t workspace_bytes, bde_stream_t stream);
+
+/*
+ * Host-buffer entry (the end-to-end path): X_host/G_host/out_host are HOST arrays
+ * [n, D] with row stride ld_host (pinned memory gives full PCIe bandwidth).  The
+ * columns are streamed through the device in `chunk_cols`-wide pieces on internal
+ * copy/compute streams: H2D X chunk -> K1(accumulate) ... -> K1b -> per chunk:
+ * H2D G -> K2 -> D2H out.  dX/dG/dOut are caller-provided device staging buffers:
+ * dX [n, D] (X stays resident between the two phases), dG and dOut [2][n, chunk_cols].
+ * Blocks until out_host is complete.  info_host[4], sel_host[2] may be NULL.
+ */
+int bde_svgd_step_host(const float* X_host, const float* G_host, float* out_host, int n,
+                       int64_t D, int64_t ld_host, double l2_reg, double kernel_grad_scale,
+                       double dataset_size, double h_override, int64_t chunk_cols,
+                       float* dX, float* dG, float* dOut, double* dist, float* K, float* A,
+                       double* info, int32_t* sel, void* workspace, size_t workspace_bytes,
+                       double* info_host, int32_t* sel_host);
+
+/* ---- SWAG (reference: src/algos/swag.py) ---------------------------------- */
+
+/*
+ * K3: running moments + one deviation column, swag.py:98-104 with `updates` the
+ * value AFTER the increment at swag.py:98:
+ *   mean <- (updates*mean + theta)/(updates+1);  sq <- (updates*sq + theta^2)/(updates+1);
+ *   dev_row <- theta - mean_new.
+ * dev_row is the ring-buffer row that replaces the reference's roll(-1)+last-column
+ * write (the buffer is [K, D] row-major on device instead of [D, K] on the host).
+ */
+int bde_swag_update(const float* theta, float* mean, float* sq, float* dev_row, int64_t D,
+                    int64_t updates, bde_stream_t stream);
+
+/*
+ * K4: theta = mean + sum_k dev[(head+k)%K,:] * z[k]/sqrt(2(K-1))
+ *             + sqrt(0.5*(relu(sq-mean^2)+1e-6)) * eps,
+ * swag.py:112-114 + LowRankMultivariateNormal.rsample (draw order z then eps),
+ * swag.py:57.  `head` = physical row of the OLDEST column (= updates % K).
+ * eps_k: K device floats (the low-rank noise, identical on every rank) or NULL
+ * (Philox counter = k on stream_id^0x5741); eps_d: D device floats or NULL (Philox).
+ */
+int bde_swag_sample(const float* mean, const float* sq, const float* dev, int K, int head,
+                    int64_t D, int64_t ld, const float* eps_k, const float* eps_d,
+                    uint64_t seed, uint64_t stream_id, int64_t elem0, float* theta,
+                    bde_stream_t stream);
+
+/* ---- iVON (reference: src/algos/ivorn.py) --------------------------------- */
+
+/*
+ * K5: delta = eps / sqrt(N_eff*max(prec,1e-4)) (0 if deterministic); theta = mean+delta;
+ * delta_sum = first ? delta : delta_sum + delta.   ivorn.py:102-115.
+ */
+int bde_ivon_sample(const float* mean, const float* prec, float* delta_sum, float* theta,
+                    int64_t D, double n_eff, int first, int deterministic, const float* eps,
+                    uint64_t seed, uint64_t stream_id, int64_t elem0, bde_stream_t stream);
+
+/* K6: acc = first ? grad : acc + grad.   ivorn.py:120-127. */
+int bde_ivon_accumulate(float* acc, const float* grad, int64_t D, int first, bde_stream_t stream);
+
+/*
+ * K7: the update block ivorn.py:79-89 for one parameter group.  `step` is the value
+ * after the increment at ivorn.py:68.  mean uses the OLD precision.
+ */
+int bde_ivon_update(const float* acc_grad, const float* delta_sum, float* mean, float* momentum,
+                    float* prec, int64_t D, int mc_samples, int64_t step, double lr, double beta1,
+                    double beta2, double prior_prec, double n_eff, double tempering,
+                    double damping, bde_stream_t stream);
+
+/* ---- BBB / Rank-1 (reference: src/algos/bbb.py, util.py:151-186) ----------- */
+
+/* K8 fwd: w = mu + eps * softplus(rho).   util.py:170-171,181-183. */
+int bde_gauss_sample_fwd(const float* mu, const float* rho, float* w, int64_t P, const float* eps,
+                         uint64_t seed, uint64_t stream_id, int64_t elem0, bde_stream_t stream);
+
+/* K8 bwd: grad_rho = grad_w * eps * exp(rho)/(exp(rho)+1) (grad_mu aliases grad_w). */
+int bde_gauss_sample_bwd(const float* grad_w, const float* rho, float* grad_rho, int64_t P,
+                         const float* eps, uint64_t seed, uint64_t stream_id, int64_t elem0,
+                         bde_stream_t stream);
+
+/*
+ * K9: Gaussian-prior KL of N(mu, softplus(rho)^2) against N(prior_mu, prior_sigma^2),
+ * bbb.py:18-21 via util.py:173-174, summed in fp64 into *value (device double, may be
+ * NULL), and its analytic gradient times grad_scale (host) times *grad_scale_dev
+ * (device float, may be NULL) written (accumulate=0) or added (accumulate=1) to
+ * grad_mu / grad_rho (both may be NULL for value only).
+ */
+int bde_kl_gauss_value_and_grad(const float* mu, const float* rho, int64_t P, double prior_mu,
+                                double prior_sigma, double* value, float* grad_mu,
+                                float* grad_rho, double grad_scale, const float* grad_scale_dev,
+                                int accumulate, void* workspace, size_t workspace_bytes,
+                                bde_stream_t stream);
+
+/*
+ * K9b: scale-mixture prior, bbb.py:23-37: value = -sum logaddexp(ln pi + clamp(lnN(mu;0,s1),-23,0),
+ * ln(1-pi) + clamp(lnN(mu;0,s2),-23,0)); gradient w.r.t. mu only (rho does not enter).
+ */
+int bde_kl_mixture_value_and_grad(const float* mu, int64_t P, double pi, double sigma1,
+                                  double sigma2, double* value, float* grad_mu,
+                                  double grad_scale, const float* grad_scale_dev, int accumulate,
+                                  void* workspace, size_t workspace_bytes, bde_stream_t stream);
+
+/*
+ * K10: L2 term of the deterministic parameters, bbb.py:75-76:
+ * value = l2_scale/2 * sum theta^2 (fp64), grad (+)= l2_scale * theta * scale.
+ */
+int bde_l2_value_and_grad(const float* theta, int64_t D, double l2_scale, double* value,
+                          float* grad, double grad_scale, const float* grad_scale_dev,
+                          int accumulate, void* workspace, size_t workspace_bytes,
+                          bde_stream_t stream);
+
+/* ---- utilities ------------------------------------------------------------ */
+
+/* out = standard normals from the library's Philox stream (for tests/diagnostics). */
+int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint64_t stream_id, int64_t elem0,
+                      bde_stream_t stream);
+
+/*
+ * Multi-tensor gather/scatter between a list of scattered tensors and a flat arena
+ * row (replaces parameters_to_vector / the cat+stack at svgd.py:83-84 and the
+ * slice+clone scatter at svgd.py:92-97).  ptrs/offsets/sizes are DEVICE arrays of
+ * `count` entries (element offsets into flat).  mode 0: flat <- tensors (copy),
+ * 1: flat <- flat + tensors, 2: tensors <- flat.
+ */
+int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs, const int64_t* offsets,
+                          const int64_t* sizes, int count, int64_t total, int mode,
+                          bde_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDE_B200_H */
