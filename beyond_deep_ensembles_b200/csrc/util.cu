@@ -15,15 +15,25 @@ philox_normal_kernel(float* __restrict__ out, int64_t count, uint64_t seed, uint
     }
 }
 
-// Gather/scatter between `count` scattered tensors and one flat arena row.
+// Gather/scatter between scattered tensors and one flat arena row.
 // Replaces parameters_to_vector / cat+stack (svgd.py:83-84) and the per-parameter
-// slice+clone scatter (svgd.py:92-97).  One thread per 4 flat elements; the owning tensor is
-// found by binary search over the (ascending) flat offsets.
-__device__ __forceinline__ int find_tensor(const int64_t* __restrict__ offsets, int count, int64_t e) {
-    int lo = 0, hi = count - 1;
+// slice+clone scatter (svgd.py:92-97).  The table of up to kMtcChunk tensors travels in the
+// kernel parameters (no device-side table to upload); one thread per 4 flat elements, the
+// owning tensor is found by binary search over the ascending flat offsets.
+constexpr int kMtcChunk = 112;
+struct MtcTable {
+    uint64_t ptr[kMtcChunk];
+    int64_t off[kMtcChunk];
+    int64_t size[kMtcChunk];
+    int count;
+    int64_t begin, end;  // flat range covered by this chunk
+};
+
+__device__ __forceinline__ int find_tensor(const MtcTable& t, int64_t e) {
+    int lo = 0, hi = t.count - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (__ldg(offsets + mid) <= e)
+        if (t.off[mid] <= e)
             lo = mid;
         else
             hi = mid - 1;
@@ -32,16 +42,15 @@ __device__ __forceinline__ int find_tensor(const int64_t* __restrict__ offsets, 
 }
 
 __global__ void __launch_bounds__(kEwThreads)
-multi_tensor_copy_kernel(float* __restrict__ flat, const uint64_t* __restrict__ ptrs,
-                         const int64_t* __restrict__ offsets, const int64_t* __restrict__ sizes, int count,
-                         int64_t total, int mode) {
-    BDE_QUAD_LOOP(q, total) {
-        const int64_t e0 = q << 2;
-        const int t = find_tensor(offsets, count, e0);
-        const int64_t off = __ldg(offsets + t), sz = __ldg(sizes + t);
-        float* tp = reinterpret_cast<float*>(__ldg(ptrs + t));
+multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTable tab, int mode) {
+    const int64_t base = tab.begin & ~static_cast<int64_t>(3);
+    BDE_QUAD_LOOP(q, tab.end - base) {
+        const int64_t e0 = base + (q << 2);
+        const int t = find_tensor(tab, e0);
+        const int64_t off = tab.off[t], sz = tab.size[t];
+        float* tp = reinterpret_cast<float*>(tab.ptr[t]);
         const int64_t local = e0 - off;
-        if (local >= 0 && local + 4 <= sz && e0 + 4 <= total && ((reinterpret_cast<uintptr_t>(tp + local) & 15u) == 0) &&
+        if (local >= 0 && local + 4 <= sz && ((reinterpret_cast<uintptr_t>(tp + local) & 15u) == 0) &&
             ((reinterpret_cast<uintptr_t>(flat + e0) & 15u) == 0)) {
             if (mode == 2) {
                 stg_stream_f4(tp + local, ld_f4(flat + e0));
@@ -56,12 +65,11 @@ multi_tensor_copy_kernel(float* __restrict__ flat, const uint64_t* __restrict__ 
         } else {
             for (int k = 0; k < 4; ++k) {
                 const int64_t e = e0 + k;
-                if (e >= total) break;
-                const int tt = find_tensor(offsets, count, e);
-                const int64_t o2 = __ldg(offsets + tt), s2 = __ldg(sizes + tt);
-                const int64_t l2 = e - o2;
-                if (l2 < 0 || l2 >= s2) continue;  // padding between tensors
-                float* p2 = reinterpret_cast<float*>(__ldg(ptrs + tt));
+                if (e < tab.begin || e >= tab.end) continue;
+                const int tt = find_tensor(tab, e);
+                const int64_t l2 = e - tab.off[tt];
+                if (l2 < 0 || l2 >= tab.size[tt]) continue;  // padding between tensors
+                float* p2 = reinterpret_cast<float*>(tab.ptr[tt]);
                 if (mode == 2)
                     p2[l2] = flat[e];
                 else if (mode == 1)
@@ -116,14 +124,28 @@ extern "C" int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint6
     return BDE_OK;
 }
 
-extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs, const int64_t* offsets, const int64_t* sizes,
-                                     int count, int64_t total, int mode, bde_stream_t stream) {
-    if (!flat || !ptrs || !offsets || !sizes || count < 1 || total < 0 || mode < 0 || mode > 2)
+extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
+                                     const int64_t* sizes_host, int count, int mode, bde_stream_t stream) {
+    if (!flat || !ptrs_host || !offsets_host || !sizes_host || count < 1 || mode < 0 || mode > 2)
         return BDE_ERR_INVALID_ARG;
-    if (total == 0) return BDE_OK;
-    const EwGrid g = ew_grid(total, kEwThreads, kEwCtasPerSm);
-    multi_tensor_copy_kernel<<<g.blocks, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(flat, ptrs, offsets, sizes,
-                                                                                           count, total, mode);
-    BDE_CHECK_LAUNCH();
+    for (int i = 0; i < count; ++i) {
+        if (sizes_host[i] < 0 || offsets_host[i] < 0) return BDE_ERR_INVALID_ARG;
+        if (i > 0 && offsets_host[i] < offsets_host[i - 1] + sizes_host[i - 1]) return BDE_ERR_INVALID_ARG;
+    }
+    for (int c0 = 0; c0 < count; c0 += kMtcChunk) {
+        MtcTable tab;
+        tab.count = (count - c0 < kMtcChunk) ? count - c0 : kMtcChunk;
+        for (int i = 0; i < tab.count; ++i) {
+            tab.ptr[i] = ptrs_host[c0 + i];
+            tab.off[i] = offsets_host[c0 + i];
+            tab.size[i] = sizes_host[c0 + i];
+        }
+        tab.begin = tab.off[0];
+        tab.end = tab.off[tab.count - 1] + tab.size[tab.count - 1];
+        if (tab.end <= tab.begin) continue;
+        const EwGrid g = ew_grid(tab.end - (tab.begin & ~static_cast<int64_t>(3)), kEwThreads, kEwCtasPerSm);
+        multi_tensor_copy_kernel<<<g.blocks, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(flat, tab, mode);
+        BDE_CHECK_LAUNCH();
+    }
     return BDE_OK;
 }

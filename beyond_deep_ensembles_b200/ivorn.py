@@ -1,0 +1,167 @@
+"""Improved Variational Online Newton — drop-in for the reference's iVONOptimizer.
+
+Reference: src/algos/ivorn.py:8-127 (the reference spells the module "ivorn").  Per parameter
+group the state lives in flat HBM arenas (mean, momentum, precision, delta_sum, acc_grad and the
+sampled weights theta that the model parameters alias), so that a step is
+  mc_samples x [ K5 sample (1 launch) -> closure fwd/bwd -> K6 gather-accumulate (1 launch) ]
+  -> K7 update (1 launch)
+instead of ~30 eager ops per tensor.  State-dict keys and shapes match the reference
+(state[param]["mean" | "momentum" | "precision" | "delta" | "acc_grad"]).
+"""
+from __future__ import annotations
+
+import torch
+from torch.amp.grad_scaler import OptState
+
+from . import noise, ops
+from .algo import BayesianOptimizer
+from .layout import ParamLayout
+
+_ROWS = ("mean", "momentum", "precision", "delta", "acc_grad", "theta")
+
+
+class iVONOptimizer(BayesianOptimizer):
+    def __init__(self, params, lr, prior_prec, dataset_size, betas=(0.9, 0.999), damping=0.0, tempering=1.0,
+                 augmentation=1.0, mc_samples=5, deterministic=False):
+        defaults = {
+            "lr": lr,
+            "betas": betas,
+            "prior_prec": prior_prec,
+            "damping": damping,
+            "tempering": tempering,
+            "augmentation": augmentation,
+            "N": dataset_size,
+            "deterministic": deterministic,
+            "step": 0,
+        }
+        super().__init__(params, defaults)
+        ops.require_cuda(*self._params())
+
+        self._arenas = []  # one dict per param_group
+        for group in self.param_groups:
+            plist = group["params"]
+            L = ParamLayout(plist)
+            arena = L.new_arena(len(_ROWS), plist[0].device)
+            rows = {name: arena[i] for i, name in enumerate(_ROWS)}
+            views = {name: L.views(rows[name]) for name in _ROWS}
+            with torch.no_grad():
+                for k, param in enumerate(plist):
+                    views["mean"][k].copy_(param.detach())
+                    state = self.state[param]
+                    state["mean"] = views["mean"][k]
+                    state["momentum"] = views["momentum"][k]
+                    state["precision"] = views["precision"][k]
+                    state["delta"] = None
+                    state["acc_grad"] = None
+                # ivorn.py:35: precision starts at prior_prec / N (the padding too, so it stays finite)
+                rows["precision"].fill_(group["prior_prec"] / group["N"])
+                rows["theta"].copy_(rows["mean"])
+                for k, param in enumerate(plist):
+                    param.data = views["theta"][k]
+            self._arenas.append({"layout": L, "rows": rows, "views": views, "n_samples": 0})
+
+        assert mc_samples > 0
+        self.mc_samples = mc_samples
+
+    # ------------------------------------------------------------------ step
+    def step(self, forward_closure, backward_closure, grad_scaler=None):
+        self._reset_state()
+
+        acc_loss = None
+        for _ in range(self.mc_samples):
+            # READY so that GradScaler.unscale_ may be called once per MC sample (ivorn.py:47)
+            self._set_grad_scaler_state(grad_scaler, OptState.READY)
+
+            self.sample_parameters()
+            with torch.enable_grad():
+                self.zero_grad()
+                loss = forward_closure()
+                backward_closure(loss)
+
+            if acc_loss is None:
+                acc_loss = loss
+            else:
+                acc_loss += loss
+
+            if not self._prepare_and_check_grads(grad_scaler):
+                return None
+
+            self._store_gradients()
+        acc_loss /= self.mc_samples
+
+        with torch.no_grad():
+            for group, ar in zip(self.param_groups, self._arenas):
+                group["step"] += 1
+                beta1, beta2 = group["betas"]
+                r = ar["rows"]
+                ops.ivon_update(r["acc_grad"], r["delta"], r["mean"], r["momentum"], r["precision"],
+                                mc_samples=self.mc_samples, step=group["step"], lr=group["lr"], beta1=beta1,
+                                beta2=beta2, prior_prec=group["prior_prec"], n_eff=group["N"] * group["augmentation"],
+                                tempering=group["tempering"], damping=group["damping"])
+
+        self._set_grad_scaler_state(grad_scaler, OptState.STEPPED)
+        return acc_loss
+
+    def _reset_state(self):
+        for group, ar in zip(self.param_groups, self._arenas):
+            ar["n_samples"] = 0
+            ar["n_grads"] = 0
+            for param in group["params"]:
+                state = self.state[param]
+                state["delta"] = None
+                state["acc_grad"] = None
+
+    def sample_parameters(self):
+        """theta = mean + eps / sqrt(N max(prec, 1e-4)); delta_sum (+)= delta (ivorn.py:102-115)."""
+        for group, ar in zip(self.param_groups, self._arenas):
+            L, r, v = ar["layout"], ar["rows"], ar["views"]
+            first = ar["n_samples"] == 0
+            eps = None
+            if not group["deterministic"]:
+                eps = noise.draw("ivon", L.logical_size, r["mean"].device)
+                if eps is not None:
+                    eps = L.from_logical(eps)
+            ops.ivon_sample(r["mean"], r["precision"], r["delta"], r["theta"], n_eff=group["N"] * group["augmentation"],
+                            first=first, deterministic=bool(group["deterministic"]), eps=eps, seed=noise.seed(),
+                            stream_id=noise.next_stream_id())
+            ar["n_samples"] += 1
+            plist = group["params"]
+            if first or plist[0].data_ptr() != v["theta"][0].data_ptr():
+                for k, param in enumerate(plist):
+                    param.data = v["theta"][k]
+                    self.state[param]["delta"] = v["delta"][k]
+
+    def get_base_optimizer(self):
+        return self
+
+    def _store_gradients(self):
+        """acc_grad (+)= grad, gathered straight from the scattered .grad tensors (ivorn.py:120-127)."""
+        for group, ar in zip(self.param_groups, self._arenas):
+            L, r, v = ar["layout"], ar["rows"], ar["views"]
+            grads = []
+            for param in group["params"]:
+                if param.grad is None:
+                    raise TypeError("iVON needs a gradient for every parameter after backward_closure")
+                grads.append(param.grad if param.grad.is_contiguous() else param.grad.contiguous())
+            first = ar.get("n_grads", 0) == 0
+            ops.multi_tensor_copy(r["acc_grad"], grads, L.offsets, mode=0 if first else 1)
+            ar["n_grads"] = ar.get("n_grads", 0) + 1
+            if first:
+                for k, param in enumerate(group["params"]):
+                    self.state[param]["acc_grad"] = v["acc_grad"][k]
+
+    # ------------------------------------------------------------------ checkpoints
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            for group, ar in zip(self.param_groups, self._arenas):
+                v = ar["views"]
+                for k, param in enumerate(group["params"]):
+                    state = self.state[param]
+                    for name in ("mean", "momentum", "precision", "delta", "acc_grad"):
+                        loaded = state.get(name)
+                        if loaded is None:
+                            continue
+                        if loaded.data_ptr() != v[name][k].data_ptr():
+                            v[name][k].copy_(loaded)
+                        state[name] = v[name][k]

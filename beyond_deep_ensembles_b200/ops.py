@@ -1,0 +1,290 @@
+"""Tensor-level wrappers over the C-ABI (include/bde_b200.h).
+
+Every function validates dtype / device / strides, extracts raw device pointers and the
+current CUDA stream, and calls the library through ctypes.  No arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+_VALUE_WS_BYTES = 16 + 8 * 148 * 8 * 2  # grid_reduce workspace of the value kernels (elementwise.cuh)
+
+
+def require_cuda(*tensors: torch.Tensor) -> None:
+    """The product path is CUDA-only; anything else is an error, never a fallback."""
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.BdeError("beyond_deep_ensembles_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def _rows(t: torch.Tensor):
+    """(n, D, ld) of a row-major 2-D fp32 matrix whose rows are contiguous."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError("expected a 2-D tensor with contiguous rows")
+    n, D = t.shape
+    ld = t.stride(0) if n > 1 else max(D, 1)
+    return n, D, ld
+
+
+def _vec(t: torch.Tensor | None):
+    if t is not None and (t.dim() != 1 or (t.numel() > 1 and t.stride(0) != 1)):
+        raise ValueError("expected a contiguous 1-D tensor")
+    return t
+
+
+def _s(t: torch.Tensor) -> int:
+    return _lib.stream_ptr(t.device)
+
+
+def zeros_bytes(nbytes: int, device) -> torch.Tensor:
+    return torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# SVGD
+# --------------------------------------------------------------------------------------
+@dataclass
+class SvgdScratch:
+    """Per-(device, n) scratch of the SVGD kernels: all small and allocated once."""
+    n: int
+    dist: torch.Tensor   # [n, n] fp64
+    K: torch.Tensor      # [n, n] fp32
+    A: torch.Tensor      # [n, n] fp32
+    info: torch.Tensor   # [4] fp64: h, median, d_lo, d_hi
+    sel: torch.Tensor    # [2] int32
+    ws: torch.Tensor     # reduction workspace (zero-filled once)
+
+    @staticmethod
+    def allocate(n: int, device) -> "SvgdScratch":
+        nbytes = C.c_size_t(0)
+        _lib.check(_lib.get().bde_svgd_workspace_bytes(n, C.byref(nbytes)), "bde_svgd_workspace_bytes")
+        return SvgdScratch(
+            n=n,
+            dist=torch.zeros((n, n), dtype=torch.float64, device=device),
+            K=torch.zeros((n, n), dtype=torch.float32, device=device),
+            A=torch.zeros((n, n), dtype=torch.float32, device=device),
+            info=torch.zeros(4, dtype=torch.float64, device=device),
+            sel=torch.zeros(2, dtype=torch.int32, device=device),
+            ws=zeros_bytes(nbytes.value, device),
+        )
+
+    @property
+    def ws_bytes(self) -> int:
+        return self.ws.numel() * 8
+
+
+def svgd_pairdist(X: torch.Tensor, sc: SvgdScratch, accumulate: bool = False) -> torch.Tensor:
+    """K1: sc.dist (+)= squared pair distances over X's columns (svgd.py:15)."""
+    require_cuda(X)
+    _lib.require_f32(X)
+    n, D, ld = _rows(X)
+    assert n == sc.n
+    _lib.call("bde_svgd_pairdist", X.data_ptr(), n, D, ld, sc.dist.data_ptr(), int(accumulate), sc.ws.data_ptr(),
+              sc.ws_bytes, _s(X))
+    return sc.dist
+
+
+def svgd_bandwidth(sc: SvgdScratch, l2_reg: float, kernel_grad_scale: float, dataset_size: float,
+                   h_override: float = 0.0) -> None:
+    """K1b: median heuristic, K and A from sc.dist (svgd.py:17-31,86,89)."""
+    require_cuda(sc.dist)
+    _lib.call("bde_svgd_bandwidth", sc.dist.data_ptr(), sc.n, float(l2_reg), float(kernel_grad_scale),
+              float(dataset_size), float(h_override or 0.0), sc.K.data_ptr(), sc.A.data_ptr(), sc.info.data_ptr(),
+              sc.sel.data_ptr(), _s(sc.dist))
+
+
+def svgd_apply(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScratch) -> torch.Tensor:
+    """K2: out = K G + A X (svgd.py:86-97)."""
+    require_cuda(X, G, out)
+    _lib.require_f32(X, G, out)
+    n, D, ld = _rows(X)
+    if _rows(G) != (n, D, ld) or _rows(out) != (n, D, ld):
+        raise ValueError("X, G and out must share shape and row stride")
+    _lib.call("bde_svgd_apply", X.data_ptr(), G.data_ptr(), out.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(), n, D, ld,
+              _s(X))
+    return out
+
+
+def svgd_step(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScratch, l2_reg: float,
+              kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0) -> torch.Tensor:
+    """Single-GPU K1 + K1b + K2 (two launches)."""
+    require_cuda(X, G, out)
+    _lib.require_f32(X, G, out)
+    n, D, ld = _rows(X)
+    if _rows(G) != (n, D, ld) or _rows(out) != (n, D, ld):
+        raise ValueError("X, G and out must share shape and row stride")
+    _lib.call("bde_svgd_step", X.data_ptr(), G.data_ptr(), out.data_ptr(), n, D, ld, float(l2_reg),
+              float(kernel_grad_scale), float(dataset_size), float(h_override or 0.0), sc.dist.data_ptr(),
+              sc.K.data_ptr(), sc.A.data_ptr(), sc.info.data_ptr(), sc.sel.data_ptr(), sc.ws.data_ptr(), sc.ws_bytes,
+              _s(X))
+    _lib.launch_count += 1  # K1(+K1b fused) and K2
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# SWAG
+# --------------------------------------------------------------------------------------
+def swag_update(theta, mean, sq, dev_row, updates: int) -> None:
+    """K3 (swag.py:98-104); `updates` is the count after the increment."""
+    require_cuda(theta, mean, sq, dev_row)
+    _lib.require_f32(theta, mean, sq, dev_row)
+    D = _vec(theta).numel()
+    assert _vec(mean).numel() == D and _vec(sq).numel() == D and _vec(dev_row).numel() == D
+    _lib.call("bde_swag_update", theta.data_ptr(), mean.data_ptr(), sq.data_ptr(), dev_row.data_ptr(), D, int(updates),
+              _s(theta))
+
+
+def swag_sample(mean, sq, dev, head: int, theta, *, eps_k=None, eps_d=None, seed: int = 0, stream_id: int = 0,
+                elem0: int = 0) -> None:
+    """K4 (swag.py:53-58,107-114).  dev: [K, ld] ring buffer, head = physical row of the oldest column."""
+    require_cuda(mean, sq, dev, theta, eps_k, eps_d)
+    _lib.require_f32(mean, sq, dev, theta, eps_k, eps_d)
+    D = _vec(mean).numel()
+    K, Dd, ld = _rows(dev)
+    assert Dd == D and _vec(sq).numel() == D and _vec(theta).numel() == D
+    if eps_k is not None:
+        assert _vec(eps_k).numel() == K
+    if eps_d is not None:
+        assert _vec(eps_d).numel() == D
+    _lib.call("bde_swag_sample", mean.data_ptr(), sq.data_ptr(), dev.data_ptr(), K, int(head), D, ld, _lib.ptr(eps_k),
+              _lib.ptr(eps_d), int(seed), int(stream_id), int(elem0), theta.data_ptr(), _s(mean))
+
+
+# --------------------------------------------------------------------------------------
+# iVON
+# --------------------------------------------------------------------------------------
+def ivon_sample(mean, prec, delta_sum, theta, *, n_eff: float, first: bool, deterministic: bool = False, eps=None,
+                seed: int = 0, stream_id: int = 0, elem0: int = 0) -> None:
+    """K5 (ivorn.py:102-115)."""
+    require_cuda(mean, prec, delta_sum, theta, eps)
+    _lib.require_f32(mean, prec, delta_sum, theta, eps)
+    D = _vec(mean).numel()
+    assert _vec(prec).numel() == D and _vec(delta_sum).numel() == D and _vec(theta).numel() == D
+    _lib.call("bde_ivon_sample", mean.data_ptr(), prec.data_ptr(), delta_sum.data_ptr(), theta.data_ptr(), D,
+              float(n_eff), int(first), int(deterministic), _lib.ptr(_vec(eps)), int(seed), int(stream_id), int(elem0),
+              _s(mean))
+
+
+def ivon_accumulate(acc, grad, first: bool) -> None:
+    """K6 (ivorn.py:120-127)."""
+    require_cuda(acc, grad)
+    _lib.require_f32(acc, grad)
+    D = _vec(acc).numel()
+    assert _vec(grad).numel() == D
+    _lib.call("bde_ivon_accumulate", acc.data_ptr(), grad.data_ptr(), D, int(first), _s(acc))
+
+
+def ivon_update(acc_grad, delta_sum, mean, momentum, prec, *, mc_samples: int, step: int, lr: float, beta1: float,
+                beta2: float, prior_prec: float, n_eff: float, tempering: float, damping: float) -> None:
+    """K7 (ivorn.py:66-89)."""
+    require_cuda(acc_grad, delta_sum, mean, momentum, prec)
+    _lib.require_f32(acc_grad, delta_sum, mean, momentum, prec)
+    D = _vec(mean).numel()
+    for t in (acc_grad, delta_sum, momentum, prec):
+        assert _vec(t).numel() == D
+    _lib.call("bde_ivon_update", acc_grad.data_ptr(), delta_sum.data_ptr(), mean.data_ptr(), momentum.data_ptr(),
+              prec.data_ptr(), D, int(mc_samples), int(step), float(lr), float(beta1), float(beta2), float(prior_prec),
+              float(n_eff), float(tempering), float(damping), _s(mean))
+
+
+# --------------------------------------------------------------------------------------
+# BBB / Rank-1
+# --------------------------------------------------------------------------------------
+def gauss_sample_fwd(mu, rho, w, *, eps=None, seed: int = 0, stream_id: int = 0, elem0: int = 0) -> None:
+    """K8 forward (util.py:170-171)."""
+    require_cuda(mu, rho, w, eps)
+    _lib.require_f32(mu, rho, w, eps)
+    P = mu.numel()
+    assert rho.numel() == P and w.numel() == P and mu.is_contiguous() and rho.is_contiguous() and w.is_contiguous()
+    _lib.call("bde_gauss_sample_fwd", mu.data_ptr(), rho.data_ptr(), w.data_ptr(), P, _lib.ptr(eps), int(seed),
+              int(stream_id), int(elem0), _s(mu))
+
+
+def gauss_sample_bwd(grad_w, rho, grad_rho, *, eps=None, seed: int = 0, stream_id: int = 0, elem0: int = 0) -> None:
+    """K8 backward: grad_rho (grad_mu aliases grad_w)."""
+    require_cuda(grad_w, rho, grad_rho, eps)
+    _lib.require_f32(grad_w, rho, grad_rho, eps)
+    P = rho.numel()
+    assert grad_w.numel() == P and grad_rho.numel() == P and grad_w.is_contiguous() and rho.is_contiguous()
+    _lib.call("bde_gauss_sample_bwd", grad_w.data_ptr(), rho.data_ptr(), grad_rho.data_ptr(), P, _lib.ptr(eps),
+              int(seed), int(stream_id), int(elem0), _s(rho))
+
+
+def value_workspace(device) -> torch.Tensor:
+    return zeros_bytes(_VALUE_WS_BYTES, device)
+
+
+def kl_gauss(mu, rho, prior_mu: float, prior_sigma: float, *, value=None, grad_mu=None, grad_rho=None,
+             grad_scale: float = 1.0, grad_scale_dev=None, accumulate: bool = False, ws=None) -> None:
+    """K9 (bbb.py:18-21): value (fp64 device scalar) and/or analytic gradient."""
+    require_cuda(mu, rho, value, grad_mu, grad_rho, grad_scale_dev)
+    _lib.require_f32(mu, rho, grad_mu, grad_rho, grad_scale_dev)
+    P = mu.numel()
+    assert rho.numel() == P and mu.is_contiguous() and rho.is_contiguous()
+    if value is not None:
+        assert value.dtype == torch.float64 and ws is not None
+    _lib.call("bde_kl_gauss_value_and_grad", mu.data_ptr(), rho.data_ptr(), P, float(prior_mu), float(prior_sigma),
+              _lib.ptr(value), _lib.ptr(grad_mu), _lib.ptr(grad_rho), float(grad_scale), _lib.ptr(grad_scale_dev),
+              int(accumulate), _lib.ptr(ws), 0 if ws is None else ws.numel() * 8, _s(mu))
+
+
+def kl_mixture(mu, pi: float, sigma1: float, sigma2: float, *, value=None, grad_mu=None, grad_scale: float = 1.0,
+               grad_scale_dev=None, accumulate: bool = False, ws=None) -> None:
+    """K9b (bbb.py:23-37)."""
+    require_cuda(mu, value, grad_mu, grad_scale_dev)
+    _lib.require_f32(mu, grad_mu, grad_scale_dev)
+    P = mu.numel()
+    assert mu.is_contiguous()
+    if value is not None:
+        assert value.dtype == torch.float64 and ws is not None
+    _lib.call("bde_kl_mixture_value_and_grad", mu.data_ptr(), P, float(pi), float(sigma1), float(sigma2),
+              _lib.ptr(value), _lib.ptr(grad_mu), float(grad_scale), _lib.ptr(grad_scale_dev), int(accumulate),
+              _lib.ptr(ws), 0 if ws is None else ws.numel() * 8, _s(mu))
+
+
+def l2_term(theta, l2_scale: float, *, value=None, grad=None, grad_scale: float = 1.0, grad_scale_dev=None,
+            accumulate: bool = False, ws=None) -> None:
+    """K10 (bbb.py:75-76)."""
+    require_cuda(theta, value, grad, grad_scale_dev)
+    _lib.require_f32(theta, grad, grad_scale_dev)
+    D = theta.numel()
+    assert theta.is_contiguous()
+    if value is not None:
+        assert value.dtype == torch.float64 and ws is not None
+    _lib.call("bde_l2_value_and_grad", theta.data_ptr(), D, float(l2_scale), _lib.ptr(value), _lib.ptr(grad),
+              float(grad_scale), _lib.ptr(grad_scale_dev), int(accumulate), _lib.ptr(ws),
+              0 if ws is None else ws.numel() * 8, _s(theta))
+
+
+# --------------------------------------------------------------------------------------
+# utilities
+# --------------------------------------------------------------------------------------
+def philox_normal(out: torch.Tensor, seed: int, stream_id: int, elem0: int = 0) -> torch.Tensor:
+    require_cuda(out)
+    _lib.require_f32(out)
+    _lib.call("bde_philox_normal", out.data_ptr(), out.numel(), int(seed), int(stream_id), int(elem0), _s(out))
+    return out
+
+
+def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int) -> None:
+    """Gather (mode 0), gather-add (1) or scatter (2) between `tensors` and a flat arena row.
+
+    offsets: element offsets of each tensor inside flat_row (ascending)."""
+    require_cuda(flat_row, *tensors)
+    _lib.require_f32(flat_row, *tensors)
+    count = len(tensors)
+    if count == 0:
+        return
+    for t in tensors:
+        if not t.is_contiguous():
+            raise ValueError("multi_tensor_copy needs contiguous tensors")
+    ptrs = (C.c_uint64 * count)(*[t.data_ptr() for t in tensors])
+    offs = (C.c_int64 * count)(*[int(o) for o in offsets])
+    sizes = (C.c_int64 * count)(*[t.numel() for t in tensors])
+    _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(offs, C.c_void_p),
+              C.cast(sizes, C.c_void_p), count, int(mode), _s(flat_row))

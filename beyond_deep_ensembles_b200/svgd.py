@@ -1,0 +1,161 @@
+"""Stein Variational Gradient Descent — drop-in for the reference's SVGDOptimizer.
+
+Reference: src/algos/svgd.py:37-136.  Same constructor, same step()/sample_parameters()
+semantics (particle/parameter aliasing, one shared base optimizer stepped once per particle,
+persistent particle cursor), same state-dict keys.  The arithmetic of svgd.py:83-97 runs as
+two CUDA launches on flat [n, D] arenas: K1 (+K1b) and K2.
+"""
+from __future__ import annotations
+
+import torch
+from torch.amp.grad_scaler import OptState
+
+from . import dist as bdist
+from . import ops
+from .algo import BayesianOptimizer
+from .layout import ParamLayout
+
+
+def rbf(particles: torch.Tensor, h_override=None):
+    """RBF kernel with the median heuristic and its gradient (reference: svgd.py:14-32).
+
+    Returns (kernel [n, n], grad_kernel [n, D]) like the reference; computed by K1/K1b/K2
+    (grad_kernel = A X with l2_reg = 0, dataset_size = kernel_grad_scale = 1 and G = 0).
+    """
+    X = particles.detach().contiguous().float()
+    n = X.shape[0]
+    sc = ops.SvgdScratch.allocate(n, X.device)
+    ops.svgd_pairdist(X, sc)
+    # out = K*0 + A X with A = c K - c diag(rowsum K), c = 1/h^2  ->  -(grad_kernel)
+    ops.svgd_bandwidth(sc, 0.0, 1.0, 1.0, 0.0 if h_override is None else float(h_override))
+    out = torch.empty_like(X)
+    ops.svgd_apply(X, torch.zeros_like(X), out, sc)
+    return sc.K.clone(), -out
+
+
+class SVGDOptimizer(BayesianOptimizer):
+    """Stein Variational Gradient Descent over `particle_count` particles.
+
+    One param_group per tensor (svgd.py:50); `reset_params_closure` is called
+    particle_count - 1 times to initialise the particles (svgd.py:58-63);
+    `base_optimizer` must optimise the same parameters.
+    """
+
+    def __init__(self, params, reset_params_closure, base_optimizer, particle_count, dataset_size, l2_reg=0.0,
+                 kernel_grad_scale=1.0, process_group=None):
+        params = list(params)
+        super().__init__(map(lambda p: {"params": p}, params), {})
+        self.state["__base_optimizer"] = base_optimizer
+        self.state["__l2_reg"] = l2_reg
+        self.state["__dataset_size"] = dataset_size
+        self.state["__current_particle"] = 0
+        self.state["__particle_count"] = particle_count
+        self.state["__kernel_grad_scale"] = kernel_grad_scale
+
+        plist = list(self._params())
+        ops.require_cuda(*plist)
+        device = plist[0].device
+        self._layout = ParamLayout(plist)
+        n = particle_count
+        # HBM layout: particles X, their gradients G and the new gradients OUT as [n, size] arenas
+        self._X = self._layout.new_arena(n, device)
+        self._G = self._layout.new_arena(n, device)
+        self._out = self._layout.new_arena(n, device)
+        self._scratch = ops.SvgdScratch.allocate(n, device)
+        self._group = process_group
+        self._xviews = [self._layout.views(self._X[i]) for i in range(n)]
+        self._gviews = [self._layout.views(self._G[i]) for i in range(n)]
+        self._oviews = [self._layout.views(self._out[i]) for i in range(n)]
+
+        for particle_idx in range(n):
+            with torch.no_grad():
+                for param, view, gview in zip(plist, self._xviews[particle_idx], self._gviews[particle_idx]):
+                    view.copy_(param.detach())
+                    self.state[param][f"particle_{particle_idx}"] = view
+                    view.grad = gview  # the reference keeps particle gradients in particle.grad (svgd.py:133)
+            if particle_idx < n - 1:
+                reset_params_closure()
+
+    # ------------------------------------------------------------------ step
+    def step(self, forward_closure, backward_closure, grad_scaler=None):
+        n = self.state["__particle_count"]
+        base = self.state["__base_optimizer"]
+        plist = list(self._params())
+        total_loss = torch.tensor(0.0, device=self._params_device())
+        for particle_idx in range(n):
+            self._set_grad_scaler_state(grad_scaler, OptState.READY, base)
+            self._use_particle(particle_idx)
+            base.zero_grad()
+
+            loss = forward_closure()
+            total_loss += loss.detach()
+            backward_closure(loss)
+            if not self._prepare_and_check_grads(grad_scaler, base):
+                return None
+            self._store_grads(particle_idx, plist)
+
+        with torch.no_grad():
+            # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b -> K2
+            bdist.svgd_step_sharded(self._X, self._G, self._out, self._scratch, self.state["__l2_reg"],
+                                    self.state["__kernel_grad_scale"], self.state["__dataset_size"], 0.0, self._group)
+
+            # svgd.py:92-103: hand the new gradients to the ORIGINAL parameters, alias them to the
+            # particle and let the (shared) base optimizer step once per particle
+            for particle_idx in range(n):
+                for param, xview, oview in zip(plist, self._xviews[particle_idx], self._oviews[particle_idx]):
+                    param.grad = oview
+                    param.data = xview
+                if grad_scaler is not None:
+                    self._set_grad_scaler_state(grad_scaler, OptState.UNSCALED, base)
+                    grad_scaler.step(base)
+                else:
+                    base.step()
+
+        return total_loss / n
+
+    def sample_parameters(self):
+        """Cycles through the particles (svgd.py:107-112)."""
+        self._use_particle(self.state["__current_particle"])
+        self.state["__current_particle"] = (self.state["__current_particle"] + 1) % self.state["__particle_count"]
+
+    # ------------------------------------------------------------------ helpers
+    def _params_for_particle(self, particle_idx):
+        particle = f"particle_{particle_idx}"
+        for group in self.param_groups:
+            for param in group["params"]:
+                yield self.state[param][particle]
+
+    def _use_particle(self, particle_idx):
+        """No copy: the model parameters alias the particle's arena row (svgd.py:120-127)."""
+        for param, view in zip(self._params(), self._xviews[particle_idx]):
+            param.data = view
+
+    def _store_grads(self, particle_idx, plist):
+        """Gather this particle's gradients into row `particle_idx` of G (one launch)."""
+        grads = []
+        for p in plist:
+            if p.grad is None:
+                raise AttributeError("SVGD needs a gradient for every parameter after backward_closure")
+            grads.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
+        ops.multi_tensor_copy(self._G[particle_idx], grads, self._layout.offsets, mode=0)
+
+    def get_base_optimizer(self):
+        return self.state["__base_optimizer"]
+
+    # ------------------------------------------------------------------ checkpoints
+    def load_state_dict(self, state_dict):
+        """Accepts reference-written state dicts: per-parameter `particle_i` tensors are copied
+        into the arena rows and the state keeps pointing at the arena views."""
+        super().load_state_dict(state_dict)
+        n = self.state["__particle_count"]
+        if n != self._X.shape[0]:
+            raise ValueError("particle_count of the checkpoint differs from this optimizer")
+        with torch.no_grad():
+            for k, param in enumerate(self._params()):
+                for i in range(n):
+                    loaded = self.state[param][f"particle_{i}"]
+                    view = self._xviews[i][k]
+                    if loaded.data_ptr() != view.data_ptr():
+                        view.copy_(loaded)
+                    view.grad = self._gviews[i][k]
+                    self.state[param][f"particle_{i}"] = view

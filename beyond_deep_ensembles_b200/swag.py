@@ -1,0 +1,171 @@
+"""Stochastic Weight Averaging-Gaussian — drop-in for the reference's SwagOptimizer.
+
+Reference: src/algos/swag.py:10-114.  The reference keeps mean / second moment / [D, K]
+deviations on the HOST and moves the whole parameter vector D2H on every update (swag.py:100)
+and (K+2)*D floats H2D before sampling (swag.py:112-114).  Here everything lives in HBM:
+  theta  [size]     the training weights (the model's parameters are views of it),
+  mean, sq [size]   running moments,
+  dev    [K, size]  deviation ring buffer (row updates % K is overwritten next; no roll),
+  sample [size]     the last drawn weights (parameters alias it between sample and step).
+state_dict()/load_state_dict() convert to/from the reference layout (`__mean`, `__sq_weights`
+as [D] CPU tensors, `__deviations` as [D, K] CPU tensor in roll order).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import noise, ops
+from .algo import BayesianOptimizer
+from .layout import ParamLayout
+
+
+class SwagOptimizer(BayesianOptimizer):
+    def __init__(self, params, base_optimizer, update_interval, start_epoch=0, deviation_samples=30):
+        super().__init__(params, {})
+
+        self.start_epoch = start_epoch
+        self.update_interval = math.floor(update_interval)
+        self.deviation_samples = deviation_samples
+
+        plist = list(self._params())
+        ops.require_cuda(*plist)
+        device = plist[0].device
+        self._layout = ParamLayout(plist)
+        L = self._layout
+        self._theta = L.new_arena(1, device)[0]
+        self._sample = L.new_arena(1, device)[0]
+        self._mean = L.new_arena(1, device)[0]
+        self._sq = L.new_arena(1, device)[0]
+        self._dev = L.new_arena(deviation_samples, device)
+        self._tviews = L.views(self._theta)
+        self._sviews = L.views(self._sample)
+
+        with torch.no_grad():
+            for param, tview in zip(plist, self._tviews):
+                tview.copy_(param.detach())
+                param.data = tview  # re-home: base-optimizer updates now land in the arena
+                self.state[param]["original_param"] = tview
+            # swag.py:32-33: the initial weights count as sample 0 of both moments
+            self._mean.copy_(self._theta)
+            torch.mul(self._theta, self._theta, out=self._sq)
+
+        self.state["__base_optimizer"] = base_optimizer
+        self.state["__epoch"] = 0
+        self.state["__steps_since_swag_start"] = 0
+        self.state["__updates"] = 0
+        self.state["__params_dirty"] = False
+
+    # ------------------------------------------------------------------ step
+    def step(self, forward_closure, backward_closure, grad_scaler=None):
+        self._restore_original_params()
+        base = self.state["__base_optimizer"]
+        base.zero_grad()
+
+        loss = forward_closure()
+        backward_closure(loss)
+
+        if grad_scaler is not None:
+            grad_scaler.step(base)
+        else:
+            base.step()
+
+        self._swag_update()
+        return loss
+
+    def sample_parameters(self):
+        """theta~ = mean + Dev z / sqrt(2(K-1)) + sqrt(diag) eps (swag.py:53-58, 107-114), one launch."""
+        self._save_original_params()
+        self.state["__params_dirty"] = True
+        K, dev_ = self.deviation_samples, self._theta.device
+        eps_k = noise.draw("swag_k", K, dev_)
+        eps_d = noise.draw("swag_d", self._layout.logical_size, dev_)
+        if eps_d is not None:
+            eps_d = self._layout.from_logical(eps_d)
+        ops.swag_sample(self._mean, self._sq, self._dev, self.state["__updates"] % K, self._sample, eps_k=eps_k,
+                        eps_d=eps_d, seed=noise.seed(), stream_id=noise.next_stream_id())
+        for param, sview in zip(self._params(), self._sviews):
+            param.data = sview
+
+    def complete_epoch(self):
+        self.state["__epoch"] += 1
+
+    def get_base_optimizer(self):
+        return self.state["__base_optimizer"]
+
+    # ------------------------------------------------------------------ helpers
+    def _restore_original_params(self):
+        if self.state["__params_dirty"]:
+            for param, tview in zip(self._params(), self._tviews):
+                param.data = tview
+            self.state["__params_dirty"] = False
+
+    def _save_original_params(self):
+        if not self.state["__params_dirty"]:
+            self._sync_theta()
+
+    def _sync_theta(self):
+        """The training weights normally ARE the theta arena.  If a caller re-bound param.data
+        to other storage, gather it back (one launch) and re-home the parameters."""
+        plist = list(self._params())
+        if all(p.data_ptr() == v.data_ptr() for p, v in zip(plist, self._tviews)):
+            return
+        with torch.no_grad():
+            ops.multi_tensor_copy(self._theta, [p.detach().contiguous() for p in plist], self._layout.offsets, mode=0)
+            for param, tview in zip(plist, self._tviews):
+                param.data = tview
+
+    def _swag_update(self):
+        if self.state["__epoch"] >= self.start_epoch:
+            self.state["__steps_since_swag_start"] += 1
+
+            if self.state["__steps_since_swag_start"] % self.update_interval == 0:
+                assert not self.state["__params_dirty"]
+                with torch.no_grad():
+                    self._sync_theta()
+                    self.state["__updates"] += 1
+                    updates = self.state["__updates"]
+                    row = (updates - 1) % self.deviation_samples
+                    ops.swag_update(self._theta, self._mean, self._sq, self._dev[row], updates)
+
+    # ------------------------------------------------------------------ checkpoints
+    def _export_moments(self):
+        L = self._layout
+        K, u = self.deviation_samples, self.state["__updates"]
+        order = [(u % K + k) % K for k in range(K)]  # oldest ... newest = the reference's roll order
+        dev = L.to_logical(self._dev[order])          # [K, D]
+        return (L.to_logical(self._mean).cpu(), L.to_logical(self._sq).cpu(), dev.t().contiguous().cpu())
+
+    def state_dict(self):
+        mean, sq, dev = self._export_moments()
+        self.state["__mean"], self.state["__sq_weights"], self.state["__deviations"] = mean, sq, dev
+        try:
+            return super().state_dict()
+        finally:
+            for key in ("__mean", "__sq_weights", "__deviations"):
+                del self.state[key]
+
+    def load_state_dict(self, state_dict: dict):
+        super().load_state_dict(state_dict)
+        L, dev_ = self._layout, self._theta.device
+        mean = self.state.pop("__mean").to(dev_).float()
+        sq = self.state.pop("__sq_weights").to(dev_).float()
+        dev = self.state.pop("__deviations").to(dev_).float()  # [D, K], column K-1 newest
+        K, u = self.deviation_samples, self.state["__updates"]
+        if dev.shape != (L.logical_size, K):
+            raise ValueError("checkpoint deviations do not match this optimizer (D, deviation_samples)")
+        with torch.no_grad():
+            L.from_logical(mean, out=self._mean)
+            L.from_logical(sq, out=self._sq)
+            ring = L.from_logical(dev.t().contiguous())          # logical column k -> row (u + k) % K
+            for k in range(K):
+                self._dev[(u % K + k) % K].copy_(ring[k])
+            # parameters: keep whatever the model holds, re-homed into the arena
+            for param, tview in zip(self._params(), self._tviews):
+                loaded = self.state[param].get("original_param")
+                if self.state["__params_dirty"] and loaded is not None:
+                    tview.copy_(loaded)
+                self.state[param]["original_param"] = tview
+            if not self.state["__params_dirty"]:
+                self._sync_theta()

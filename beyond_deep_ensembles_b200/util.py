@@ -1,0 +1,189 @@
+"""Gaussian variational parameter with reparameterised sampling (reference: src/algos/util.py:151-186).
+
+`GaussianParameter.sample()` draws w = mean + eps * softplus(rho) with ONE fused kernel (Philox
+noise generated in-kernel) and a custom backward that regenerates eps instead of storing it:
+  d/dmean = dL/dw,   d/drho = dL/dw * eps * sigmoid(rho).
+`GaussianParameter.kl_divergence(prior)` evaluates the prior KL and its analytic gradient with
+the K9 kernels for the priors of bbb.py.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import noise, ops
+
+
+class _GaussSample(torch.autograd.Function):
+    """K8: w = mu + eps * softplus(rho)."""
+
+    @staticmethod
+    def forward(ctx, mean, rho):
+        mu_c, rho_c = mean.detach().contiguous(), rho.detach().contiguous()
+        w = torch.empty_like(mu_c)
+        eps = noise.draw("gauss", mu_c.numel(), mu_c.device)
+        seed, sid = noise.seed(), noise.next_stream_id()
+        ops.gauss_sample_fwd(mu_c, rho_c, w, eps=eps, seed=seed, stream_id=sid)
+        ctx.save_for_backward(rho_c, eps if eps is not None else torch.empty(0, device=mu_c.device))
+        ctx.philox = (seed, sid)
+        ctx.injected = eps is not None
+        return w.view_as(mean)
+
+    @staticmethod
+    def backward(ctx, grad_w):
+        rho_c, eps = ctx.saved_tensors
+        g = grad_w.contiguous()
+        grad_rho = torch.empty_like(rho_c)
+        seed, sid = ctx.philox
+        ops.gauss_sample_bwd(g, rho_c, grad_rho, eps=eps if ctx.injected else None, seed=seed, stream_id=sid)
+        return grad_w, grad_rho.view_as(grad_w)
+
+
+class _KLGauss(torch.autograd.Function):
+    """K9: KL(N(mu, softplus(rho)^2) || N(mu_p, sigma_p^2)) and its analytic gradient."""
+
+    @staticmethod
+    def forward(ctx, mean, rho, prior_mu, prior_sigma):
+        mu_c, rho_c = mean.detach().contiguous(), rho.detach().contiguous()
+        value = torch.zeros((), dtype=torch.float64, device=mu_c.device)
+        ops.kl_gauss(mu_c, rho_c, prior_mu, prior_sigma, value=value, ws=ops.value_workspace(mu_c.device))
+        ctx.save_for_backward(mu_c, rho_c)
+        ctx.prior = (prior_mu, prior_sigma)
+        return value.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        mu_c, rho_c = ctx.saved_tensors
+        gmu, grho = torch.empty_like(mu_c), torch.empty_like(rho_c)
+        scale = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        ops.kl_gauss(mu_c, rho_c, ctx.prior[0], ctx.prior[1], grad_mu=gmu, grad_rho=grho, grad_scale_dev=scale)
+        return gmu, grho, None, None
+
+
+class _KLMixture(torch.autograd.Function):
+    """K9b: scale-mixture prior of bbb.py:23-37 (gradient w.r.t. the mean only)."""
+
+    @staticmethod
+    def forward(ctx, mean, pi, sigma1, sigma2):
+        mu_c = mean.detach().contiguous()
+        value = torch.zeros((), dtype=torch.float64, device=mu_c.device)
+        ops.kl_mixture(mu_c, pi, sigma1, sigma2, value=value, ws=ops.value_workspace(mu_c.device))
+        ctx.save_for_backward(mu_c)
+        ctx.prior = (pi, sigma1, sigma2)
+        return value.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (mu_c,) = ctx.saved_tensors
+        gmu = torch.empty_like(mu_c)
+        scale = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        ops.kl_mixture(mu_c, *ctx.prior, grad_mu=gmu, grad_scale_dev=scale)
+        return gmu, None, None, None
+
+
+class _L2(torch.autograd.Function):
+    """K10: l2_scale/2 * ||theta||^2 (bbb.py:76)."""
+
+    @staticmethod
+    def forward(ctx, theta, l2_scale):
+        t = theta.detach().contiguous()
+        value = torch.zeros((), dtype=torch.float64, device=t.device)
+        ops.l2_term(t, l2_scale, value=value, ws=ops.value_workspace(t.device))
+        ctx.save_for_backward(t)
+        ctx.l2_scale = l2_scale
+        return value.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (t,) = ctx.saved_tensors
+        g = torch.empty_like(t)
+        scale = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        ops.l2_term(t, ctx.l2_scale, grad=g, grad_scale_dev=scale)
+        return g, None
+
+
+def l2_penalty(param: torch.Tensor, l2_scale: float) -> torch.Tensor:
+    return _L2.apply(param, float(l2_scale))
+
+
+def gaussian_sample(mean: torch.Tensor, rho: torch.Tensor) -> torch.Tensor:
+    return _GaussSample.apply(mean, rho)
+
+
+def gaussian_kl(mean: torch.Tensor, rho: torch.Tensor, prior) -> torch.Tensor:
+    """KL of one Gaussian parameter tensor against `prior` (GaussianPrior / MixturePrior of bbb.py).
+    Any other prior object is evaluated by its own kl_divergence(mean, std)."""
+    kind = getattr(prior, "_bde_kind", None)
+    if kind is None:  # the reference's own prior classes (after install()) carry plain attributes
+        cls = type(prior).__name__
+        if cls == "GaussianPrior" and all(isinstance(getattr(prior, a, None), (int, float)) for a in ("mu", "sigma")):
+            kind = "gauss"
+        elif cls == "MixturePrior" and hasattr(prior, "pi") and hasattr(prior, "sigma1"):
+            kind = "mixture"
+    if kind == "gauss":
+        return _KLGauss.apply(mean, rho, float(prior.mu), float(prior.sigma))
+    if kind == "mixture":
+        return _KLMixture.apply(mean, float(prior.pi), float(prior.sigma1), float(prior.sigma2))
+    return prior.kl_divergence(mean, F.softplus(rho))
+
+
+class GaussianParameter(nn.Module):
+    """Mean / rho pair with std = softplus(rho) (reference: util.py:151-183).
+
+    The mean parameter carries `get_parameter_kl` and `_is_gaussian_mean`, the rho parameter
+    `_is_gaussian_rho`, which is how BBBOptimizer tells them apart (bbb.py:73-75).
+    """
+
+    def __init__(self, size, device=None):
+        super().__init__()
+        self.overwrite_mean(torch.empty(size, device=device))
+        self.rho = nn.Parameter(torch.empty(size, device=device))
+        self.rho._is_gaussian_rho = True
+
+    def blundell_init(self, mean_std=0.1):
+        torch.nn.init.normal_(self.mean, 0, mean_std)
+        torch.nn.init.constant_(self.rho, -3)
+
+    def sign_init(self):
+        with torch.no_grad():
+            self.mean.data = (torch.rand_like(self.mean) > 0.5).float() * 2 - 1
+        torch.nn.init.constant_(self.rho, -3)
+
+    def sample(self) -> torch.Tensor:
+        return gaussian_sample(self.mean, self.rho)
+
+    def kl_divergence(self, prior):
+        return gaussian_kl(self.mean, self.rho, prior)
+
+    def overwrite_mean(self, mean):
+        self.mean = nn.Parameter(mean)
+        self.mean.get_parameter_kl = self.kl_divergence
+        self.mean._is_gaussian_mean = True
+
+    @property
+    def std(self) -> torch.Tensor:
+        return F.softplus(self.rho)
+
+
+def normal_like(tensor) -> torch.Tensor:
+    """Standard normal noise shaped like `tensor` from the library's Philox stream (util.py:185-186)."""
+    out = torch.empty_like(tensor, dtype=torch.float32).contiguous()
+    injected = noise.draw("gauss", out.numel(), out.device)
+    if injected is not None:
+        return injected.view_as(out).to(tensor.dtype)
+    ops.philox_normal(out.view(-1), noise.seed(), noise.next_stream_id())
+    return out.to(tensor.dtype)
+
+
+def non_mle_params(params):
+    return filter(lambda p: getattr(p, "use_mle_training", False) is False, params)
+
+
+def reset_model_params(model):
+    """Re-initialise every submodule that implements reset_parameters (util.py:191-202)."""
+    def weight_reset(m):
+        reset_parameters = getattr(m, "reset_parameters", None)
+        if callable(reset_parameters):
+            m.reset_parameters()
+    model.apply(weight_reset)

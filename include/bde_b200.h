@@ -210,13 +210,14 @@ int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint64_t stream_
 /*
  * Multi-tensor gather/scatter between a list of scattered tensors and a flat arena
  * row (replaces parameters_to_vector / the cat+stack at svgd.py:83-84 and the
- * slice+clone scatter at svgd.py:92-97).  ptrs/offsets/sizes are DEVICE arrays of
- * `count` entries (element offsets into flat).  mode 0: flat <- tensors (copy),
- * 1: flat <- flat + tensors, 2: tensors <- flat.
+ * slice+clone scatter at svgd.py:92-97).  ptrs_host / offsets_host / sizes_host are HOST
+ * arrays of `count` entries: device pointers of the tensors, their element offsets into
+ * `flat` (ascending, non-overlapping) and their element counts; the table is passed to
+ * the kernel by value.  mode 0: flat <- tensors, 1: flat <- flat + tensors,
+ * 2: tensors <- flat.
  */
-int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs, const int64_t* offsets,
-                          const int64_t* sizes, int count, int64_t total, int mode,
-                          bde_stream_t stream);
+int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
+                          const int64_t* sizes_host, int count, int mode, bde_stream_t stream);
 
 #ifdef __cplusplus
 }

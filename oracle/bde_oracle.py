@@ -227,16 +227,17 @@ def kl_gauss(mu, rho, prior_mu: float, prior_sigma: float, dtype=torch.float32):
 
 def kl_mixture(mu, pi: float, sigma1: float, sigma2: float, dtype=torch.float32):
     """bbb.py:23-37.  Returns (value, grad_mu) with the gradient taken by autograd."""
-    m = mu.to(dtype).clone().requires_grad_(True)
     pit = torch.tensor(pi, dtype=dtype)
 
     def logp(v, s):
         return -(v ** 2) / (2 * s ** 2) - math.log(s) - math.log(math.sqrt(2 * math.pi))
 
-    p1 = torch.log(pit) + torch.clamp(logp(m, sigma1), -23, 0)
-    p2 = torch.log(1 - pit) + torch.clamp(logp(m, sigma2), -23, 0)
-    val = -torch.logaddexp(p1, p2).to(torch.float64).sum()
-    (g,) = torch.autograd.grad(val, m)
+    with torch.enable_grad():  # may be called from inside an autograd.Function (grad mode off)
+        m = mu.detach().to(dtype).clone().requires_grad_(True)
+        p1 = torch.log(pit) + torch.clamp(logp(m, sigma1), -23, 0)
+        p2 = torch.log(1 - pit) + torch.clamp(logp(m, sigma2), -23, 0)
+        val = -torch.logaddexp(p1, p2).to(torch.float64).sum()
+        (g,) = torch.autograd.grad(val, m)
     return val.detach(), g
 
 

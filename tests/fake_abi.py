@@ -1,0 +1,218 @@
+"""Test double that sits BELOW the C-ABI: an object exporting the same `bde_*` entry points as
+lib/libbde_b200.so (include/bde_b200.h), implemented with the oracle on HOST pointers.
+
+Only tests use it (monkeypatched over `_lib._handle`) so that the host-side logic of the
+optimizer classes — closures, GradScaler handling, arena aliasing, state dicts, sharding — is
+exercised on a machine without a GPU.  The product never loads it and has no such switch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from oracle import bde_oracle as O
+
+
+def _f32(ptr, count):
+    if count == 0:
+        return torch.empty(0)
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_float * count).from_address(ptr)))
+
+
+def _f64(ptr, count):
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_double * count).from_address(ptr)))
+
+
+def _i32(ptr, count):
+    return torch.from_numpy(np.ctypeslib.as_array((C.c_int32 * count).from_address(ptr)))
+
+
+def _mat(ptr, n, D, ld):
+    flat = _f32(ptr, (n - 1) * ld + D)
+    return torch.as_strided(flat, (n, D), (ld, 1))
+
+
+def _addr(v):
+    return v.value if isinstance(v, C.c_void_p) else v
+
+
+class FakeLib:
+    """Implements every symbol in _lib.SIGNATURES (checked by tests/test_abi.py)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def bde_version(self):
+        return 100
+
+    def bde_error_string(self, code):
+        return f"fake error {code}".encode()
+
+    def bde_device_sm_count(self, out):
+        return 0
+
+    def bde_svgd_workspace_bytes(self, n, out):
+        out._obj.value = 64
+        return 0
+
+    def bde_svgd_pairdist(self, X, n, D, ld, dist, accumulate, ws, wsb, stream):
+        self.calls.append("pairdist")
+        d = O.svgd_pairdist(_mat(X, n, D, ld))
+        out = _f64(dist, n * n).view(n, n)
+        if accumulate:
+            out += d
+        else:
+            out.copy_(d)
+        return 0
+
+    def bde_svgd_bandwidth(self, dist, n, l2, kgs, N, h_override, K, A, info, sel, stream):
+        self.calls.append("bandwidth")
+        bw = O.svgd_bandwidth(_f64(dist, n * n).view(n, n).clone(), l2, kgs, N, h_override if h_override > 0 else None)
+        _f32(K, n * n).copy_(bw["K"].reshape(-1).float())
+        _f32(A, n * n).copy_(bw["A"].reshape(-1).float())
+        if info:
+            _f64(info, 4).copy_(torch.tensor([bw["h"], bw["median"], bw["d_lo"], bw["d_hi"]], dtype=torch.float64))
+        if sel:
+            _i32(sel, 2).copy_(torch.tensor(bw["sel"], dtype=torch.int32))
+        return 0
+
+    def bde_svgd_apply(self, X, G, out, K, A, n, D, ld, stream):
+        self.calls.append("apply")
+        Km, Am = _f32(K, n * n).view(n, n), _f32(A, n * n).view(n, n)
+        res = O.svgd_apply(_mat(X, n, D, ld), _mat(G, n, D, ld), Km, Am)
+        _mat(out, n, D, ld).copy_(res.float())
+        return 0
+
+    def bde_svgd_step(self, X, G, out, n, D, ld, l2, kgs, N, h_override, dist, K, A, info, sel, ws, wsb, stream):
+        self.bde_svgd_pairdist(X, n, D, ld, dist, 0, ws, wsb, stream)
+        self.bde_svgd_bandwidth(dist, n, l2, kgs, N, h_override, K, A, info, sel, stream)
+        return self.bde_svgd_apply(X, G, out, K, A, n, D, ld, stream)
+
+    def bde_svgd_step_host(self, *a):
+        raise NotImplementedError("host pipeline is CUDA-only")
+
+    def bde_swag_update(self, theta, mean, sq, dev_row, D, updates, stream):
+        self.calls.append("swag_update")
+        m, s, col = O.swag_update(_f32(theta, D), _f32(mean, D), _f32(sq, D), updates)
+        _f32(mean, D).copy_(m)
+        _f32(sq, D).copy_(s)
+        _f32(dev_row, D).copy_(col)
+        return 0
+
+    def bde_swag_sample(self, mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed, sid, elem0, theta, stream):
+        self.calls.append("swag_sample")
+        ring = _mat(dev, K, D, ld)
+        order = [(head + k) % K for k in range(K)]
+        dev_DK = ring[order].t().contiguous()
+        ek = _f32(eps_k, K) if eps_k else torch.from_numpy(O.philox_normal(K, seed, sid ^ 0x5741))
+        ed = _f32(eps_d, D) if eps_d else torch.from_numpy(O.philox_normal(D, seed, sid, elem0))
+        _f32(theta, D).copy_(O.swag_sample(_f32(mean, D), _f32(sq, D), dev_DK, ek, ed))
+        return 0
+
+    def bde_ivon_sample(self, mean, prec, delta_sum, theta, D, n_eff, first, deterministic, eps, seed, sid, elem0, stream):
+        self.calls.append("ivon_sample")
+        e = _f32(eps, D) if eps else torch.from_numpy(O.philox_normal(D, seed, sid, elem0))
+        th, ds = O.ivon_sample(_f32(mean, D), _f32(prec, D), None if first else _f32(delta_sum, D).clone(), e, n_eff,
+                               bool(deterministic))
+        _f32(theta, D).copy_(th)
+        _f32(delta_sum, D).copy_(ds)
+        return 0
+
+    def bde_ivon_accumulate(self, acc, grad, D, first, stream):
+        a = _f32(acc, D)
+        a.copy_(_f32(grad, D) if first else a + _f32(grad, D))
+        return 0
+
+    def bde_ivon_update(self, acc, dsum, mean, mom, prec, D, S, step, lr, b1, b2, prior_prec, n_eff, tempering, damping,
+                        stream):
+        self.calls.append("ivon_update")
+        m, mo, p = O.ivon_update(_f32(acc, D), _f32(dsum, D), _f32(mean, D), _f32(mom, D), _f32(prec, D), mc_samples=S,
+                                 step=step, lr=lr, betas=(b1, b2), prior_prec=prior_prec, n_eff=n_eff,
+                                 tempering=tempering, damping=damping)
+        _f32(mean, D).copy_(m)
+        _f32(mom, D).copy_(mo)
+        _f32(prec, D).copy_(p)
+        return 0
+
+    def bde_gauss_sample_fwd(self, mu, rho, w, P, eps, seed, sid, elem0, stream):
+        self.calls.append("gauss_fwd")
+        e = _f32(eps, P) if eps else torch.from_numpy(O.philox_normal(P, seed, sid, elem0))
+        _f32(w, P).copy_(O.gauss_sample_fwd(_f32(mu, P), _f32(rho, P), e))
+        return 0
+
+    def bde_gauss_sample_bwd(self, grad_w, rho, grad_rho, P, eps, seed, sid, elem0, stream):
+        self.calls.append("gauss_bwd")
+        e = _f32(eps, P) if eps else torch.from_numpy(O.philox_normal(P, seed, sid, elem0))
+        _f32(grad_rho, P).copy_(O.gauss_sample_bwd(_f32(grad_w, P), _f32(rho, P), e)[1])
+        return 0
+
+    @staticmethod
+    def _scale(host, dev):
+        return host * (_f32(dev, 1).item() if dev else 1.0)
+
+    @staticmethod
+    def _emit(dst, P, grad, scale, accumulate):
+        d = _f32(dst, P)
+        d.copy_(d + scale * grad if accumulate else scale * grad)
+
+    def bde_kl_gauss_value_and_grad(self, mu, rho, P, pm, ps, value, gmu, grho, gs, gsd, accumulate, ws, wsb, stream):
+        self.calls.append("kl_gauss")
+        val, a, b = O.kl_gauss(_f32(mu, P), _f32(rho, P), pm, ps)
+        if value:
+            _f64(value, 1)[0] = val
+        if gmu:
+            s = self._scale(gs, gsd)
+            self._emit(gmu, P, a, s, accumulate)
+            self._emit(grho, P, b, s, accumulate)
+        return 0
+
+    def bde_kl_mixture_value_and_grad(self, mu, P, pi, s1, s2, value, gmu, gs, gsd, accumulate, ws, wsb, stream):
+        self.calls.append("kl_mixture")
+        val, g = O.kl_mixture(_f32(mu, P), pi, s1, s2)
+        if value:
+            _f64(value, 1)[0] = val
+        if gmu:
+            self._emit(gmu, P, g, self._scale(gs, gsd), accumulate)
+        return 0
+
+    def bde_l2_value_and_grad(self, theta, D, l2, value, grad, gs, gsd, accumulate, ws, wsb, stream):
+        self.calls.append("l2")
+        val, g = O.l2_term(_f32(theta, D), l2)
+        if value:
+            _f64(value, 1)[0] = val
+        if grad:
+            self._emit(grad, D, g, self._scale(gs, gsd), accumulate)
+        return 0
+
+    def bde_philox_normal(self, out, count, seed, sid, elem0, stream):
+        _f32(out, count).copy_(torch.from_numpy(O.philox_normal(count, seed, sid, elem0)))
+        return 0
+
+    def bde_multi_tensor_copy(self, flat, ptrs, offsets, sizes, count, mode, stream):
+        self.calls.append("mtc")
+        P = np.ctypeslib.as_array((C.c_uint64 * count).from_address(_addr(ptrs)))
+        Of = np.ctypeslib.as_array((C.c_int64 * count).from_address(_addr(offsets)))
+        Sz = np.ctypeslib.as_array((C.c_int64 * count).from_address(_addr(sizes)))
+        for p, o, s in zip(P, Of, Sz):
+            if s == 0:
+                continue
+            t = _f32(int(p), int(s))
+            f = _f32(flat + 4 * int(o), int(s))
+            if mode == 0:
+                f.copy_(t)
+            elif mode == 1:
+                f.add_(t)
+            else:
+                t.copy_(f)
+        return 0
+
+
+def install(monkeypatch):
+    """Route the package's C-ABI calls to the oracle-backed double (CPU tests only)."""
+    from beyond_deep_ensembles_b200 import _lib, ops
+    fake = FakeLib()
+    monkeypatch.setattr(_lib, "_handle", fake)
+    monkeypatch.setattr(ops, "require_cuda", lambda *a: None)
+    return fake

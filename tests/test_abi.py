@@ -1,0 +1,78 @@
+"""The C-ABI library loads and exports every symbol include/bde_b200.h declares (no compute)."""
+from __future__ import annotations
+
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "bde_b200.h"
+
+
+def declared_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(bde_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from beyond_deep_ensembles_b200 import build_ext
+    return build_ext.build(verbose=False)
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("bde_svgd_pairdist", "bde_svgd_bandwidth", "bde_svgd_apply", "bde_swag_update", "bde_swag_sample",
+                 "bde_ivon_sample", "bde_ivon_update", "bde_gauss_sample_fwd", "bde_gauss_sample_bwd",
+                 "bde_kl_gauss_value_and_grad", "bde_l2_value_and_grad", "bde_svgd_step_host"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(str(built_lib))
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in bde_b200.h but not exported"
+    lib.bde_version.restype = ctypes.c_int
+    assert lib.bde_version() == 100
+    lib.bde_error_string.restype = ctypes.c_char_p
+    assert lib.bde_error_string(-3) == b"bde: workspace missing or too small"
+
+
+def test_python_binding_covers_the_header(built_lib):
+    from beyond_deep_ensembles_b200 import _lib
+    bound = set(_lib.SIGNATURES) | {"bde_error_string"}
+    assert bound == set(declared_symbols())
+
+
+def test_fake_abi_mirrors_the_header():
+    from fake_abi import FakeLib
+    for name in declared_symbols():
+        assert callable(getattr(FakeLib, name, None)), f"test double lacks {name}"
+
+
+def test_sass_uses_packed_fp32(built_lib):
+    """The SVGD kernels must compile to Blackwell's packed FADD2/FFMA2 (not scalar FFMA)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN3bde20svgd_pairdist_kernelILi10EEEvPKfllPdiPviNS_15BandwidthParamsE",
+                           str(built_lib)], capture_output=True, text=True).stdout
+    assert sass.count("FFMA2") >= 90 and sass.count("FADD2") >= 90, "pairdist<10> lost its packed-fp32 inner loop"
+    assert "LDG.E.128" in sass or "LDG.E.ENL2.128" in sass or ".128" in sass
+
+
+def test_no_fallback_when_library_missing(monkeypatch, tmp_path):
+    from beyond_deep_ensembles_b200 import _lib
+    monkeypatch.setattr(_lib, "_handle", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.BdeError):
+        _lib.get()
+
+
+def test_cpu_tensors_are_rejected(built_lib):
+    import torch
+    from beyond_deep_ensembles_b200 import _lib, ops
+    with pytest.raises(_lib.BdeError):
+        ops.require_cuda(torch.zeros(4))
