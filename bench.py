@@ -1,0 +1,457 @@
+#!/usr/bin/env python
+"""bench.py — optimizer-step time and HBM GB/s of the posterior-update hot path.
+
+Headline workload (BASELINE.json configs[4], the sweep the north-star target is quoted on):
+one SVGD posterior update over n=10 particles x D=100 M parameters PER GPU (weak scaling:
+every rank holds a [10, D] column slice of X / G / out; only the 10x10 fp64 partial distance
+matrix is all-reduced).  A step is K1 (+K1b) -> K2 over data resident in HBM.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference        # the reference's CPU path (oracle port) on host cores
+
+Prints ONE JSON line on rank 0 (everything else goes to stderr).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PARTICLES = 10
+D_PER_GPU = 100_000_000
+L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE = 0.01, 1.0, 50000.0
+CPU_SAMPLE_D = 10_000_000
+METRIC = "svgd_posterior_update_algorithmic_GBps"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------
+# clocks (sampled DURING the timed region)
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] NVML unavailable: {e}")
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU baseline: the reference's op sequence (oracle port) on the host cores
+# --------------------------------------------------------------------------------------
+def synth_host(n, D, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, D, generator=g)
+    X *= (0.05 * (1 + 0.1 * torch.arange(n, dtype=torch.float32))).unsqueeze(1)
+    G = torch.randn(n, D, generator=g) * 1e-3
+    return X, G
+
+
+def cpu_reference_run(steps: int, warmup: int, D: int = CPU_SAMPLE_D):
+    """Times oracle.svgd_step_reference_order (the same ATen op sequence as svgd.py:86-89 + rbf)
+    in fp32 with every host thread torch will use.  Returns (GB/s, ms/step, threads)."""
+    from oracle import bde_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    X, G = synth_host(N_PARTICLES, D)
+    for _ in range(max(1, warmup)):
+        O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+    times = []
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    gbs = 16.0 * N_PARTICLES * D / (ms * 1e-3) / 1e9
+    return gbs, ms, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = min(args.steps, 10)
+    gbs, ms, threads = cpu_reference_run(steps, min(args.warmup, 2))
+    sample = (f"n={N_PARTICLES} x D={CPU_SAMPLE_D} fp32 on the host ({CPU_SAMPLE_D / D_PER_GPU:.0%} of one GPU's columns), "
+              f"{steps} timed steps of oracle.svgd_step_reference_order (reference op order, torch CPU ops)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "MultiX-SVGD optimizer-step sweep point: n=10 particles x D=100M params per GPU, D-sharded",
+        "particles": N_PARTICLES, "D_per_gpu": D_PER_GPU, "D_total": D_PER_GPU * n_gpus,
+        "l2_reg": L2_REG, "dataset_size": DATASET_SIZE, "kernel_grad_scale": KERNEL_GRAD_SCALE,
+        "algorithmic_bytes_per_step_per_gpu": 16 * N_PARTICLES * D_PER_GPU,
+        "l2_flush": "inputs (12 GB per GPU) are larger than the 126 MB L2",
+        "parallelism": f"D-shard x{n_gpus}; all-reduce of the 10x10 fp64 partial distances only",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# GPU helpers
+# --------------------------------------------------------------------------------------
+def time_kernel(fn, iters, warmup, flush=None):
+    """Mean device ms of fn() with CUDA events on the current stream; optional L2 flush between."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    return total / iters
+
+
+def other_paths(ops, peak_gbs, dev):
+    """The other kernels of the path at their named configs, device-resident,
+    L2 flushed between iterations when the working set is smaller than L2."""
+    res = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def rec(name, ms, nbytes, cfg):
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "GBps": gbs, "frac_of_measured_peak": gbs / peak_gbs, "algorithmic_bytes": nbytes,
+                     "config": cfg}
+        log(f"[bench] {name}: {ms:.4f} ms  {gbs:.0f} GB/s  ({gbs / peak_gbs:.2%} of measured copy peak)")
+
+    g = torch.Generator(device=dev).manual_seed(1)
+    # C3 SWAG, ResNet-50 + fc182, K = 10
+    D, K = 23_880_950, 10
+    Dp = (D + 63) // 64 * 64
+    theta = torch.randn(Dp, device=dev, generator=g) * 0.05
+    mean, sq = theta.clone(), theta * theta
+    ring = torch.randn(K, Dp, device=dev, generator=g) * 0.01
+    out = torch.empty(Dp, device=dev)
+    u = [0]
+
+    def swag_upd():
+        u[0] += 1
+        ops.swag_update(theta, mean, sq, ring[(u[0] - 1) % K], u[0])
+
+    rec("swag_update", time_kernel(swag_upd, 20, 3), 24 * Dp, f"ResNet-50 D={D}, K={K}")
+    rec("swag_sample", time_kernel(lambda: ops.swag_sample(mean, sq, ring, 3, out, seed=1, stream_id=2), 20, 3),
+        4 * (K + 3) * Dp, f"ResNet-50 D={D}, K={K}, Philox noise")
+    del theta, mean, sq, ring, out
+    # C4b iVON, DistilBERT + head
+    D = 66_955_010
+    Dp = (D + 63) // 64 * 64
+    mean = torch.randn(Dp, device=dev, generator=g) * 0.05
+    prec = torch.full((Dp,), 10.0 / 269038, device=dev)
+    mom, dsum, theta, acc = (torch.zeros(Dp, device=dev) for _ in range(4))
+    grad = torch.randn(Dp, device=dev, generator=g) * 1e-3
+    kw = dict(n_eff=269038.0)
+    rec("ivon_sample", time_kernel(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=1, stream_id=3, **kw), 20, 3),
+        20 * Dp, f"DistilBERT D={D}, Philox noise")
+    rec("ivon_accumulate", time_kernel(lambda: ops.ivon_accumulate(acc, grad, first=False), 20, 3), 12 * Dp, f"D={D}")
+    step = [0]
+
+    def ivon_upd():
+        step[0] += 1
+        ops.ivon_update(acc, dsum, mean, mom, prec, mc_samples=2, step=step[0], lr=1e-5, beta1=0.9, beta2=0.999,
+                        prior_prec=10.0, n_eff=269038.0, tempering=1.0, damping=1e-3)
+
+    rec("ivon_update", time_kernel(ivon_upd, 20, 3), 32 * Dp, f"DistilBERT D={D}")
+    del mean, prec, mom, dsum, theta, acc, grad
+    # C4a BBB last layer: P = 592,130 Gaussian weights; deterministic DistilBERT body 66.36 M
+    P = 592_130
+    Pp = (P + 63) // 64 * 64
+    mu = torch.randn(Pp, device=dev, generator=g) * 0.1
+    rho = torch.full((Pp,), -3.0, device=dev)
+    w, gmu, grho = (torch.zeros(Pp, device=dev) for _ in range(3))
+    val = torch.zeros((), dtype=torch.float64, device=dev)
+    ws = ops.value_workspace(dev)
+    rec("gauss_sample_fwd", time_kernel(lambda: ops.gauss_sample_fwd(mu, rho, w, seed=1, stream_id=4), 20, 3, flush),
+        12 * Pp, f"BBB head P={P} (launch-bound)")
+    rec("gauss_sample_bwd", time_kernel(lambda: ops.gauss_sample_bwd(w, rho, grho, seed=1, stream_id=4), 20, 3, flush),
+        16 * Pp, f"BBB head P={P} (launch-bound)")
+    rec("kl_gauss_value_and_grad",
+        time_kernel(lambda: ops.kl_gauss(mu, rho, 0.0, 1.0, value=val, grad_mu=gmu, grad_rho=grho, accumulate=True, ws=ws), 20, 3, flush),
+        24 * Pp, f"BBB head P={P} (launch-bound)")
+    Dd = 66_362_880
+    body = torch.randn(Dd, device=dev, generator=g) * 0.02
+    gbody = torch.zeros(Dd, device=dev)
+    rec("l2_value_and_grad",
+        time_kernel(lambda: ops.l2_term(body, 0.01, value=val, grad=gbody, accumulate=True, ws=ws), 20, 3),
+        12 * Dd, f"DistilBERT body D={Dd}")
+    del body, gbody
+    # C2 CIFAR ResNet-20 SVGD, n = 20 (small D: latency-bound, reported as time)
+    n2, D2 = 20, 273_610
+    D2p = (D2 + 63) // 64 * 64
+    X2 = torch.randn(n2, D2p, device=dev, generator=g) * 0.05
+    G2 = torch.randn(n2, D2p, device=dev, generator=g) * 1e-3
+    O2 = torch.empty_like(X2)
+    sc2 = ops.SvgdScratch.allocate(n2, dev)
+    rec("svgd_step_n20_resnet20", time_kernel(lambda: ops.svgd_step(X2, G2, O2, sc2, 3e-4, 1.0, 50000.0), 20, 3, flush),
+        16 * n2 * D2p, f"ResNet-20 D={D2}, n={n2} (FFMA-heavy, small D)")
+    # C1 UCI MLP SVGD, n = 10, D = 501 (pure launch latency)
+    X1 = torch.randn(10, 512, device=dev, generator=g)
+    G1 = torch.randn(10, 512, device=dev, generator=g)
+    O1 = torch.empty_like(X1)
+    sc1 = ops.SvgdScratch.allocate(10, dev)
+    rec("svgd_step_n10_uci", time_kernel(lambda: ops.svgd_step(X1, G1, O1, sc1, 0.01, 1.0, 768.0), 50, 5),
+        16 * 10 * 512, "UCI MLP D=501, n=10 (launch latency)")
+    return res
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    global D_PER_GPU
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--d-per-gpu", type=int, default=D_PER_GPU, help=argparse.SUPPRESS)
+    ap.add_argument("--skip-extras", action="store_true", help="skip e2e / cpu baseline / other paths (profiling runs)")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    D_PER_GPU = args.d_per_gpu
+    import torch.distributed as dist
+    from beyond_deep_ensembles_b200 import _lib, ops
+    from beyond_deep_ensembles_b200 import dist as bdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: launch with torch.distributed.run for N > 1")
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(2)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.get()  # fail loudly if libbde_b200.so is missing
+    peak_gbs, peak_src = measured_peaks()
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    n, D = N_PARTICLES, D_PER_GPU
+
+    # ---- synthetic, device-resident inputs: this rank's column slice [rank*D, (rank+1)*D) ----
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    X = torch.randn(n, D, device=dev, generator=g)
+    X *= (0.05 * (1 + 0.1 * torch.arange(n, device=dev, dtype=torch.float32))).unsqueeze(1)
+    G = torch.randn(n, D, device=dev, generator=g) * 1e-3
+    out = torch.empty_like(X)
+    sc = ops.SvgdScratch.allocate(n, dev)
+
+    def step(events=None):
+        """One posterior update; `events` collects (K1 start, K1 end / K2 start, K2 end)."""
+        if events is not None:
+            events[0].record()
+        if world == 1:
+            ops.svgd_pairdist_bandwidth(X, sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        else:
+            ops.svgd_pairdist(X, sc)
+            bdist.allreduce_dist(sc)
+            ops.svgd_bandwidth(sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        if events is not None:
+            events[1].record()
+        ops.svgd_apply(X, G, out, sc)
+        if events is not None:
+            events[2].record()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    launches0 = _lib.launch_count
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_begin.record()
+        for s in range(steps):
+            step(evs[s])
+        t_end.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count - launches0
+
+    total_ms = t_begin.elapsed_time(t_end)
+    k1_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    k2_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = tm.item()
+    ms_per_step = total_ms / steps
+    value = 16.0 * n * D * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
+    e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
+    paths, cpu_base = None, None
+    if not args.skip_extras:
+        try:
+            import psutil
+            need = 3 * 4 * n * D * world
+            avail = psutil.virtual_memory().available
+            if avail < 2 * need:
+                raise RuntimeError(f"host memory: need {need >> 30} GiB pinned, {avail >> 30} GiB available")
+            Xh = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+            Gh = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+            Oh = torch.empty((n, D), dtype=torch.float32, pin_memory=True)
+            Xh.copy_(X)
+            Gh.copy_(G)
+            ref_cols = out[:, :1024].cpu()
+            del out
+            torch.cuda.empty_cache()
+            st = ops.HostStaging.allocate(n, D, 4_000_000, dev, dX=X if D % 4 == 0 else None)
+            e2e_steps = min(steps, 5)
+
+            def e2e_step():
+                ops.svgd_step_host(Xh, Gh, Oh, st, sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+
+            e2e_step()  # warm-up (page-locks, stream creation)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            e2e_ms = 1e3 * dt.item() / e2e_steps
+            if not torch.allclose(Oh[:, :1024], ref_cols, rtol=1e-5, atol=1e-6):
+                raise RuntimeError("end-to-end result differs from the device-resident step")
+            e2e.update(value=16.0 * n * D * world / (e2e_ms * 1e-3) / 1e9, ms_per_step=e2e_ms, steps=e2e_steps,
+                       api="ops.svgd_step_host -> bde_svgd_host_pairdist / bde_svgd_host_apply (C-ABI, pinned host buffers)")
+            del Xh, Gh, Oh, st
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] e2e skipped: {e}")
+            e2e["skipped"] = str(e)
+
+        if rank == 0 and world == 1:
+            del X, G
+            torch.cuda.empty_cache()
+            try:
+                paths = other_paths(ops, peak_gbs, dev)
+            except Exception as e:  # noqa: BLE001
+                log(f"[bench] other paths failed: {e}")
+                paths = {"error": str(e)}
+            gbs, ms, threads = cpu_reference_run(3, 1)
+            cpu_base = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "cores": threads, "kind": "port",
+                        "sample": f"n={N_PARTICLES} x D={CPU_SAMPLE_D} fp32 on the host ({CPU_SAMPLE_D / D_PER_GPU:.0%} of "
+                                  "one GPU's columns), 3 timed steps of oracle.svgd_step_reference_order "
+                                  "(reference op order, torch CPU ops, all host threads)"}
+
+    if rank == 0:
+        k2_bytes = 12.0 * n * D
+        k1_bytes = 4.0 * n * D
+        k2_gbs = k2_bytes / (k2_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "svgd_apply_kernel<10> (K2: out = K G + A X)",
+                         "achieved": k2_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": k2_gbs / peak_gbs,
+                         "peak_source": peak_src, "frac_of_nominal_8TBps": k2_gbs / 8000.0,
+                         "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms, "traffic": None},
+            "kernels": {
+                "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
+                                               "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,
+                                               "algorithmic_bytes": k1_bytes,
+                                               "includes": "n*n all-reduce + K1b" if world > 1 else "fused K1b tail"},
+                "svgd_apply": {"ms": k2_ms, "GBps": k2_gbs, "frac": k2_gbs / peak_gbs, "algorithmic_bytes": k2_bytes},
+            },
+            "step_frac_of_measured_peak": value / world / peak_gbs,
+            "step_frac_of_nominal_8TBps": value / world / 8000.0,
+            "cpu_baseline": cpu_base, "paths": paths,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -24,10 +24,14 @@ _sz = C.c_size_t
 SIGNATURES = {
     "bde_version": [],
     "bde_device_sm_count": [_p],
+    "bde_tune": [C.c_char_p, _i],
     "bde_svgd_workspace_bytes": [_i, C.POINTER(_sz)],
     "bde_svgd_pairdist": [_p, _i, _i64, _i64, _p, _i, _p, _sz, _p],
     "bde_svgd_bandwidth": [_p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _p],
     "bde_svgd_apply": [_p, _p, _p, _p, _p, _i, _i64, _i64, _p],
+    "bde_svgd_pairdist_bandwidth": [_p, _i, _i64, _i64, _d, _d, _d, _d, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "bde_svgd_host_pairdist": [_p, _i, _i64, _i64, _i64, _p, _p, _p, _sz],
+    "bde_svgd_host_apply": [_p, _p, _i, _i64, _i64, _d, _d, _d, _d, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "bde_svgd_step": [_p, _p, _p, _i, _i64, _i64, _d, _d, _d, _d, _p, _p, _p, _p, _p, _p, _sz, _p],
     "bde_svgd_step_host": [_p, _p, _p, _i, _i64, _i64, _d, _d, _d, _d, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                            _p, _p],

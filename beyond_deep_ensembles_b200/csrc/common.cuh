@@ -35,6 +35,14 @@ inline int sm_count_cached() {
     return cached[dev];
 }
 
+// runtime launch-geometry overrides (0 = automatic); set through bde_tune(), used by the sweep tool
+struct Tuning {
+    int pairdist_ctas_per_sm = 0;
+    int apply_ctas_per_sm = 0;
+    int ew_ctas_per_sm = 0;
+};
+Tuning& tuning();
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ----------------------------------------------------------------------------
@@ -220,6 +228,7 @@ struct EwGrid {
 inline EwGrid ew_grid(int64_t n_elems, int threads, int ctas_per_sm) {
     const int64_t quads = (n_elems + 3) / 4;
     int64_t want = (quads + threads - 1) / threads;
+    if (tuning().ew_ctas_per_sm > 0) ctas_per_sm = tuning().ew_ctas_per_sm;
     const int64_t cap = (int64_t)sm_count_cached() * ctas_per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;

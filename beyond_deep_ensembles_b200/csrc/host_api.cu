@@ -41,13 +41,10 @@ static int get_pipe(HostPipe** out) {
 
 using namespace bde;
 
-extern "C" int bde_svgd_step_host(const float* X_host, const float* G_host, float* out_host, int n, int64_t D,
-                                  int64_t ld_host, double l2_reg, double kernel_grad_scale, double dataset_size,
-                                  double h_override, int64_t chunk_cols, float* dX, float* dG, float* dOut,
-                                  double* dist, float* K, float* A, double* info, int32_t* sel, void* workspace,
-                                  size_t workspace_bytes, double* info_host, int32_t* sel_host) {
-    if (!X_host || !G_host || !out_host || !dX || !dG || !dOut || !dist || !K || !A || n < 1 ||
-        n > BDE_MAX_PARTICLES || D < 1 || ld_host < D || chunk_cols < 4 || (chunk_cols & 3) || !(dataset_size > 0.0))
+extern "C" int bde_svgd_host_pairdist(const float* X_host, int n, int64_t D, int64_t ld_host, int64_t chunk_cols,
+                                      float* dX, double* dist, void* workspace, size_t workspace_bytes) {
+    if (!X_host || !dX || !dist || n < 1 || n > BDE_MAX_PARTICLES || D < 1 || ld_host < D || chunk_cols < 4 ||
+        (chunk_cols & 3))
         return BDE_ERR_INVALID_ARG;
     HostPipe* p = nullptr;
     int rc = get_pipe(&p);
@@ -55,8 +52,6 @@ extern "C" int bde_svgd_step_host(const float* X_host, const float* G_host, floa
     const int64_t ld_dev = (D + 3) & ~static_cast<int64_t>(3);
     const int64_t nchunks = (D + chunk_cols - 1) / chunk_cols;
     const size_t fsz = sizeof(float);
-
-    // ---- phase 1: X up, pair distances accumulate chunk by chunk ----
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t col0 = c * chunk_cols;
         const int64_t w = (D - col0 < chunk_cols) ? D - col0 : chunk_cols;
@@ -68,14 +63,30 @@ extern "C" int bde_svgd_step_host(const float* X_host, const float* G_host, floa
         rc = pairdist_impl(dX + col0, n, w, ld_dev, dist, c > 0 ? 1 : 0, workspace, workspace_bytes, 0, none, p->comp);
         if (rc != BDE_OK) return rc;
     }
+    BDE_RETURN_IF_CUDA(cudaStreamSynchronize(p->comp));
+    return BDE_OK;
+}
+
+extern "C" int bde_svgd_host_apply(const float* G_host, float* out_host, int n, int64_t D, int64_t ld_host,
+                                   double l2_reg, double kernel_grad_scale, double dataset_size, double h_override,
+                                   int64_t chunk_cols, const float* dX, float* dG, float* dOut, const double* dist,
+                                   float* K, float* A, double* info, int32_t* sel, double* info_host,
+                                   int32_t* sel_host) {
+    if (!G_host || !out_host || !dX || !dG || !dOut || !dist || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 1 ||
+        ld_host < D || chunk_cols < 4 || (chunk_cols & 3) || !(dataset_size > 0.0))
+        return BDE_ERR_INVALID_ARG;
+    HostPipe* p = nullptr;
+    int rc = get_pipe(&p);
+    if (rc != BDE_OK) return rc;
+    const int64_t ld_dev = (D + 3) & ~static_cast<int64_t>(3);
+    const int64_t nchunks = (D + chunk_cols - 1) / chunk_cols;
+    const size_t fsz = sizeof(float);
     rc = bde_svgd_bandwidth(dist, n, l2_reg, kernel_grad_scale, dataset_size, h_override, K, A, info, sel, p->comp);
     if (rc != BDE_OK) return rc;
     if (info_host && info)
         BDE_RETURN_IF_CUDA(cudaMemcpyAsync(info_host, info, 4 * sizeof(double), cudaMemcpyDeviceToHost, p->comp));
     if (sel_host && sel)
         BDE_RETURN_IF_CUDA(cudaMemcpyAsync(sel_host, sel, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, p->comp));
-
-    // ---- phase 2: G up, out = K G + A X, out down (double-buffered) ----
     for (int64_t c = 0; c < nchunks; ++c) {
         const int b = static_cast<int>(c & 1);
         const int64_t col0 = c * chunk_cols;
@@ -99,4 +110,15 @@ extern "C" int bde_svgd_step_host(const float* X_host, const float* G_host, floa
     BDE_RETURN_IF_CUDA(cudaStreamSynchronize(p->comp));
     BDE_RETURN_IF_CUDA(cudaStreamSynchronize(p->d2h));
     return BDE_OK;
+}
+
+extern "C" int bde_svgd_step_host(const float* X_host, const float* G_host, float* out_host, int n, int64_t D,
+                                  int64_t ld_host, double l2_reg, double kernel_grad_scale, double dataset_size,
+                                  double h_override, int64_t chunk_cols, float* dX, float* dG, float* dOut,
+                                  double* dist, float* K, float* A, double* info, int32_t* sel, void* workspace,
+                                  size_t workspace_bytes, double* info_host, int32_t* sel_host) {
+    int rc = bde_svgd_host_pairdist(X_host, n, D, ld_host, chunk_cols, dX, dist, workspace, workspace_bytes);
+    if (rc != BDE_OK) return rc;
+    return bde_svgd_host_apply(G_host, out_host, n, D, ld_host, l2_reg, kernel_grad_scale, dataset_size, h_override,
+                               chunk_cols, dX, dG, dOut, dist, K, A, info, sel, info_host, sel_host);
 }

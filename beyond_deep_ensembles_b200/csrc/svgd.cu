@@ -190,6 +190,15 @@ extern "C" int bde_svgd_pairdist(const float* X, int n, int64_t D, int64_t ld, d
                          static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int bde_svgd_pairdist_bandwidth(const float* X, int n, int64_t D, int64_t ld, double l2_reg,
+                                           double kernel_grad_scale, double dataset_size, double h_override,
+                                           double* dist, float* K, float* A, double* info, int32_t* sel,
+                                           void* workspace, size_t workspace_bytes, bde_stream_t stream) {
+    if (!K || !A || !(dataset_size > 0.0)) return BDE_ERR_INVALID_ARG;
+    BandwidthParams bp{l2_reg, kernel_grad_scale, dataset_size, h_override, K, A, info, sel};
+    return pairdist_impl(X, n, D, ld, dist, 0, workspace, workspace_bytes, 1, bp, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int bde_svgd_bandwidth(const double* dist, int n, double l2_reg, double kernel_grad_scale,
                                   double dataset_size, double h_override, float* K, float* A, double* info,
                                   int32_t* sel, bde_stream_t stream) {

@@ -356,7 +356,9 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     }
     const int64_t nquads = D >> 2;
     int64_t want = (nquads + TPB - 1) / TPB;
-    int64_t cap = static_cast<int64_t>(sm_count_cached()) * ctas_per_sm;
+    int per_sm = ctas_per_sm;
+    if (tuning().pairdist_ctas_per_sm > 0 && tuning().pairdist_ctas_per_sm < per_sm) per_sm = tuning().pairdist_ctas_per_sm;
+    int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
     if (cap > kMaxCtasPairdist) cap = kMaxCtasPairdist;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
@@ -377,7 +379,8 @@ int launch_apply(const float* X, const float* G, float* out, const float* K, con
     }
     const int64_t nquads = D >> 2;
     int64_t want = (nquads + 127) / 128;
-    const int64_t cap = static_cast<int64_t>(sm_count_cached()) * ctas_per_sm;
+    const int per_sm = tuning().apply_ctas_per_sm > 0 ? tuning().apply_ctas_per_sm : ctas_per_sm;
+    const int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     svgd_apply_kernel<N><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo);

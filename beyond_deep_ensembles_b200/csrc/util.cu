@@ -1,4 +1,6 @@
 // util.cu — library info, Philox diagnostic entry and the multi-tensor gather/scatter.
+#include <string>
+
 #include "elementwise.cuh"
 
 namespace bde {
@@ -83,9 +85,26 @@ multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTa
 
 }  // namespace bde
 
+namespace bde {
+Tuning& tuning() {
+    static Tuning t;
+    return t;
+}
+}  // namespace bde
+
 using namespace bde;
 
 extern "C" int bde_version(void) { return 100; }
+
+extern "C" int bde_tune(const char* key, int value) {
+    if (!key || value < 0) return BDE_ERR_INVALID_ARG;
+    const std::string k(key);
+    if (k == "pairdist_ctas_per_sm") tuning().pairdist_ctas_per_sm = value;
+    else if (k == "apply_ctas_per_sm") tuning().apply_ctas_per_sm = value;
+    else if (k == "ew_ctas_per_sm") tuning().ew_ctas_per_sm = value;
+    else return BDE_ERR_INVALID_ARG;
+    return BDE_OK;
+}
 
 extern "C" const char* bde_error_string(int code) {
     switch (code) {

@@ -110,20 +110,23 @@ def svgd_apply(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScra
     return out
 
 
+def svgd_pairdist_bandwidth(X: torch.Tensor, sc: SvgdScratch, l2_reg: float, kernel_grad_scale: float,
+                            dataset_size: float, h_override: float = 0.0) -> None:
+    """K1 with K1b fused into its tail (single-GPU form, one launch)."""
+    require_cuda(X)
+    _lib.require_f32(X)
+    n, D, ld = _rows(X)
+    assert n == sc.n
+    _lib.call("bde_svgd_pairdist_bandwidth", X.data_ptr(), n, D, ld, float(l2_reg), float(kernel_grad_scale),
+              float(dataset_size), float(h_override or 0.0), sc.dist.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(),
+              sc.info.data_ptr(), sc.sel.data_ptr(), sc.ws.data_ptr(), sc.ws_bytes, _s(X))
+
+
 def svgd_step(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScratch, l2_reg: float,
               kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0) -> torch.Tensor:
-    """Single-GPU K1 + K1b + K2 (two launches)."""
-    require_cuda(X, G, out)
-    _lib.require_f32(X, G, out)
-    n, D, ld = _rows(X)
-    if _rows(G) != (n, D, ld) or _rows(out) != (n, D, ld):
-        raise ValueError("X, G and out must share shape and row stride")
-    _lib.call("bde_svgd_step", X.data_ptr(), G.data_ptr(), out.data_ptr(), n, D, ld, float(l2_reg),
-              float(kernel_grad_scale), float(dataset_size), float(h_override or 0.0), sc.dist.data_ptr(),
-              sc.K.data_ptr(), sc.A.data_ptr(), sc.info.data_ptr(), sc.sel.data_ptr(), sc.ws.data_ptr(), sc.ws_bytes,
-              _s(X))
-    _lib.launch_count += 1  # K1(+K1b fused) and K2
-    return out
+    """Single-GPU posterior update: K1(+K1b) then K2 — two launches."""
+    svgd_pairdist_bandwidth(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+    return svgd_apply(X, G, out, sc)
 
 
 # --------------------------------------------------------------------------------------
@@ -288,3 +291,64 @@ def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int) -> No
     sizes = (C.c_int64 * count)(*[t.numel() for t in tensors])
     _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(offs, C.c_void_p),
               C.cast(sizes, C.c_void_p), count, int(mode), _s(flat_row))
+
+
+# --------------------------------------------------------------------------------------
+# host-buffer (end-to-end) SVGD step
+# --------------------------------------------------------------------------------------
+@dataclass
+class HostStaging:
+    """Device staging of the host-buffer path: X resident, G / out double-buffered chunks."""
+    n: int
+    D: int
+    chunk_cols: int
+    dX: torch.Tensor    # [n, ld_dev]
+    dG: torch.Tensor    # [2, n, chunk_cols]
+    dOut: torch.Tensor  # [2, n, chunk_cols]
+
+    @staticmethod
+    def allocate(n: int, D: int, chunk_cols: int, device, dX: torch.Tensor | None = None) -> "HostStaging":
+        chunk_cols = max(4, (min(chunk_cols, D) + 3) // 4 * 4)
+        ld_dev = (D + 3) // 4 * 4
+        if dX is None:
+            dX = torch.empty((n, ld_dev), dtype=torch.float32, device=device)
+        assert dX.shape == (n, ld_dev) and dX.is_contiguous()
+        return HostStaging(n, D, chunk_cols, dX,
+                           torch.empty((2, n, chunk_cols), dtype=torch.float32, device=device),
+                           torch.empty((2, n, chunk_cols), dtype=torch.float32, device=device))
+
+
+def _host_rows(t: torch.Tensor):
+    if t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D fp32 HOST tensor with contiguous rows")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def svgd_host_pairdist(X_host: torch.Tensor, st: HostStaging, sc: SvgdScratch) -> None:
+    """Phase 1 of the end-to-end step: stream X up, accumulate the local partial distances (blocks)."""
+    n, D, ld = _host_rows(X_host)
+    assert (n, D) == (st.n, st.D)
+    _lib.call("bde_svgd_host_pairdist", X_host.data_ptr(), n, D, ld, st.chunk_cols, st.dX.data_ptr(),
+              sc.dist.data_ptr(), sc.ws.data_ptr(), sc.ws_bytes)
+
+
+def svgd_host_apply(G_host: torch.Tensor, out_host: torch.Tensor, st: HostStaging, sc: SvgdScratch, l2_reg: float,
+                    kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0) -> None:
+    """Phase 2: K1b, then stream G up / out down through K2 (blocks until out_host is complete)."""
+    n, D, ld = _host_rows(G_host)
+    assert (n, D) == (st.n, st.D) and _host_rows(out_host) == (n, D, ld)
+    _lib.call("bde_svgd_host_apply", G_host.data_ptr(), out_host.data_ptr(), n, D, ld, float(l2_reg),
+              float(kernel_grad_scale), float(dataset_size), float(h_override or 0.0), st.chunk_cols, st.dX.data_ptr(),
+              st.dG.data_ptr(), st.dOut.data_ptr(), sc.dist.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(),
+              sc.info.data_ptr(), sc.sel.data_ptr(), None, None)
+
+
+def svgd_step_host(X_host, G_host, out_host, st: HostStaging, sc: SvgdScratch, l2_reg: float, kernel_grad_scale: float,
+                   dataset_size: float, h_override: float = 0.0, group=None) -> None:
+    """End-to-end SVGD posterior update on HOST buffers (this rank's column slice when D-sharded)."""
+    from . import dist as bdist
+    svgd_host_pairdist(X_host, st, sc)
+    bdist.allreduce_dist(sc, group)
+    if bdist.world(group) > 1:
+        torch.cuda.current_stream(sc.dist.device).synchronize()  # phase 2 runs on the library's streams
+    svgd_host_apply(G_host, out_host, st, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)

@@ -44,6 +44,11 @@ typedef void* bde_stream_t;
 /* ---- library ------------------------------------------------------------- */
 int bde_version(void);
 const char* bde_error_string(int code);
+/*
+ * Launch-geometry override for tuning sweeps: key is "pairdist_ctas_per_sm",
+ * "apply_ctas_per_sm" or "ew_ctas_per_sm"; value 0 restores the automatic choice.
+ */
+int bde_tune(const char* key, int value);
 /* number of SMs of the current device (grid sizing is done inside the library) */
 int bde_device_sm_count(int* sm_count);
 
@@ -88,7 +93,16 @@ int bde_svgd_apply(const float* X, const float* G, float* out, const float* K, c
                    int n, int64_t D, int64_t ld, bde_stream_t stream);
 
 /*
- * Single-GPU convenience: K1 + K1b + K2 on one stream (no collective in between).
+ * K1 with K1b fused into its tail (the last CTA to finish runs the n*n epilogue): the
+ * single-GPU form, one launch instead of two.  Arguments as in the two calls above.
+ */
+int bde_svgd_pairdist_bandwidth(const float* X, int n, int64_t D, int64_t ld, double l2_reg,
+                                double kernel_grad_scale, double dataset_size, double h_override,
+                                double* dist, float* K, float* A, double* info, int32_t* sel,
+                                void* workspace, size_t workspace_bytes, bde_stream_t stream);
+
+/*
+ * Single-GPU convenience: K1(+K1b) + K2 on one stream (no collective in between).
  */
 int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, int64_t ld,
                   double l2_reg, double kernel_grad_scale, double dataset_size,
@@ -96,14 +110,25 @@ int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, 
                   int32_t* sel, void* workspace, size_t workspace_bytes, bde_stream_t stream);
 
 /*
- * Host-buffer entry (the end-to-end path): X_host/G_host/out_host are HOST arrays
+ * Host-buffer entries (the end-to-end path): X_host/G_host/out_host are HOST arrays
  * [n, D] with row stride ld_host (pinned memory gives full PCIe bandwidth).  The
- * columns are streamed through the device in `chunk_cols`-wide pieces on internal
- * copy/compute streams: H2D X chunk -> K1(accumulate) ... -> K1b -> per chunk:
- * H2D G -> K2 -> D2H out.  dX/dG/dOut are caller-provided device staging buffers:
- * dX [n, D] (X stays resident between the two phases), dG and dOut [2][n, chunk_cols].
- * Blocks until out_host is complete.  info_host[4], sel_host[2] may be NULL.
+ * columns are streamed through the device in `chunk_cols`-wide pieces (a multiple of 4)
+ * on the library's own copy/compute streams so that PCIe traffic in both directions
+ * overlaps the kernels.  Caller-provided device staging: dX [n, ld_dev] with
+ * ld_dev = D rounded up to 4 (X stays resident between the two phases), dG and dOut
+ * [2][n, chunk_cols].  Both calls block until their results are complete.
+ *   bde_svgd_host_pairdist: per chunk H2D X -> K1(accumulate); dist = local partial sums.
+ *   (D-sharded jobs all-reduce `dist` here.)
+ *   bde_svgd_host_apply:    K1b, then per chunk H2D G -> K2 -> D2H out.
+ *   bde_svgd_step_host:     both, for a single rank.  info_host[4], sel_host[2] may be NULL.
  */
+int bde_svgd_host_pairdist(const float* X_host, int n, int64_t D, int64_t ld_host, int64_t chunk_cols,
+                           float* dX, double* dist, void* workspace, size_t workspace_bytes);
+int bde_svgd_host_apply(const float* G_host, float* out_host, int n, int64_t D, int64_t ld_host,
+                        double l2_reg, double kernel_grad_scale, double dataset_size,
+                        double h_override, int64_t chunk_cols, const float* dX, float* dG, float* dOut,
+                        const double* dist, float* K, float* A, double* info, int32_t* sel,
+                        double* info_host, int32_t* sel_host);
 int bde_svgd_step_host(const float* X_host, const float* G_host, float* out_host, int n,
                        int64_t D, int64_t ld_host, double l2_reg, double kernel_grad_scale,
                        double dataset_size, double h_override, int64_t chunk_cols,

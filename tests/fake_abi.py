@@ -53,6 +53,9 @@ class FakeLib:
     def bde_device_sm_count(self, out):
         return 0
 
+    def bde_tune(self, key, value):
+        return 0
+
     def bde_svgd_workspace_bytes(self, n, out):
         out._obj.value = 64
         return 0
@@ -90,7 +93,17 @@ class FakeLib:
         self.bde_svgd_bandwidth(dist, n, l2, kgs, N, h_override, K, A, info, sel, stream)
         return self.bde_svgd_apply(X, G, out, K, A, n, D, ld, stream)
 
+    def bde_svgd_pairdist_bandwidth(self, X, n, D, ld, l2, kgs, N, h_override, dist, K, A, info, sel, ws, wsb, stream):
+        self.bde_svgd_pairdist(X, n, D, ld, dist, 0, ws, wsb, stream)
+        return self.bde_svgd_bandwidth(dist, n, l2, kgs, N, h_override, K, A, info, sel, stream)
+
     def bde_svgd_step_host(self, *a):
+        raise NotImplementedError("host pipeline is CUDA-only")
+
+    def bde_svgd_host_pairdist(self, *a):
+        raise NotImplementedError("host pipeline is CUDA-only")
+
+    def bde_svgd_host_apply(self, *a):
         raise NotImplementedError("host pipeline is CUDA-only")
 
     def bde_swag_update(self, theta, mean, sq, dev_row, D, updates, stream):
