@@ -163,15 +163,25 @@ def workload_config(n_gpus):
 # GPU helpers
 # --------------------------------------------------------------------------------------
 def time_kernel(fn, iters, warmup, flush=None):
-    """Mean device ms of fn() with CUDA events on the current stream; optional L2 flush between."""
+    """Mean device ms of fn() (CUDA events on the current stream).
+
+    Working set larger than L2 (flush=None): `iters` back-to-back launches between one event pair,
+    as inside a real optimizer step.  Working set smaller than L2: every launch is timed on its
+    own after overwriting a buffer larger than L2."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if flush is None:
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1) / iters
     total = 0.0
     for _ in range(iters):
-        if flush is not None:
-            flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.zero_()
         e0.record()
         fn()
         e1.record()
@@ -197,7 +207,8 @@ def other_paths(ops, peak_gbs, dev):
     D, K = 23_880_950, 10
     Dp = (D + 63) // 64 * 64
     theta = torch.randn(Dp, device=dev, generator=g) * 0.05
-    mean, sq = theta.clone(), theta * theta
+    mean = theta + torch.randn(Dp, device=dev, generator=g) * 0.01
+    sq = mean * mean + 1e-4
     ring = torch.randn(K, Dp, device=dev, generator=g) * 0.01
     out = torch.empty(Dp, device=dev)
     u = [0]
@@ -214,8 +225,11 @@ def other_paths(ops, peak_gbs, dev):
     D = 66_955_010
     Dp = (D + 63) // 64 * 64
     mean = torch.randn(Dp, device=dev, generator=g) * 0.05
-    prec = torch.full((Dp,), 10.0 / 269038, device=dev)
-    mom, dsum, theta, acc = (torch.zeros(Dp, device=dev) for _ in range(4))
+    prec = torch.rand(Dp, device=dev, generator=g) * 1e-4 + 10.0 / 269038   # mid-training state: all non-trivial
+    mom = torch.randn(Dp, device=dev, generator=g) * 1e-4
+    dsum = torch.randn(Dp, device=dev, generator=g) * 0.3
+    acc = torch.randn(Dp, device=dev, generator=g) * 2e-3
+    theta = torch.zeros(Dp, device=dev)
     grad = torch.randn(Dp, device=dev, generator=g) * 1e-3
     kw = dict(n_eff=269038.0)
     rec("ivon_sample", time_kernel(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=1, stream_id=3, **kw), 20, 3),
@@ -225,7 +239,7 @@ def other_paths(ops, peak_gbs, dev):
 
     def ivon_upd():
         step[0] += 1
-        ops.ivon_update(acc, dsum, mean, mom, prec, mc_samples=2, step=step[0], lr=1e-5, beta1=0.9, beta2=0.999,
+        ops.ivon_update(acc, dsum, mean, mom, prec, mc_samples=2, step=100 + step[0], lr=1e-5, beta1=0.9, beta2=0.999,
                         prior_prec=10.0, n_eff=269038.0, tempering=1.0, damping=1e-3)
 
     rec("ivon_update", time_kernel(ivon_upd, 20, 3), 32 * Dp, f"DistilBERT D={D}")

@@ -179,11 +179,6 @@ l2_kernel(const float* __restrict__ theta, int64_t D, float l2_scale, double val
     finish_value(local, value_factor, value, ws);
 }
 
-inline int value_grid(int64_t n) {
-    EwGrid g = ew_grid(n, kEwThreads, kEwCtasPerSm);
-    return g.blocks > kMaxCtasEw ? kMaxCtasEw : g.blocks;
-}
-
 }  // namespace bde
 
 using namespace bde;
@@ -193,14 +188,13 @@ extern "C" int bde_gauss_sample_fwd(const float* mu, const float* rho, float* w,
     if (!mu || !rho || !w || P < 0 || elem0 < 0 || (elem0 & 3)) return BDE_ERR_INVALID_ARG;
     if (P == 0) return BDE_OK;
     const bool vec = aligned16(mu) && aligned16(rho) && aligned16(w) && (!eps || aligned16(eps));
-    const EwGrid g = ew_grid(P, kEwThreads, kEwCtasPerSm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        gauss_sample_fwd_kernel<true><<<g.blocks, g.threads, 0, st>>>(mu, rho, w, P, eps, seed, stream_id, elem0 >> 2);
+        rc_ = launch_ew(gauss_sample_fwd_kernel<true>, P, st, mu, rho, w, P, eps, seed, stream_id, elem0 >> 2);
     else
-        gauss_sample_fwd_kernel<false><<<g.blocks, g.threads, 0, st>>>(mu, rho, w, P, eps, seed, stream_id, elem0 >> 2);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+        rc_ = launch_ew(gauss_sample_fwd_kernel<false>, P, st, mu, rho, w, P, eps, seed, stream_id, elem0 >> 2);
+    return rc_;
 }
 
 extern "C" int bde_gauss_sample_bwd(const float* grad_w, const float* rho, float* grad_rho, int64_t P,
@@ -209,14 +203,13 @@ extern "C" int bde_gauss_sample_bwd(const float* grad_w, const float* rho, float
     if (!grad_w || !rho || !grad_rho || P < 0 || elem0 < 0 || (elem0 & 3)) return BDE_ERR_INVALID_ARG;
     if (P == 0) return BDE_OK;
     const bool vec = aligned16(grad_w) && aligned16(rho) && aligned16(grad_rho) && (!eps || aligned16(eps));
-    const EwGrid g = ew_grid(P, kEwThreads, kEwCtasPerSm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        gauss_sample_bwd_kernel<true><<<g.blocks, g.threads, 0, st>>>(grad_w, rho, grad_rho, P, eps, seed, stream_id, elem0 >> 2);
+        rc_ = launch_ew(gauss_sample_bwd_kernel<true>, P, st, grad_w, rho, grad_rho, P, eps, seed, stream_id, elem0 >> 2);
     else
-        gauss_sample_bwd_kernel<false><<<g.blocks, g.threads, 0, st>>>(grad_w, rho, grad_rho, P, eps, seed, stream_id, elem0 >> 2);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+        rc_ = launch_ew(gauss_sample_bwd_kernel<false>, P, st, grad_w, rho, grad_rho, P, eps, seed, stream_id, elem0 >> 2);
+    return rc_;
 }
 
 static int check_value_ws(double* value, void* ws, size_t ws_bytes) {
@@ -224,23 +217,23 @@ static int check_value_ws(double* value, void* ws, size_t ws_bytes) {
     return BDE_OK;
 }
 
-#define BDE_DISPATCH3(KERNEL, vec, grad, acc, ...)                                        \
-    do {                                                                                  \
-        if (vec) {                                                                        \
-            if (!grad)                                                                    \
-                KERNEL<true, false, false><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);   \
-            else if (acc)                                                                 \
-                KERNEL<true, true, true><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);     \
-            else                                                                          \
-                KERNEL<true, true, false><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);    \
-        } else {                                                                          \
-            if (!grad)                                                                    \
-                KERNEL<false, false, false><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);  \
-            else if (acc)                                                                 \
-                KERNEL<false, true, true><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);    \
-            else                                                                          \
-                KERNEL<false, true, false><<<blocks, kEwThreads, 0, st>>>(__VA_ARGS__);   \
-        }                                                                                 \
+#define BDE_DISPATCH3(KERNEL, nelem, vec, grad, acc, ...)                                          \
+    do {                                                                                           \
+        if (vec) {                                                                                 \
+            if (!grad)                                                                             \
+                rc = launch_ew(KERNEL<true, false, false>, nelem, st, __VA_ARGS__);                \
+            else if (acc)                                                                          \
+                rc = launch_ew(KERNEL<true, true, true>, nelem, st, __VA_ARGS__);                  \
+            else                                                                                   \
+                rc = launch_ew(KERNEL<true, true, false>, nelem, st, __VA_ARGS__);                 \
+        } else {                                                                                   \
+            if (!grad)                                                                             \
+                rc = launch_ew(KERNEL<false, false, false>, nelem, st, __VA_ARGS__);               \
+            else if (acc)                                                                          \
+                rc = launch_ew(KERNEL<false, true, true>, nelem, st, __VA_ARGS__);                 \
+            else                                                                                   \
+                rc = launch_ew(KERNEL<false, true, false>, nelem, st, __VA_ARGS__);                \
+        }                                                                                          \
     } while (0)
 
 extern "C" int bde_kl_gauss_value_and_grad(const float* mu, const float* rho, int64_t P, double prior_mu,
@@ -258,12 +251,10 @@ extern "C" int bde_kl_gauss_value_and_grad(const float* mu, const float* rho, in
     }
     const bool grad = grad_mu != nullptr;
     const bool vec = aligned16(mu) && aligned16(rho) && (!grad || (aligned16(grad_mu) && aligned16(grad_rho)));
-    const int blocks = value_grid(P);
-    BDE_DISPATCH3(kl_gauss_kernel, vec, grad, accumulate != 0, mu, rho, P, static_cast<float>(prior_mu),
+    BDE_DISPATCH3(kl_gauss_kernel, P, vec, grad, accumulate != 0, mu, rho, P, static_cast<float>(prior_mu),
                   static_cast<float>(prior_sigma), value, grad_mu, grad_rho, static_cast<float>(grad_scale),
                   grad_scale_dev, workspace);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return rc;
 }
 
 extern "C" int bde_kl_mixture_value_and_grad(const float* mu, int64_t P, double pi, double sigma1, double sigma2,
@@ -289,11 +280,9 @@ extern "C" int bde_kl_mixture_value_and_grad(const float* mu, int64_t P, double 
     c.lognorm2 = static_cast<float>(-log(sigma2) - half_log_2pi);
     const bool grad = grad_mu != nullptr;
     const bool vec = aligned16(mu) && (!grad || aligned16(grad_mu));
-    const int blocks = value_grid(P);
-    BDE_DISPATCH3(kl_mixture_kernel, vec, grad, accumulate != 0, mu, P, c, value, grad_mu,
+    BDE_DISPATCH3(kl_mixture_kernel, P, vec, grad, accumulate != 0, mu, P, c, value, grad_mu,
                   static_cast<float>(grad_scale), grad_scale_dev, workspace);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return rc;
 }
 
 extern "C" int bde_l2_value_and_grad(const float* theta, int64_t D, double l2_scale, double* value, float* grad,
@@ -309,9 +298,7 @@ extern "C" int bde_l2_value_and_grad(const float* theta, int64_t D, double l2_sc
     }
     const bool has_grad = grad != nullptr;
     const bool vec = aligned16(theta) && (!has_grad || aligned16(grad));
-    const int blocks = value_grid(D);
-    BDE_DISPATCH3(l2_kernel, vec, has_grad, accumulate != 0, theta, D, static_cast<float>(l2_scale), 0.5 * l2_scale, value,
+    BDE_DISPATCH3(l2_kernel, D, vec, has_grad, accumulate != 0, theta, D, static_cast<float>(l2_scale), 0.5 * l2_scale, value,
                   grad, static_cast<float>(grad_scale), grad_scale_dev, workspace);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return rc;
 }

@@ -40,6 +40,8 @@ struct Tuning {
     int pairdist_ctas_per_sm = 0;
     int apply_ctas_per_sm = 0;
     int ew_ctas_per_sm = 0;
+    int apply_variant = 0;     // 0 auto, 1 direct-LDG kernel, 2 TMA-staged kernel
+    int pairdist_variant = 0;  // same for K1
 };
 Tuning& tuning();
 
@@ -119,6 +121,47 @@ __device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
 }
 
 // ----------------------------------------------------------------------------
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on shared-memory mbarriers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both sides 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ V4 lds_v4(const float* p) {
+    V4 v;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(smem_u32(p)));
+    return v;
+}
+
+// ----------------------------------------------------------------------------
 // reductions
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -135,15 +178,18 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Deterministic grid-wide fp64 sum of `count` values per CTA.
 //   cta_vals: this CTA's values in shared memory (count doubles), valid after __syncthreads.
 //   ws layout: [0] ticket (unsigned, padded to 16 B), then gridDim.x*count doubles.
-// Returns true in every thread of the LAST CTA to arrive, after which
-// total[k] = sum over CTAs in blockIdx order is available in `total` (shared, count doubles).
-// The ticket is reset so the workspace can be reused by the next launch.
+// Returns true in every thread of the LAST CTA to arrive, after which total[k] = sum over all
+// CTAs is available in `total` (shared, count doubles).  The order of the additions depends only
+// on (gridDim, blockDim, count): the CTA list is cut into S = threads/count interleaved slices
+// summed in parallel, then the S slice sums are added in slice order.  The ticket is reset so the
+// workspace can be reused by the next launch.
 __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int count, void* ws, double* total) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
     double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     __shared__ bool is_last;
+    __shared__ double slice_sum[1024];
     for (int k = tid; k < count; k += nthreads) parts[(size_t)blockIdx.x * count + k] = cta_vals[k];
     __threadfence();
     __syncthreads();
@@ -154,10 +200,26 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    for (int k = tid; k < count; k += nthreads) {
-        double s = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&parts[(size_t)b * count + k]);
-        total[k] = s;
+    if (count <= nthreads) {
+        const int S = nthreads / count;
+        const int k = tid % count, sl = tid / count;
+        if (sl < S) {
+            double s = 0.0;
+            for (unsigned int b = sl; b < gridDim.x; b += S) s += __ldcg(&parts[(size_t)b * count + k]);
+            slice_sum[sl * count + k] = s;
+        }
+        __syncthreads();
+        if (tid < count) {
+            double s = 0.0;
+            for (int j = 0; j < S; ++j) s += slice_sum[j * count + tid];
+            total[tid] = s;
+        }
+    } else {
+        for (int k = tid; k < count; k += nthreads) {
+            double s = 0.0;
+            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&parts[(size_t)b * count + k]);
+            total[k] = s;
+        }
     }
     if (tid == 0) *ticket = 0u;
     __syncthreads();
@@ -189,14 +251,15 @@ __device__ __forceinline__ float u01_open(unsigned int r) {
     return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
 }
 
+// Box-Muller on the SFU: radius from MUFU.LG2, angle uniform on [-pi, pi) where MUFU.SIN/COS
+// are accurate to 2^-21.4 absolute.  (Noise quality, not reference parity: parity tests inject
+// the reference's own noise.)
 __device__ __forceinline__ void box_muller(unsigned int r0, unsigned int r1, float& z0, float& z1) {
     const float u = u01_open(r0);
-    const float ang2 = static_cast<float>(r1 >> 8) * 1.1920928955078125e-07f;  // 2*u2 in [0, 2)
-    const float rad = sqrtf(-2.0f * logf(u));
-    float s, c;
-    sincospif(ang2, &s, &c);
-    z0 = rad * c;
-    z1 = rad * s;
+    const float ang = fmaf(static_cast<float>(r1 >> 8), 3.7450702829239286e-07f, -3.14159265358979323846f);
+    const float rad = sqrtf(fmaxf(-1.3862943611198906f * __log2f(u), 0.0f));  // sqrt(-2 ln u)
+    z0 = rad * __cosf(ang);
+    z1 = rad * __sinf(ang);
 }
 
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream_id, uint64_t quad) {

@@ -3,6 +3,9 @@
 // a full group on 16-byte-aligned pointers moves with one 128-bit access, anything else
 // (ragged tail, unaligned views) falls back to guarded scalar accesses in the same kernel.
 #pragma once
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace bde {
@@ -56,7 +59,29 @@ __device__ __forceinline__ void block_sum_fp64(double v, double* cta_val) {
 }
 
 constexpr int kEwThreads = 256;
-constexpr int kEwCtasPerSm = 8;
-constexpr int kMaxCtasEw = 148 * kEwCtasPerSm * 2;
+constexpr int kMaxCtasEw = 148 * 8 * 2;
+
+// Resident CTAs per SM of a kernel at kEwThreads threads, cached per kernel.
+inline int ew_occupancy(const void* kernel) {
+    static std::mutex mu;
+    static std::map<const void*, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) return it->second;
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kEwThreads, 0) != cudaSuccess || v < 1) v = 1;
+    cache[kernel] = v;
+    return v;
+}
+
+// One full wave of persistent CTAs (SMs x measured occupancy), grid-stride over the quads:
+// a grid larger than what is resident leaves a partial second wave (measured: -25 % bandwidth).
+template <typename... KArgs, typename... Args>
+inline int launch_ew(void (*kernel)(KArgs...), int64_t n_elems, cudaStream_t st, Args... args) {
+    const EwGrid g = ew_grid(n_elems, kEwThreads, ew_occupancy(reinterpret_cast<const void*>(kernel)));
+    kernel<<<g.blocks, g.threads, 0, st>>>(args...);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
 
 }  // namespace bde

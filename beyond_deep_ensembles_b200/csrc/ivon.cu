@@ -128,31 +128,29 @@ extern "C" int bde_ivon_sample(const float* mean, const float* prec, float* delt
     if (D == 0) return BDE_OK;
     const bool vec = aligned16(mean) && aligned16(prec) && aligned16(delta_sum) && aligned16(theta) &&
                      (!eps || aligned16(eps));
-    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float nf = static_cast<float>(n_eff);
+    int rc_;
     if (vec)
-        ivon_sample_kernel<true><<<g.blocks, g.threads, 0, st>>>(mean, prec, delta_sum, theta, D, nf, first,
+        rc_ = launch_ew(ivon_sample_kernel<true>, D, st, mean, prec, delta_sum, theta, D, nf, first,
                                                                  deterministic, eps, seed, stream_id, elem0 >> 2);
     else
-        ivon_sample_kernel<false><<<g.blocks, g.threads, 0, st>>>(mean, prec, delta_sum, theta, D, nf, first,
+        rc_ = launch_ew(ivon_sample_kernel<false>, D, st, mean, prec, delta_sum, theta, D, nf, first,
                                                                   deterministic, eps, seed, stream_id, elem0 >> 2);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return rc_;
 }
 
 extern "C" int bde_ivon_accumulate(float* acc, const float* grad, int64_t D, int first, bde_stream_t stream) {
     if (!acc || !grad || D < 0) return BDE_ERR_INVALID_ARG;
     if (D == 0) return BDE_OK;
     const bool vec = aligned16(acc) && aligned16(grad);
-    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        ivon_accumulate_kernel<true><<<g.blocks, g.threads, 0, st>>>(acc, grad, D, first);
+        rc_ = launch_ew(ivon_accumulate_kernel<true>, D, st, acc, grad, D, first);
     else
-        ivon_accumulate_kernel<false><<<g.blocks, g.threads, 0, st>>>(acc, grad, D, first);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+        rc_ = launch_ew(ivon_accumulate_kernel<false>, D, st, acc, grad, D, first);
+    return rc_;
 }
 
 extern "C" int bde_ivon_update(const float* acc_grad, const float* delta_sum, float* mean, float* momentum,
@@ -175,12 +173,11 @@ extern "C" int bde_ivon_update(const float* acc_grad, const float* delta_sum, fl
     c.omb2 = static_cast<float>(1.0 - beta2);
     c.c2 = static_cast<float>(0.5 * (1.0 - beta2) * (1.0 - beta2));
     const bool vec = aligned16(acc_grad) && aligned16(delta_sum) && aligned16(mean) && aligned16(momentum) && aligned16(prec);
-    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        ivon_update_kernel<true><<<g.blocks, g.threads, 0, st>>>(acc_grad, delta_sum, mean, momentum, prec, D, c);
+        rc_ = launch_ew(ivon_update_kernel<true>, D, st, acc_grad, delta_sum, mean, momentum, prec, D, c);
     else
-        ivon_update_kernel<false><<<g.blocks, g.threads, 0, st>>>(acc_grad, delta_sum, mean, momentum, prec, D, c);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+        rc_ = launch_ew(ivon_update_kernel<false>, D, st, acc_grad, delta_sum, mean, momentum, prec, D, c);
+    return rc_;
 }

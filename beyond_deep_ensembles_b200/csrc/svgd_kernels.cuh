@@ -262,6 +262,161 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
 }
 
 // ---------------------------------------------------------------------------------
+// K1, TMA-staged: one persistent CTA per SM; a producer warp streams [N x TC]-column tiles of X
+// into a shared-memory ring with cp.async.bulk, consumer warps accumulate the pair distances of
+// one column quad per thread per tile.  Besides keeping ~200 KB per SM in flight, this leaves
+// only gridDim = #SMs partial sets for the deterministic last-CTA reduction.
+// ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int pd_tile_cols(int n) { return 1024 / pair_groups(n); }
+__host__ __device__ constexpr int pd_stage_bytes(int n) { return n * pd_tile_cols(n) * 4; }
+__host__ __device__ constexpr int pd_stages(int n) {
+    return (200 * 1024) / pd_stage_bytes(n) > 8 ? 8 : (200 * 1024) / pd_stage_bytes(n);
+}
+constexpr int kPdConsumers = 256;  // pair_groups(n) * pd_tile_cols(n) / 4
+constexpr int kFlushTiles = 64;
+
+template <int N, int G>
+__device__ __forceinline__ void pairdist_tma_consumer(const float* __restrict__ X, int64_t D, int64_t ld,
+                                                      const float* __restrict__ tiles, uint64_t* full_bar,
+                                                      uint64_t* empty_bar, double* __restrict__ wacc, int qi) {
+    constexpr int PG = pairs_per_group(N);
+    constexpr int TC = pd_tile_cols(N);
+    constexpr int STAGES = pd_stages(N);
+    f32x2 acc[PG > 0 ? PG : 1];
+#pragma unroll
+    for (int k = 0; k < PG; ++k) acc[k] = 0ull;
+    const int lane = threadIdx.x & 31;
+    const int64_t d4 = D & ~static_cast<int64_t>(3);
+    const int64_t ntiles = (d4 + TC - 1) / TC;
+    int it = 0, since_flush = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t use = static_cast<uint32_t>(it / STAGES);
+        const int64_t col0 = t * TC;
+        const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
+        mbar_wait(&full_bar[s], use & 1u);
+        const float* sx = tiles + static_cast<size_t>(s) * N * TC + 4 * qi;
+        V4 v[N];
+        if (4 * qi < w) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = lds_v4(sx + i * TC);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);  // data is in registers: release the stage
+        pair_accumulate<N, G>(v, acc);
+        if (++since_flush == kFlushTiles) {
+            flush_pairs<PG>(acc, wacc, lane);
+            since_flush = 0;
+        }
+    }
+    if (blockIdx.x == 0) {  // ragged tail columns (D % 4)
+        V4 v[N];
+        const int64_t c = d4 + qi;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            v[i].lo = (qi < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+            v[i].hi = 0ull;
+        }
+        pair_accumulate<N, G>(v, acc);
+    }
+    flush_pairs<PG>(acc, wacc, lane);
+}
+
+template <int N, int G>
+__device__ __forceinline__ void pairdist_tma_dispatch(int g, const float* X, int64_t D, int64_t ld, const float* tiles,
+                                                      uint64_t* full_bar, uint64_t* empty_bar, double* wacc, int qi) {
+    if (g == G) {
+        pairdist_tma_consumer<N, G>(X, D, ld, tiles, full_bar, empty_bar, wacc, qi);
+    } else {
+        if constexpr (G + 1 < pair_groups(N)) pairdist_tma_dispatch<N, G + 1>(g, X, D, ld, tiles, full_bar, empty_bar, wacc, qi);
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kPdConsumers + 32, 1)
+svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double* __restrict__ dist, int accumulate,
+                         void* ws, int fuse_bandwidth, BandwidthParams bp) {
+    constexpr int P = pair_count(N);
+    constexpr int PG = pairs_per_group(N);
+    constexpr int NG = pair_groups(N);
+    constexpr int TC = pd_tile_cols(N);
+    constexpr int QT = TC / 4;  // consumer threads per pair group
+    constexpr int STAGES = pd_stages(N);
+    constexpr int CWARPS = kPdConsumers / 32;
+    static_assert(NG * QT == kPdConsumers, "consumer layout");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][N][TC]
+    __shared__ double wacc[CWARPS][PG];
+    __shared__ double cta_vals[P];
+    __shared__ double total[P];
+    __shared__ double sd[N * N];
+    __shared__ double sk[N * N];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int nthreads = kPdConsumers + 32;
+    for (int k = tid; k < CWARPS * PG; k += nthreads) (&wacc[0][0])[k] = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (tid >= kPdConsumers) {
+        if (tid == kPdConsumers) {
+            const int64_t d4 = D & ~static_cast<int64_t>(3);
+            const int64_t ntiles = (d4 + TC - 1) / TC;
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                const uint32_t use = static_cast<uint32_t>(it / STAGES);
+                mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
+                const int64_t col0 = t * TC;
+                const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
+                const uint32_t row_bytes = static_cast<uint32_t>(w) * 4u;
+                mbar_arrive_expect_tx(&full_bar[s], N * row_bytes);
+                float* sx = tiles + static_cast<size_t>(s) * N * TC;
+#pragma unroll
+                for (int r = 0; r < N; ++r) tma_load_1d(sx + r * TC, X + r * ld + col0, row_bytes, &full_bar[s]);
+            }
+        }
+    } else {
+        const int g = tid / QT, qi = tid - g * QT;
+        pairdist_tma_dispatch<N, 0>(g, X, D, ld, tiles, full_bar, empty_bar, wacc[tid >> 5], qi);
+    }
+    __syncthreads();
+
+    // pair p of group grp is accumulated by that group's warps only
+    for (int p = tid; p < P; p += nthreads) {
+        const int grp = p / PG, k = p - grp * PG;
+        double sacc = 0.0;
+        for (int wv = grp * (QT / 32); wv < (grp + 1) * (QT / 32); ++wv) sacc += wacc[wv][k];
+        cta_vals[p] = sacc;
+    }
+    __syncthreads();
+    if (!grid_reduce_fp64(cta_vals, P, ws, total)) return;
+    for (int e = tid; e < N * N; e += nthreads) {
+        const int i = e / N, j = e - i * N;
+        double v = 0.0;
+        if (i != j) v = total[i < j ? pair_index(i, j, N) : pair_index(j, i, N)];
+        if (accumulate) v += dist[e];
+        dist[e] = v;
+    }
+    if (fuse_bandwidth) {
+        __syncthreads();
+        bandwidth_device(dist, N, bp, sd, sk);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------------
 __host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : 8; }
@@ -341,6 +496,136 @@ svgd_apply_kernel(const float* __restrict__ X, const float* __restrict__ G, floa
 }
 
 // ---------------------------------------------------------------------------------
+// K2, TMA-staged: a producer warp streams [N x TC]-column tiles of X and G into a ring of
+// shared-memory stages with cp.async.bulk (completion on mbarriers); the consumer warps
+// compute out = K G + A X for one column quad per thread straight from shared memory and
+// stream the result to HBM.  The loads are decoupled from the FFMA2 work, so the bytes in
+// flight per SM are set by the ring depth (~200 KB) instead of by register occupancy.
+// ---------------------------------------------------------------------------------
+__host__ __device__ constexpr int apply_tile_cols(int n) { return n <= 12 ? 512 : 256; }
+__host__ __device__ constexpr int apply_stage_bytes(int n) { return 2 * n * apply_tile_cols(n) * 4; }
+__host__ __device__ constexpr int apply_stages(int n) {
+    return (200 * 1024) / apply_stage_bytes(n) > 8 ? 8 : (200 * 1024) / apply_stage_bytes(n);
+}
+
+template <int N>
+__global__ void __launch_bounds__(apply_tile_cols(N) / 4 + 32, 1)
+svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ out,
+                      const float* __restrict__ K, const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg,
+                      int64_t ldo) {
+    constexpr int NP = (N + 3) & ~3;
+    constexpr int TC = apply_tile_cols(N);
+    constexpr int STAGES = apply_stages(N);
+    constexpr int CONSUMERS = TC / 4;  // threads; one column quad each
+    constexpr int CWARPS = CONSUMERS / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][2][N][TC]: X rows then G rows
+    __shared__ __align__(16) float sKT[N][NP];
+    __shared__ __align__(16) float sAT[N][NP];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    for (int e = tid; e < N * NP; e += blockDim.x) {
+        const int j = e / NP, i = e - j * NP;
+        sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
+        sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], CWARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t d4 = D & ~static_cast<int64_t>(3);
+    const int64_t ntiles = (d4 + TC - 1) / TC;
+    const bool is_producer = tid >= CONSUMERS;
+
+    if (is_producer) {
+        if (tid == CONSUMERS) {  // one elected lane drives the copy engine
+            int it = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+                const int s = it % STAGES;
+                const uint32_t use = static_cast<uint32_t>(it / STAGES);
+                mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
+                const int64_t col0 = t * TC;
+                const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
+                const uint32_t row_bytes = static_cast<uint32_t>(w) * 4u;
+                mbar_arrive_expect_tx(&full_bar[s], 2u * N * row_bytes);
+                float* sx = tiles + static_cast<size_t>(s) * 2 * N * TC;
+                float* sg = sx + N * TC;
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    tma_load_1d(sx + r * TC, X + r * ldx + col0, row_bytes, &full_bar[s]);
+                    tma_load_1d(sg + r * TC, G + r * ldg + col0, row_bytes, &full_bar[s]);
+                }
+            }
+        }
+    } else {
+        const int lane = tid & 31;
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t use = static_cast<uint32_t>(it / STAGES);
+            const int64_t col0 = t * TC;
+            const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
+            const bool active = 4 * tid < w;
+            mbar_wait(&full_bar[s], use & 1u);
+            const float* sx = tiles + static_cast<size_t>(s) * 2 * N * TC + 4 * tid;
+            const float* sg = sx + N * TC;
+            f32x2 acc[N][2];
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc[i][0] = acc[i][1] = 0ull;
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const V4 g = lds_v4(sg + j * TC);
+                    const V4 x = lds_v4(sx + j * TC);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const float kij = sKT[j][i];
+                        const float aij = sAT[j][i];
+                        acc[i][0] = fma2s(kij, g.lo, acc[i][0]);
+                        acc[i][1] = fma2s(kij, g.hi, acc[i][1]);
+                        acc[i][0] = fma2s(aij, x.lo, acc[i][0]);
+                        acc[i][1] = fma2s(aij, x.hi, acc[i][1]);
+                    }
+                }
+            }
+            // this warp is done reading the stage: hand it back to the producer, then store
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (active) {
+                float* op = out + col0 + 4 * tid;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    V4 o;
+                    o.lo = acc[i][0];
+                    o.hi = acc[i][1];
+                    stg_stream_v4(op + i * ldo, o);
+                }
+            }
+        }
+        // ragged tail columns (D % 4), CTA 0 only
+        if (blockIdx.x == 0 && tid < (D & 3)) {
+            const int64_t c = d4 + tid;
+            for (int i = 0; i < N; ++i) {
+                float sacc = 0.0f;
+                for (int j = 0; j < N; ++j) {
+                    sacc = fmaf(sKT[j][i], __ldg(G + j * ldg + c), sacc);
+                    sacc = fmaf(sAT[j][i], __ldg(X + j * ldx + c), sacc);
+                }
+                out[i * ldo + c] = sacc;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------------
 template <int N>
@@ -348,6 +633,27 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
                     const BandwidthParams& bp, cudaStream_t st) {
     constexpr int TPB = pairdist_tpb(N);
     constexpr int NG = pair_groups(N);
+    if constexpr (N <= 12) {
+        constexpr int TC = pd_tile_cols(N);
+        const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
+        int variant = tuning().pairdist_variant;
+        if (variant == 0) variant = (ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+        if (variant == 2) {
+            constexpr int smem = pd_stages(N) * pd_stage_bytes(N);
+            static bool configured = false;
+            if (!configured) {
+                BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_pairdist_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                configured = true;
+            }
+            int64_t grid = sm_count_cached();
+            if (grid > ntiles) grid = ntiles;
+            if (grid < 1) grid = 1;
+            svgd_pairdist_tma_kernel<N><<<static_cast<unsigned>(grid), kPdConsumers + 32, smem, st>>>(X, D, ld, dist, accumulate,
+                                                                                                 ws, fuse, bp);
+            BDE_CHECK_LAUNCH();
+            return BDE_OK;
+        }
+    }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int v = 0;
@@ -371,13 +677,33 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
 template <int N>
 int launch_apply(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
                  int64_t ldg, int64_t ldo, cudaStream_t st) {
+    const int64_t nquads = D >> 2;
+    constexpr int TC = apply_tile_cols(N);
+    const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
+    int variant = tuning().apply_variant;
+    // auto: the staged kernel wins once every SM has a few tiles; for N > 12 (two consumer warps per
+    // CTA at the 256-column tile) the direct kernel is still faster — measured, see DESIGN.md
+    if (variant == 0) variant = (N <= 12 && ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+    if (variant == 2) {
+        constexpr int smem = apply_stages(N) * apply_stage_bytes(N);
+        static bool configured = false;
+        if (!configured) {
+            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            configured = true;
+        }
+        int64_t grid = sm_count_cached();
+        if (grid > ntiles) grid = ntiles;
+        if (grid < 1) grid = 1;
+        svgd_apply_tma_kernel<N><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo);
+        BDE_CHECK_LAUNCH();
+        return BDE_OK;
+    }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int v = 0;
         BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N>, 128, 0));
         ctas_per_sm = v > 0 ? v : 1;
     }
-    const int64_t nquads = D >> 2;
     int64_t want = (nquads + 127) / 128;
     const int per_sm = tuning().apply_ctas_per_sm > 0 ? tuning().apply_ctas_per_sm : ctas_per_sm;
     const int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;

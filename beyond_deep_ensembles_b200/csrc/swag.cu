@@ -103,15 +103,14 @@ extern "C" int bde_swag_update(const float* theta, float* mean, float* sq, float
     if (!theta || !mean || !sq || !dev_row || D < 0 || updates < 1) return BDE_ERR_INVALID_ARG;
     if (D == 0) return BDE_OK;
     const bool vec = aligned16(theta) && aligned16(mean) && aligned16(sq) && aligned16(dev_row);
-    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
     const float fu = static_cast<float>(updates), fu1 = static_cast<float>(updates + 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        swag_update_kernel<true><<<g.blocks, g.threads, 0, st>>>(theta, mean, sq, dev_row, D, fu, fu1);
+        rc_ = launch_ew(swag_update_kernel<true>, D, st, theta, mean, sq, dev_row, D, fu, fu1);
     else
-        swag_update_kernel<false><<<g.blocks, g.threads, 0, st>>>(theta, mean, sq, dev_row, D, fu, fu1);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+        rc_ = launch_ew(swag_update_kernel<false>, D, st, theta, mean, sq, dev_row, D, fu, fu1);
+    return rc_;
 }
 
 extern "C" int bde_swag_sample(const float* mean, const float* sq, const float* dev, int K, int head, int64_t D,
@@ -123,15 +122,14 @@ extern "C" int bde_swag_sample(const float* mean, const float* sq, const float* 
     if (D == 0) return BDE_OK;
     const bool vec = aligned16(mean) && aligned16(sq) && aligned16(dev) && aligned16(theta) && (ld % 4 == 0) &&
                      (!eps_d || aligned16(eps_d));
-    const EwGrid g = ew_grid(D, kEwThreads, kEwCtasPerSm);
     const float den = static_cast<float>(sqrt(2.0 * (K - 1)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc_;
     if (vec)
-        swag_sample_kernel<true, 5><<<g.blocks, g.threads, 0, st>>>(mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
+        rc_ = launch_ew(swag_sample_kernel<true, 5>, D, st, mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
                                                                     stream_id, elem0 >> 2, den, theta);
     else
-        swag_sample_kernel<false, 5><<<g.blocks, g.threads, 0, st>>>(mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
+        rc_ = launch_ew(swag_sample_kernel<false, 5>, D, st, mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
                                                                      stream_id, elem0 >> 2, den, theta);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return rc_;
 }

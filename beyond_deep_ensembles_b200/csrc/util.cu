@@ -102,6 +102,8 @@ extern "C" int bde_tune(const char* key, int value) {
     if (k == "pairdist_ctas_per_sm") tuning().pairdist_ctas_per_sm = value;
     else if (k == "apply_ctas_per_sm") tuning().apply_ctas_per_sm = value;
     else if (k == "ew_ctas_per_sm") tuning().ew_ctas_per_sm = value;
+    else if (k == "apply_variant") tuning().apply_variant = value;
+    else if (k == "pairdist_variant") tuning().pairdist_variant = value;
     else return BDE_ERR_INVALID_ARG;
     return BDE_OK;
 }
@@ -136,11 +138,8 @@ extern "C" int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint6
                                  bde_stream_t stream) {
     if (!out || count < 0 || elem0 < 0 || (elem0 & 3)) return BDE_ERR_INVALID_ARG;
     if (count == 0) return BDE_OK;
-    const EwGrid g = ew_grid(count, kEwThreads, kEwCtasPerSm);
-    philox_normal_kernel<<<g.blocks, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(out, count, seed, stream_id,
-                                                                                       elem0 >> 2, aligned16(out) ? 1 : 0);
-    BDE_CHECK_LAUNCH();
-    return BDE_OK;
+    return launch_ew(philox_normal_kernel, count, static_cast<cudaStream_t>(stream), out, count, seed, stream_id,
+                     elem0 >> 2, aligned16(out) ? 1 : 0);
 }
 
 extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
@@ -162,9 +161,9 @@ extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, con
         tab.begin = tab.off[0];
         tab.end = tab.off[tab.count - 1] + tab.size[tab.count - 1];
         if (tab.end <= tab.begin) continue;
-        const EwGrid g = ew_grid(tab.end - (tab.begin & ~static_cast<int64_t>(3)), kEwThreads, kEwCtasPerSm);
-        multi_tensor_copy_kernel<<<g.blocks, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(flat, tab, mode);
-        BDE_CHECK_LAUNCH();
+        const int rc = launch_ew(multi_tensor_copy_kernel, tab.end - (tab.begin & ~static_cast<int64_t>(3)),
+                                 static_cast<cudaStream_t>(stream), flat, tab, mode);
+        if (rc != BDE_OK) return rc;
     }
     return BDE_OK;
 }

@@ -284,9 +284,9 @@ def philox_normal(count: int, seed: int, stream_id: int, elem0: int = 0) -> np.n
     def bm(r0, r1):
         u = (r0 >> np.uint32(8)).astype(np.float64) * 2.0 ** -24 + 2.0 ** -25
         u = u.astype(np.float32).astype(np.float64)  # the kernel forms u with one fp32 FMA
-        ang = (r1 >> np.uint32(8)).astype(np.float64) * 2.0 ** -23  # 2*u2, exact in fp32
+        ang = (r1 >> np.uint32(8)).astype(np.float64) * (2.0 * np.pi * 2.0 ** -24) - np.pi  # uniform on [-pi, pi)
         rad = np.sqrt(-2.0 * np.log(u))
-        return rad * np.cos(np.pi * ang), rad * np.sin(np.pi * ang)
+        return rad * np.cos(ang), rad * np.sin(ang)
 
     z0, z1 = bm(r[:, 0], r[:, 1])
     z2, z3 = bm(r[:, 2], r[:, 3])

@@ -50,22 +50,38 @@ def main():
     res["torch_copy_big_GBps"] = 8 * n * D / ms / 1e6
     ms = timeit(lambda: big.sum())
     res["torch_sum_GBps"] = 4 * n * D / ms / 1e6
-    for c in (0, 1, 2, 3, 4, 6, 8):
+    h.bde_tune(b"pairdist_variant", 1)
+    for c in (0, 2, 3):
         h.bde_tune(b"pairdist_ctas_per_sm", c)
         ms = timeit(lambda: ops.svgd_pairdist(X, sc))
         res[f"pairdist_ctas{c}"] = {"ms": ms, "GBps": 4 * n * D / ms / 1e6}
     h.bde_tune(b"pairdist_ctas_per_sm", 0)
+    for variant in (1, 2):
+        h.bde_tune(b"pairdist_variant", variant)
+        ms = timeit(lambda: ops.svgd_pairdist(X, sc))
+        res[f"pairdist_variant{variant}"] = {"ms": ms, "GBps": 4 * n * D / ms / 1e6}
+        ms = timeit(lambda: ops.svgd_pairdist_bandwidth(X, sc, 0.01, 1.0, 50000.0))
+        res[f"pairdist_bandwidth_variant{variant}"] = {"ms": ms, "GBps": 4 * n * D / ms / 1e6}
+    h.bde_tune(b"pairdist_variant", 0)
     ops.svgd_bandwidth(sc, 0.01, 1.0, 50000.0)
-    for c in (0, 1, 2, 3, 4, 5, 6, 8, 12, 16):
+    h.bde_tune(b"apply_variant", 1)
+    for c in (0, 4, 8):
         h.bde_tune(b"apply_ctas_per_sm", c)
         ms = timeit(lambda: ops.svgd_apply(X, G, out, sc))
         res[f"apply_ctas{c}"] = {"ms": ms, "GBps": 12 * n * D / ms / 1e6}
     h.bde_tune(b"apply_ctas_per_sm", 0)
+    for variant in (1, 2):
+        h.bde_tune(b"apply_variant", variant)
+        ms = timeit(lambda: ops.svgd_apply(X, G, out, sc))
+        res[f"apply_variant{variant}"] = {"ms": ms, "GBps": 12 * n * D / ms / 1e6}
+    h.bde_tune(b"apply_variant", 0)
+    ms = timeit(lambda: ops.svgd_step(X, G, out, sc, 0.01, 1.0, 50000.0))
+    res["svgd_step"] = {"ms": ms, "GBps": 16 * n * D / ms / 1e6}
     # elementwise family at a large D
     Dv = 64_000_000
     v = [torch.randn(Dv, device=dev) for _ in range(6)]
     v[1].abs_().add_(0.01)
-    for c in (0, 2, 4, 8, 16, 32):
+    for c in (0, 4, 5, 6, 8, 32):
         h.bde_tune(b"ew_ctas_per_sm", c)
         ms = timeit(lambda: ops.swag_update(v[0], v[2], v[3], v[4], 3))
         res[f"swag_update_ctas{c}"] = {"ms": ms, "GBps": 24 * Dv / ms / 1e6}
@@ -75,6 +91,9 @@ def main():
         res[f"ivon_sample_injected_ctas{c}"] = {"ms": ms, "GBps": 24 * Dv / ms / 1e6}
         ms = timeit(lambda: ops.ivon_accumulate(v[4], v[0], first=False))
         res[f"ivon_accumulate_ctas{c}"] = {"ms": ms, "GBps": 12 * Dv / ms / 1e6}
+        ms = timeit(lambda: ops.ivon_update(v[0], v[4], v[2], v[3], v[1], mc_samples=2, step=3, lr=1e-5, beta1=0.9,
+                                            beta2=0.999, prior_prec=10.0, n_eff=1000.0, tempering=1.0, damping=1e-3))
+        res[f"ivon_update_ctas{c}"] = {"ms": ms, "GBps": 32 * Dv / ms / 1e6}
     h.bde_tune(b"ew_ctas_per_sm", 0)
     for k, val in res.items():
         print(k, json.dumps(val))
