@@ -228,7 +228,7 @@ def other_paths(ops, peak_gbs, dev):
     prec = torch.rand(Dp, device=dev, generator=g) * 1e-4 + 10.0 / 269038   # mid-training state: all non-trivial
     mom = torch.randn(Dp, device=dev, generator=g) * 1e-4
     dsum = torch.randn(Dp, device=dev, generator=g) * 0.3
-    acc = torch.randn(Dp, device=dev, generator=g) * 2e-3
+    acc = torch.randn(Dp, device=dev, generator=g) * 2e-5   # small enough that the precision stays positive over the timed calls
     theta = torch.zeros(Dp, device=dev)
     grad = torch.randn(Dp, device=dev, generator=g) * 1e-3
     kw = dict(n_eff=269038.0)
@@ -447,10 +447,14 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "svgd_apply_kernel<10> (K2: out = K G + A X)",
+            "roofline": {"bound": "hbm", "kernel": "bde::svgd_apply_tma_kernel<10> (K2: out = K G + A X)",
                          "achieved": k2_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": k2_gbs / peak_gbs,
                          "peak_source": peak_src, "frac_of_nominal_8TBps": k2_gbs / 8000.0,
-                         "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms, "traffic": None},
+                         "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                         # at n=10, D=1e8 (profiles/r01_ncu_summary.md): 8.001 GB + 3.969 GB per launch
+                         "traffic": 11.970e9 * (D / 1e8) if n == 10 else None,
+                         "traffic_source": "profiles/r01_ncu_summary.md (prof_apply_tma.ncu-rep)"},
             "kernels": {
                 "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
                                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,
@@ -462,8 +466,14 @@ def main():
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
             "cpu_baseline": cpu_base, "paths": paths,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
+        try:
+            os.fsync(sys.stdout.fileno())
+        except OSError:
+            pass
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -19,11 +19,10 @@ def free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,n,D", [(2, 10, 5000), (3, 5, 1237)])
-def test_sharded_step_equals_unsharded(tmp_path, world, n, D):
+def check(tmp_path, world, n, D, backend):
     import dist_worker
     out_path = str(tmp_path / "shard")
-    mp.spawn(dist_worker.run, args=(world, free_port(), n, D, out_path), nprocs=world, join=True)
+    mp.spawn(dist_worker.run, args=(world, free_port(), n, D, out_path, backend), nprocs=world, join=True)
 
     g = torch.Generator().manual_seed(1234)
     X = torch.randn(n, D, generator=g) * (0.05 * (1 + 0.1 * torch.arange(n).float())).unsqueeze(1)
@@ -35,7 +34,22 @@ def test_sharded_step_equals_unsharded(tmp_path, world, n, D):
     full = torch.cat([p["out"] for p in parts], dim=1)
     np.testing.assert_allclose(full.numpy(), ref.numpy(), rtol=1e-5, atol=1e-6)
     for p in parts:
-        np.testing.assert_allclose(p["dist"].numpy(), d_ref.numpy(), rtol=1e-12)  # summed partials
+        np.testing.assert_allclose(p["dist"].numpy(), d_ref.numpy(), rtol=1e-12 if backend == "gloo" else 2e-6)  # summed partials
         assert tuple(p["sel"].tolist()) == info["sel"]
         assert torch.equal(p["K"], parts[0]["K"])  # K1b is redundant and identical on every rank
-        assert p["calls"] == ["pairdist", "bandwidth", "apply"]  # the unfused 3-kernel form when sharded
+        if backend == "gloo":
+            assert p["calls"] == ["pairdist", "bandwidth", "apply"]  # the unfused 3-kernel form when sharded
+
+
+@pytest.mark.parametrize("world,n,D", [(2, 10, 5000), (3, 5, 1237)])
+def test_sharded_step_equals_unsharded(tmp_path, world, n, D):
+    check(tmp_path, world, n, D, "gloo")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n,D", [(2, 10, 1_000_003), (2, 20, 273_610)])
+def test_sharded_step_nccl(tmp_path, world, n, D):
+    """The same on real GPUs over NCCL (needs >= 2 devices; skipped on a single-GPU box)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    check(tmp_path, world, n, D, "nccl")
