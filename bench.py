@@ -235,6 +235,10 @@ def other_paths(ops, peak_gbs, dev):
     rec("ivon_sample", time_kernel(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=1, stream_id=3, **kw), 20, 3),
         20 * Dp, f"DistilBERT D={D}, Philox noise")
     rec("ivon_accumulate", time_kernel(lambda: ops.ivon_accumulate(acc, grad, first=False), 20, 3), 12 * Dp, f"D={D}")
+    # the two timing loops above accumulated 23 samples / gradients into dsum and acc: put a
+    # mid-training state back so that the update runs on realistic magnitudes (finite everywhere)
+    dsum.normal_(0.0, 0.3, generator=g)
+    acc.normal_(0.0, 2e-5, generator=g)
     step = [0]
 
     def ivon_upd():

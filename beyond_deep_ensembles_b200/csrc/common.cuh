@@ -42,6 +42,7 @@ struct Tuning {
     int ew_ctas_per_sm = 0;
     int apply_variant = 0;     // 0 auto, 1 direct-LDG kernel, 2 TMA-staged kernel
     int pairdist_variant = 0;  // same for K1
+    int ew_variant = 0;        // same for the elementwise family (ew_tma.cuh)
 };
 Tuning& tuning();
 
@@ -237,8 +238,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const unsigned int hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-        const unsigned int hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        // one IMAD.WIDE.U32 per product (hi and lo halves together); the key schedule is uniform
+        const unsigned long long p0 = static_cast<unsigned long long>(M0) * ctr.x;
+        const unsigned long long p1 = static_cast<unsigned long long>(M1) * ctr.z;
+        const unsigned int hi0 = static_cast<unsigned int>(p0 >> 32), lo0 = static_cast<unsigned int>(p0);
+        const unsigned int hi1 = static_cast<unsigned int>(p1 >> 32), lo1 = static_cast<unsigned int>(p1);
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
         key.x += W0;
         key.y += W1;
@@ -251,13 +255,24 @@ __device__ __forceinline__ float u01_open(unsigned int r) {
     return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
 }
 
-// Box-Muller on the SFU: radius from MUFU.LG2, angle uniform on [-pi, pi) where MUFU.SIN/COS
-// are accurate to 2^-21.4 absolute.  (Noise quality, not reference parity: parity tests inject
-// the reference's own noise.)
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.RSQ, ~1 ulp
+    return r;
+}
+
+// Box-Muller on the SFU: radius from MUFU.LG2 + MUFU.SQRT, angle uniform on [-pi, pi) where
+// MUFU.SIN/COS are accurate to 2^-21.4 absolute.  (Noise quality, not reference parity: parity
+// tests inject the reference's own noise.)
 __device__ __forceinline__ void box_muller(unsigned int r0, unsigned int r1, float& z0, float& z1) {
     const float u = u01_open(r0);
     const float ang = fmaf(static_cast<float>(r1 >> 8), 3.7450702829239286e-07f, -3.14159265358979323846f);
-    const float rad = sqrtf(fmaxf(-1.3862943611198906f * __log2f(u), 0.0f));  // sqrt(-2 ln u)
+    const float rad = sqrt_approx(fmaxf(-1.3862943611198906f * __log2f(u), 0.0f));  // sqrt(-2 ln u)
     z0 = rad * __cosf(ang);
     z1 = rad * __sinf(ang);
 }

@@ -2,7 +2,7 @@
 // Reference arithmetic: src/algos/swag.py:91-114 and torch LowRankMultivariateNormal.rsample.
 // Operation order and rounding follow the reference op by op (explicit *_rn intrinsics, no
 // FMA contraction) so that the update matches eager fp32 PyTorch.
-#include "elementwise.cuh"
+#include "ew_tma.cuh"
 
 namespace bde {
 
@@ -29,6 +29,21 @@ swag_update_kernel(const float* __restrict__ theta, float* __restrict__ mean, fl
         store_quad<VEC>(dev_row, b, D, dv);
     }
 }
+
+// K3, TMA-staged (ew_tma.cuh): inputs theta, mean, sq; outputs mean, sq, dev_row
+struct SwagUpdateOp {
+    static constexpr int NIN = 3, NOUT = 3;
+    float fu, fu1;
+    __device__ __forceinline__ void operator()(const float4 (&in)[NIN], float4 (&out)[NOUT], int64_t) const {
+        const float4 t = in[0], m = in[1], s = in[2];
+        auto upd_mean = [&](float mv, float tv) { return __fdiv_rn(__fadd_rn(__fmul_rn(fu, mv), tv), fu1); };
+        auto upd_sq = [&](float sv, float tv) { return __fdiv_rn(__fadd_rn(__fmul_rn(fu, sv), __fmul_rn(tv, tv)), fu1); };
+        const float4 mn = BDE_LANES(upd_mean(m.x, t.x), upd_mean(m.y, t.y), upd_mean(m.z, t.z), upd_mean(m.w, t.w));
+        out[0] = mn;
+        out[1] = BDE_LANES(upd_sq(s.x, t.x), upd_sq(s.y, t.y), upd_sq(s.z, t.z), upd_sq(s.w, t.w));
+        out[2] = BDE_LANES(__fsub_rn(t.x, mn.x), __fsub_rn(t.y, mn.y), __fsub_rn(t.z, mn.z), __fsub_rn(t.w, mn.w));
+    }
+};
 
 // K4 ------------------------------------------------------------------------------------
 constexpr int kMaxSwagRank = 256;
@@ -105,6 +120,16 @@ extern "C" int bde_swag_update(const float* theta, float* mean, float* sq, float
     const bool vec = aligned16(theta) && aligned16(mean) && aligned16(sq) && aligned16(dev_row);
     const float fu = static_cast<float>(updates), fu1 = static_cast<float>(updates + 1);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_ew_tma(D, vec, false)) {
+        EwPtrs<3, 3> p;
+        p.in[0] = theta;
+        p.in[1] = mean;
+        p.in[2] = sq;
+        p.out[0] = mean;
+        p.out[1] = sq;
+        p.out[2] = dev_row;
+        return launch_ew_tma<SwagUpdateOp>(p, D, SwagUpdateOp{fu, fu1}, nullptr, st);
+    }
     int rc_;
     if (vec)
         rc_ = launch_ew(swag_update_kernel<true>, D, st, theta, mean, sq, dev_row, D, fu, fu1);

@@ -104,6 +104,7 @@ extern "C" int bde_tune(const char* key, int value) {
     else if (k == "ew_ctas_per_sm") tuning().ew_ctas_per_sm = value;
     else if (k == "apply_variant") tuning().apply_variant = value;
     else if (k == "pairdist_variant") tuning().pairdist_variant = value;
+    else if (k == "ew_variant") tuning().ew_variant = value;
     else return BDE_ERR_INVALID_ARG;
     return BDE_OK;
 }

@@ -247,9 +247,17 @@ def test_svgd_full_size_properties(ops, D):
     np.testing.assert_allclose(sc.dist.cpu().numpy(), d[perm][:, perm].cpu().numpy(), rtol=1e-12)
 
 
+@pytest.fixture(params=[1, 2], ids=["direct", "tma"])
+def ew_variant(request, cuda_lib):
+    """Force the direct-LDG (1) or the TMA-staged (2) form of the elementwise kernels (ew_tma.cuh)."""
+    assert cuda_lib.bde_tune(b"ew_variant", request.param) == 0
+    yield request.param
+    cuda_lib.bde_tune(b"ew_variant", 0)
+
+
 # ---------------------------------------------------------------- SWAG
-@pytest.mark.parametrize("D,K", [(501, 4), (4099, 10), (1 << 20, 10), (1237, 1), (1_000_003, 30)])
-def test_swag_update_and_sample_vs_oracle(ops, D, K):
+@pytest.mark.parametrize("D,K", [(501, 4), (4099, 10), (1 << 20, 10), (1237, 1), (1_000_003, 30), (3, 2), (2_500_001, 3)])
+def test_swag_update_and_sample_vs_oracle(ops, ew_variant, D, K):
     g = torch.Generator().manual_seed(D + K)
     mean = torch.randn(D, generator=g) * 0.3
     sq = mean ** 2 + 0.01 * torch.rand(D, generator=g)
@@ -314,12 +322,12 @@ def test_swag_sample_philox_is_shard_independent(ops):
 
 
 # ---------------------------------------------------------------- iVON
-@pytest.mark.parametrize("D", [501, 4099, 1 << 20, 1_000_003])
-def test_ivon_kernels_vs_oracle(ops, D):
+@pytest.mark.parametrize("D", [501, 4099, 1 << 20, 1_000_003, 2, 2_500_001])
+def test_ivon_kernels_vs_oracle(ops, ew_variant, D):
     g = torch.Generator().manual_seed(D)
     mean = 0.3 * torch.randn(D, generator=g)
     prec = 10.0 / 768 + 0.01 * torch.rand(D, generator=g)
-    prec[:3] = torch.tensor([1e-6, 1e-4, 0.0])  # below / at the clamp
+    prec[:min(3, D)] = torch.tensor([1e-6, 1e-4, 0.0])[:D]  # below / at the clamp
     mom = 0.01 * torch.randn(D, generator=g)
     N, S = 768.0, 3
     d_mean, d_prec, d_mom = mean.cuda(), prec.cuda(), mom.cuda()
@@ -347,7 +355,7 @@ def test_ivon_kernels_vs_oracle(ops, D):
     assert torch.equal(d_theta, d_mean) and d_dsum.eq(0).all()
 
 
-def test_ivon_sample_philox_matches_oracle_stream(ops):
+def test_ivon_sample_philox_matches_oracle_stream(ops, ew_variant):
     D = 100_003
     mean = torch.zeros(D, device="cuda")
     prec = torch.full((D,), 1.0 / 768, device="cuda")
