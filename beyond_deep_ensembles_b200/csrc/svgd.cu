@@ -74,6 +74,43 @@ svgd_apply_scalar_kernel(const float* __restrict__ X, const float* __restrict__ 
     }
 }
 
+// fused K2 + base-optimizer step, generic form (runtime n, any alignment): one column per thread
+template <int OPT>
+__global__ void __launch_bounds__(256)
+svgd_apply_opt_scalar_kernel(float* X, const float* __restrict__ G, const float* __restrict__ K,
+                             const float* __restrict__ A, int n, int64_t D, int64_t ldx, int64_t ldg,
+                             const __grid_constant__ BaseOptParams o) {
+    __shared__ float sK[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    __shared__ float sA[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        sK[e] = K[e];
+        sA[e] = A[e];
+    }
+    __syncthreads();
+    const bool has_s0 = (OPT == kOptAdam) || (o.momentum != 0.0f && o.buf_initialized);
+    for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < D;
+         c += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float xs[BDE_MAX_PARTICLES], gs[BDE_MAX_PARTICLES];
+        for (int j = 0; j < n; ++j) {
+            xs[j] = X[j * ldx + c];
+            gs[j] = __ldg(G + j * ldg + c);
+        }
+        float s0 = has_s0 ? o.state0[c] : 0.0f;
+        float s1 = (OPT == kOptAdam) ? o.state1[c] : 0.0f;
+        for (int i = 0; i < n; ++i) {
+            float s = 0.0f;
+            for (int j = 0; j < n; ++j) {
+                s = fmaf(sK[i * n + j], gs[j], s);
+                s = fmaf(sA[i * n + j], xs[j], s);
+            }
+            if (i == n - 1 && o.out_last) o.out_last[c] = s;
+            X[i * ldx + c] = opt_update_scalar<OPT>(o, i, s, xs[i], s0, s1);
+        }
+        if (OPT == kOptAdam || o.momentum != 0.0f) o.state0[c] = s0;
+        if (OPT == kOptAdam) o.state1[c] = s1;
+    }
+}
+
 // particle counts with a register-resident fast path (explicitly instantiated in svgd_inst_*.cu);
 // any other n <= BDE_MAX_PARTICLES runs the generic runtime-n kernels.
 #define BDE_FOR_EACH_N(X_) X_(2) X_(3) X_(4) X_(5) X_(6) X_(7) X_(8) X_(9) X_(10) X_(11) X_(12) X_(16) X_(20)
@@ -82,7 +119,9 @@ svgd_apply_scalar_kernel(const float* __restrict__ X, const float* __restrict__ 
     extern template int launch_pairdist<N_>(const float*, int64_t, int64_t, double*, int, void*, int,              \
                                             const BandwidthParams&, cudaStream_t);                                 \
     extern template int launch_apply<N_>(const float*, const float*, float*, const float*, const float*, int64_t, \
-                                         int64_t, int64_t, int64_t, cudaStream_t);
+                                         int64_t, int64_t, int64_t, cudaStream_t);                           \
+    extern template int launch_apply_fused<N_>(float*, const float*, const float*, const float*, int64_t, int64_t, \
+                                               int64_t, const BaseOptParams&, cudaStream_t);
 BDE_FOR_EACH_N(X_)
 #undef X_
 
@@ -172,6 +211,41 @@ int apply_impl(const float* X, const float* G, float* out, const float* K, const
     }
 }
 
+int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ldx,
+                   int64_t ldg, const BaseOptParams& o, cudaStream_t st) {
+    if (!X || !G || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ldx < D || ldg < D) return BDE_ERR_INVALID_ARG;
+    if (o.kind != kOptSgd && o.kind != kOptAdam) return BDE_ERR_INVALID_ARG;
+    const bool needs_s0 = o.kind == kOptAdam || o.momentum != 0.0f;
+    if ((needs_s0 && !o.state0) || (o.kind == kOptAdam && !o.state1)) return BDE_ERR_INVALID_ARG;
+    if (D == 0) return BDE_OK;
+    const size_t span_x = sizeof(float) * (static_cast<size_t>(n - 1) * ldx + D);
+    const size_t span_g = sizeof(float) * (static_cast<size_t>(n - 1) * ldg + D);
+    if (overlaps(X, span_x, G, span_g)) return BDE_ERR_INVALID_ARG;
+    const bool vec_ok = aligned16(X) && aligned16(G) && (ldx % 4 == 0) && (ldg % 4 == 0) &&
+                        (!needs_s0 || aligned16(o.state0)) && (o.kind != kOptAdam || aligned16(o.state1)) &&
+                        (!o.out_last || aligned16(o.out_last));
+    if (!vec_ok || !has_fast_path(n)) {
+        int64_t want = (D + 255) / 256;
+        const int64_t cap = static_cast<int64_t>(sm_count_cached()) * 4;
+        if (want > cap) want = cap;
+        if (o.kind == kOptSgd)
+            svgd_apply_opt_scalar_kernel<kOptSgd><<<static_cast<unsigned>(want), 256, 0, st>>>(X, G, K, A, n, D, ldx, ldg, o);
+        else
+            svgd_apply_opt_scalar_kernel<kOptAdam><<<static_cast<unsigned>(want), 256, 0, st>>>(X, G, K, A, n, D, ldx, ldg, o);
+        BDE_CHECK_LAUNCH();
+        return BDE_OK;
+    }
+    switch (n) {
+#define X_(N_) \
+    case N_:   \
+        return launch_apply_fused<N_>(X, G, K, A, D, ldx, ldg, o, st);
+        BDE_FOR_EACH_N(X_)
+#undef X_
+        default:
+            return BDE_ERR_UNSUPPORTED_N;
+    }
+}
+
 }  // namespace bde
 
 using namespace bde;
@@ -224,4 +298,49 @@ extern "C" int bde_svgd_step(const float* X, const float* G, float* out, int n, 
     int rc = pairdist_impl(X, n, D, ld, dist, 0, workspace, workspace_bytes, 1, bp, st);
     if (rc != BDE_OK) return rc;
     return apply_impl(X, G, out, K, A, n, D, ld, ld, ld, st);
+}
+
+extern "C" int bde_svgd_apply_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
+                                  float* momentum_buf, int buf_initialized, double lr, double momentum, double dampening,
+                                  double weight_decay, int nesterov, float* out_last, bde_stream_t stream) {
+    BaseOptParams o;
+    o.kind = kOptSgd;
+    o.lr = static_cast<float>(lr);
+    o.momentum = static_cast<float>(momentum);
+    o.one_minus_dampening = static_cast<float>(1.0 - dampening);
+    o.weight_decay = static_cast<float>(weight_decay);
+    o.nesterov = nesterov ? 1 : 0;
+    o.buf_initialized = buf_initialized ? 1 : 0;
+    o.state0 = momentum_buf;
+    o.out_last = out_last;
+    return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bde_svgd_apply_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
+                                   float* exp_avg, float* exp_avg_sq, int64_t step0, double lr, double beta1,
+                                   double beta2, double eps, double weight_decay, int decoupled_weight_decay,
+                                   float* out_last, bde_stream_t stream) {
+    if (n < 1 || n > BDE_MAX_PARTICLES || step0 < 0) return BDE_ERR_INVALID_ARG;
+    BaseOptParams o;
+    o.kind = kOptAdam;
+    o.lr = static_cast<float>(lr);
+    o.beta1 = static_cast<float>(beta1);
+    o.one_minus_beta1 = static_cast<float>(1.0 - beta1);
+    o.beta2 = static_cast<float>(beta2);
+    o.one_minus_beta2 = static_cast<float>(1.0 - beta2);
+    o.eps = static_cast<float>(eps);
+    o.weight_decay = static_cast<float>(weight_decay);
+    o.decoupled_wd = decoupled_weight_decay ? 1 : 0;
+    o.decay_factor = static_cast<float>(1.0 - lr * weight_decay);
+    for (int i = 0; i < n; ++i) {
+        // python-side scalars of _single_tensor_adam, folded in double like eager PyTorch does
+        const double t = static_cast<double>(step0 + i + 1);
+        const double bc1 = 1.0 - pow(beta1, t), bc2 = 1.0 - pow(beta2, t);
+        o.step_size[i] = static_cast<float>(lr / bc1);
+        o.inv_bc2_sqrt[i] = static_cast<float>(1.0 / sqrt(bc2));
+    }
+    o.state0 = exp_avg;
+    o.state1 = exp_avg_sq;
+    o.out_last = out_last;
+    return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream));
 }

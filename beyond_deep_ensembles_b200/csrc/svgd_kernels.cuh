@@ -417,15 +417,132 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
 }
 
 // ---------------------------------------------------------------------------------
-// K2
+// K2 (+ optional fused base-optimizer step, f1)
 // ---------------------------------------------------------------------------------
 __host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : 8; }
 
-template <int N>
+__device__ __forceinline__ f32x2 mul2s(float s, f32x2 b) {
+    f32x2 r;
+    const f32x2 a = pack2(s, s);
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ V4 ld_coherent_v4(const float* p) {
+    V4 v;
+    asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "l"(p));
+    return v;
+}
+
+// torch.optim.SGD._single_tensor_sgd on two columns of particle `first`..: g is the new gradient
+// (out_i), x the particle value, b the shared momentum buffer.
+__device__ __forceinline__ void sgd_update2(const BaseOptParams& o, bool clone_buf, f32x2 g, f32x2& x, f32x2& b) {
+    if (o.weight_decay != 0.0f) g = fma2s(o.weight_decay, x, g);           // grad.add(param, alpha=wd)
+    if (o.momentum != 0.0f) {
+        if (clone_buf)
+            b = g;                                                          // buf = clone(grad)
+        else
+            b = fma2s(o.one_minus_dampening, g, mul2s(o.momentum, b));      // buf.mul_(m).add_(grad, alpha=1-damp)
+        g = o.nesterov ? fma2s(o.momentum, b, g) : b;
+    }
+    x = fma2s(-o.lr, g, x);                                                 // param.add_(grad, alpha=-lr)
+}
+
+// torch.optim.Adam / AdamW (_single_tensor_adam, no amsgrad) for particle i = optimizer step step0+i+1.
+// sqrt and the final division run on the SFU (MUFU.SQRT / MUFU.RCP, ~1 ulp each; the update is a small
+// correction to x, so the result stays far inside rtol 1e-5 of eager PyTorch).
+__device__ __forceinline__ float adam_update1(const BaseOptParams& o, int i, float g, float x, float& m, float& v) {
+    if (o.weight_decay != 0.0f) {
+        if (o.decoupled_wd)
+            x = x * o.decay_factor;                                         // param.mul_(1 - lr*wd)
+        else
+            g = fmaf(o.weight_decay, x, g);
+    }
+    m = fmaf(o.one_minus_beta1, g - m, m);                                  // exp_avg.lerp_(grad, 1-beta1)
+    v = fmaf(o.one_minus_beta2 * g, g, o.beta2 * v);                        // mul_(beta2).addcmul_(g, g, 1-beta2)
+    const float denom = fmaf(sqrt_approx(v), o.inv_bc2_sqrt[i], o.eps);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(denom));
+    return fmaf(-o.step_size[i] * m, r, x);                                 // param.addcdiv_(m, denom, -step_size)
+}
+__device__ __forceinline__ void adam_update2(const BaseOptParams& o, int i, f32x2 g, f32x2& x, f32x2& m, f32x2& v) {
+    float g0, g1, x0, x1, m0, m1, v0, v1;
+    unpack2(g, g0, g1);
+    unpack2(x, x0, x1);
+    unpack2(m, m0, m1);
+    unpack2(v, v0, v1);
+    x0 = adam_update1(o, i, g0, x0, m0, v0);
+    x1 = adam_update1(o, i, g1, x1, m1, v1);
+    x = pack2(x0, x1);
+    m = pack2(m0, m1);
+    v = pack2(v0, v1);
+}
+
+// one particle's optimizer step on a column quad; s0 / s1 are the shared state quads
+template <int OPT>
+__device__ __forceinline__ void opt_update_quad(const BaseOptParams& o, int i, f32x2 g_lo, f32x2 g_hi, V4& x, V4& s0, V4& s1) {
+    if constexpr (OPT == kOptSgd) {
+        const bool clone_buf = (i == 0) && !o.buf_initialized;
+        sgd_update2(o, clone_buf, g_lo, x.lo, s0.lo);
+        sgd_update2(o, clone_buf, g_hi, x.hi, s0.hi);
+    } else if constexpr (OPT == kOptAdam) {
+        adam_update2(o, i, g_lo, x.lo, s0.lo, s1.lo);
+        adam_update2(o, i, g_hi, x.hi, s0.hi, s1.hi);
+    }
+}
+__host__ __device__ constexpr int opt_state_rows(int opt) { return opt == kOptAdam ? 2 : (opt == kOptSgd ? 1 : 0); }
+
+// scalar (one column) form for ragged tails and the generic kernels
+template <int OPT>
+__device__ __forceinline__ float opt_update_scalar(const BaseOptParams& o, int i, float g, float x, float& s0, float& s1) {
+    if constexpr (OPT == kOptSgd) {
+        if (o.weight_decay != 0.0f) g = fmaf(o.weight_decay, x, g);
+        if (o.momentum != 0.0f) {
+            if (i == 0 && !o.buf_initialized)
+                s0 = g;
+            else
+                s0 = fmaf(o.one_minus_dampening, g, o.momentum * s0);
+            g = o.nesterov ? fmaf(o.momentum, s0, g) : s0;
+        }
+        return fmaf(-o.lr, g, x);
+    } else {
+        return adam_update1(o, i, g, x, s0, s1);
+    }
+}
+
+// tail columns (D % 4) of the fused / plain K2: one thread per column
+template <int N, int OPT>
+__device__ __forceinline__ void apply_tail_column(const float* X, const float* G, float* out, const float (*sKT)[(N + 3) & ~3],
+                                                  const float (*sAT)[(N + 3) & ~3], int64_t c, int64_t ldx, int64_t ldg,
+                                                  int64_t ldo, const BaseOptParams& o) {
+    float res[N];
+    for (int i = 0; i < N; ++i) {
+        float sacc = 0.0f;
+        for (int j = 0; j < N; ++j) {
+            sacc = fmaf(sKT[j][i], G[j * ldg + c], sacc);
+            sacc = fmaf(sAT[j][i], X[j * ldx + c], sacc);
+        }
+        res[i] = sacc;
+    }
+    if constexpr (OPT == kOptNone) {
+        for (int i = 0; i < N; ++i) out[i * ldo + c] = res[i];
+    } else {
+        float* Xw = const_cast<float*>(X);
+        float s0 = 0.0f, s1 = 0.0f;
+        const bool has_s0 = (OPT == kOptAdam) || (o.momentum != 0.0f && o.buf_initialized);
+        if (has_s0) s0 = o.state0[c];
+        if (OPT == kOptAdam) s1 = o.state1[c];
+        if (o.out_last) o.out_last[c] = res[N - 1];
+        for (int i = 0; i < N; ++i) Xw[i * ldx + c] = opt_update_scalar<OPT>(o, i, res[i], X[i * ldx + c], s0, s1);
+        if (OPT == kOptAdam || o.momentum != 0.0f) o.state0[c] = s0;
+        if (OPT == kOptAdam) o.state1[c] = s1;
+    }
+}
+
+template <int N, int OPT>
 __global__ void __launch_bounds__(128)
-svgd_apply_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ out,
-                  const float* __restrict__ K, const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg,
-                  int64_t ldo) {
+svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
+                  const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
+                  const __grid_constant__ BaseOptParams o) {
     constexpr int NP = (N + 3) & ~3;
     constexpr int JC = apply_row_chunk(N);
     // transposed coefficients: sKT[j][i] = K[i][j] so that the i-loop reads contiguous words
@@ -453,7 +570,9 @@ svgd_apply_kernel(const float* __restrict__ X, const float* __restrict__ G, floa
             for (int jj = 0; jj < JC; ++jj) {
                 if (jc + jj < N) {
                     g[jj] = ldg_stream_v4(gp + (jc + jj) * ldg);
-                    x[jj] = ldg_stream_v4(xp + (jc + jj) * ldx);
+                    // fused form: X is rewritten by this kernel -> coherent loads (and L1 keeps the rows for
+                    // the re-read in the optimizer epilogue)
+                    x[jj] = (OPT == kOptNone) ? ldg_stream_v4(xp + (jc + jj) * ldx) : ld_coherent_v4(xp + (jc + jj) * ldx);
                 }
             }
 #pragma unroll
@@ -472,54 +591,74 @@ svgd_apply_kernel(const float* __restrict__ X, const float* __restrict__ G, floa
                 }
             }
         }
-        float* op = out + 4 * q;
+        if constexpr (OPT == kOptNone) {
+            float* op = out + 4 * q;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            V4 o;
-            o.lo = acc[i][0];
-            o.hi = acc[i][1];
-            stg_stream_v4(op + i * ldo, o);
+            for (int i = 0; i < N; ++i) {
+                V4 v;
+                v.lo = acc[i][0];
+                v.hi = acc[i][1];
+                stg_stream_v4(op + i * ldo, v);
+            }
+        } else {
+            float* xw = const_cast<float*>(xp);
+            V4 s0, s1;
+            s0.lo = s0.hi = s1.lo = s1.hi = 0ull;
+            const bool has_s0 = (OPT == kOptAdam) || (o.momentum != 0.0f && o.buf_initialized);
+            if (has_s0) s0 = ld_coherent_v4(o.state0 + 4 * q);
+            if (OPT == kOptAdam) s1 = ld_coherent_v4(o.state1 + 4 * q);
+            if (o.out_last) {
+                V4 v;
+                v.lo = acc[N - 1][0];
+                v.hi = acc[N - 1][1];
+                stg_stream_v4(o.out_last + 4 * q, v);
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                V4 x = ld_coherent_v4(xp + i * ldx);
+                opt_update_quad<OPT>(o, i, acc[i][0], acc[i][1], x, s0, s1);
+                stg_stream_v4(xw + i * ldx, x);
+            }
+            if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + 4 * q, s0);
+            if (OPT == kOptAdam) stg_stream_v4(o.state1 + 4 * q, s1);
         }
     }
     // ragged tail columns
-    if (blockIdx.x == 0 && threadIdx.x < (D & 3)) {
-        const int64_t c = 4 * nquads + threadIdx.x;
-        for (int i = 0; i < N; ++i) {
-            float s = 0.0f;
-            for (int j = 0; j < N; ++j) {
-                s = fmaf(sKT[j][i], __ldg(G + j * ldg + c), s);
-                s = fmaf(sAT[j][i], __ldg(X + j * ldx + c), s);
-            }
-            out[i * ldo + c] = s;
-        }
-    }
+    if (blockIdx.x == 0 && threadIdx.x < (D & 3))
+        apply_tail_column<N, OPT>(X, G, out, sKT, sAT, 4 * nquads + threadIdx.x, ldx, ldg, ldo, o);
 }
 
 // ---------------------------------------------------------------------------------
-// K2, TMA-staged: a producer warp streams [N x TC]-column tiles of X and G into a ring of
-// shared-memory stages with cp.async.bulk (completion on mbarriers); the consumer warps
-// compute out = K G + A X for one column quad per thread straight from shared memory and
-// stream the result to HBM.  The loads are decoupled from the FFMA2 work, so the bytes in
-// flight per SM are set by the ring depth (~200 KB) instead of by register occupancy.
+// K2, TMA-staged: a producer warp streams [N x TC]-column tiles of X and G (and, in the fused form,
+// the optimizer-state rows) into a ring of shared-memory stages with cp.async.bulk (completion on
+// mbarriers); the consumer warps compute out = K G + A X for one column quad per thread straight
+// from shared memory and stream the result to HBM.  The loads are decoupled from the FFMA2 work,
+// so the bytes in flight per SM are set by the ring depth (~200 KB) instead of by register occupancy.
+// Fused form (OPT != 0): the thread then walks its quad through the n optimizer steps (particle
+// order, shared state in registers), re-reading x_i from the stage, and writes X in place — `out`
+// never touches HBM.
 // ---------------------------------------------------------------------------------
 __host__ __device__ constexpr int apply_tile_cols(int n) { return n <= 12 ? 512 : 256; }
-__host__ __device__ constexpr int apply_stage_bytes(int n) { return 2 * n * apply_tile_cols(n) * 4; }
-__host__ __device__ constexpr int apply_stages(int n) {
-    return (200 * 1024) / apply_stage_bytes(n) > 8 ? 8 : (200 * 1024) / apply_stage_bytes(n);
+__host__ __device__ constexpr int apply_stage_bytes(int n, int opt = 0) {
+    return (2 * n + opt_state_rows(opt)) * apply_tile_cols(n) * 4;
+}
+__host__ __device__ constexpr int apply_stages(int n, int opt = 0) {
+    return (200 * 1024) / apply_stage_bytes(n, opt) > 8 ? 8 : (200 * 1024) / apply_stage_bytes(n, opt);
 }
 
-template <int N>
+template <int N, int OPT>
 __global__ void __launch_bounds__(apply_tile_cols(N) / 4 + 32, 1)
-svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, float* __restrict__ out,
-                      const float* __restrict__ K, const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg,
-                      int64_t ldo) {
+svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
+                      const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
+                      const __grid_constant__ BaseOptParams o) {
     constexpr int NP = (N + 3) & ~3;
     constexpr int TC = apply_tile_cols(N);
-    constexpr int STAGES = apply_stages(N);
+    constexpr int STAGES = apply_stages(N, OPT);
+    constexpr int ROWS = 2 * N + opt_state_rows(OPT);
     constexpr int CONSUMERS = TC / 4;  // threads; one column quad each
     constexpr int CWARPS = CONSUMERS / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][2][N][TC]: X rows then G rows
+    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][ROWS][TC]: X rows, G rows, state rows
     __shared__ __align__(16) float sKT[N][NP];
     __shared__ __align__(16) float sAT[N][NP];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -544,6 +683,7 @@ svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, 
     const int64_t d4 = D & ~static_cast<int64_t>(3);
     const int64_t ntiles = (d4 + TC - 1) / TC;
     const bool is_producer = tid >= CONSUMERS;
+    const bool has_s0 = (OPT == kOptAdam) || (OPT == kOptSgd && o.momentum != 0.0f && o.buf_initialized);
 
     if (is_producer) {
         if (tid == CONSUMERS) {  // one elected lane drives the copy engine
@@ -555,13 +695,18 @@ svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, 
                 const int64_t col0 = t * TC;
                 const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
                 const uint32_t row_bytes = static_cast<uint32_t>(w) * 4u;
-                mbar_arrive_expect_tx(&full_bar[s], 2u * N * row_bytes);
-                float* sx = tiles + static_cast<size_t>(s) * 2 * N * TC;
+                const uint32_t nrows = 2u * N + (has_s0 ? 1u : 0u) + (OPT == kOptAdam ? 1u : 0u);
+                mbar_arrive_expect_tx(&full_bar[s], nrows * row_bytes);
+                float* sx = tiles + static_cast<size_t>(s) * ROWS * TC;
                 float* sg = sx + N * TC;
 #pragma unroll
                 for (int r = 0; r < N; ++r) {
                     tma_load_1d(sx + r * TC, X + r * ldx + col0, row_bytes, &full_bar[s]);
                     tma_load_1d(sg + r * TC, G + r * ldg + col0, row_bytes, &full_bar[s]);
+                }
+                if constexpr (OPT != kOptNone) {
+                    if (has_s0) tma_load_1d(sg + N * TC, o.state0 + col0, row_bytes, &full_bar[s]);
+                    if (OPT == kOptAdam) tma_load_1d(sg + (N + 1) * TC, o.state1 + col0, row_bytes, &full_bar[s]);
                 }
             }
         }
@@ -575,7 +720,7 @@ svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, 
             const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
             const bool active = 4 * tid < w;
             mbar_wait(&full_bar[s], use & 1u);
-            const float* sx = tiles + static_cast<size_t>(s) * 2 * N * TC + 4 * tid;
+            const float* sx = tiles + static_cast<size_t>(s) * ROWS * TC + 4 * tid;
             const float* sg = sx + N * TC;
             f32x2 acc[N][2];
 #pragma unroll
@@ -596,32 +741,50 @@ svgd_apply_tma_kernel(const float* __restrict__ X, const float* __restrict__ G, 
                     }
                 }
             }
-            // this warp is done reading the stage: hand it back to the producer, then store
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);
-            if (active) {
-                float* op = out + col0 + 4 * tid;
+            if constexpr (OPT == kOptNone) {
+                // this warp is done reading the stage: hand it back to the producer, then store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                if (active) {
+                    float* op = out + col0 + 4 * tid;
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    V4 o;
-                    o.lo = acc[i][0];
-                    o.hi = acc[i][1];
-                    stg_stream_v4(op + i * ldo, o);
+                    for (int i = 0; i < N; ++i) {
+                        V4 v;
+                        v.lo = acc[i][0];
+                        v.hi = acc[i][1];
+                        stg_stream_v4(op + i * ldo, v);
+                    }
+                }
+            } else {
+                V4 s0, s1;
+                s0.lo = s0.hi = s1.lo = s1.hi = 0ull;
+                if (active) {
+                    float* xw = const_cast<float*>(X) + col0 + 4 * tid;
+                    if (has_s0) s0 = lds_v4(sg + N * TC);
+                    if (OPT == kOptAdam) s1 = lds_v4(sg + (N + 1) * TC);
+                    if (o.out_last) {
+                        V4 v;
+                        v.lo = acc[N - 1][0];
+                        v.hi = acc[N - 1][1];
+                        stg_stream_v4(o.out_last + col0 + 4 * tid, v);
+                    }
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        V4 x = lds_v4(sx + i * TC);
+                        opt_update_quad<OPT>(o, i, acc[i][0], acc[i][1], x, s0, s1);
+                        stg_stream_v4(xw + i * ldx, x);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                if (active) {
+                    if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + col0 + 4 * tid, s0);
+                    if (OPT == kOptAdam) stg_stream_v4(o.state1 + col0 + 4 * tid, s1);
                 }
             }
         }
         // ragged tail columns (D % 4), CTA 0 only
-        if (blockIdx.x == 0 && tid < (D & 3)) {
-            const int64_t c = d4 + tid;
-            for (int i = 0; i < N; ++i) {
-                float sacc = 0.0f;
-                for (int j = 0; j < N; ++j) {
-                    sacc = fmaf(sKT[j][i], __ldg(G + j * ldg + c), sacc);
-                    sacc = fmaf(sAT[j][i], __ldg(X + j * ldx + c), sacc);
-                }
-                out[i * ldo + c] = sacc;
-            }
-        }
+        if (blockIdx.x == 0 && tid < (D & 3)) apply_tail_column<N, OPT>(X, G, out, sKT, sAT, d4 + tid, ldx, ldg, ldo, o);
     }
 }
 
@@ -674,9 +837,9 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     return BDE_OK;
 }
 
-template <int N>
-int launch_apply(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
-                 int64_t ldg, int64_t ldo, cudaStream_t st) {
+template <int N, int OPT>
+int launch_apply_opt(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
+                     int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st) {
     const int64_t nquads = D >> 2;
     constexpr int TC = apply_tile_cols(N);
     const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
@@ -685,23 +848,24 @@ int launch_apply(const float* X, const float* G, float* out, const float* K, con
     // CTA at the 256-column tile) the direct kernel is still faster — measured, see DESIGN.md
     if (variant == 0) variant = (N <= 12 && ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
     if (variant == 2) {
-        constexpr int smem = apply_stages(N) * apply_stage_bytes(N);
+        constexpr int smem = apply_stages(N, OPT) * apply_stage_bytes(N, OPT);
+        static_assert(apply_stages(N, OPT) >= 2, "ring too shallow");
         static bool configured = false;
         if (!configured) {
-            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
         int64_t grid = sm_count_cached();
         if (grid > ntiles) grid = ntiles;
         if (grid < 1) grid = 1;
-        svgd_apply_tma_kernel<N><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo);
+        svgd_apply_tma_kernel<N, OPT><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o);
         BDE_CHECK_LAUNCH();
         return BDE_OK;
     }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int v = 0;
-        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N>, 128, 0));
+        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N, OPT>, 128, 0));
         ctas_per_sm = v > 0 ? v : 1;
     }
     int64_t want = (nquads + 127) / 128;
@@ -709,9 +873,23 @@ int launch_apply(const float* X, const float* G, float* out, const float* K, con
     const int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    svgd_apply_kernel<N><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo);
+    svgd_apply_kernel<N, OPT><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
+}
+
+template <int N>
+int launch_apply(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
+                 int64_t ldg, int64_t ldo, cudaStream_t st) {
+    return launch_apply_opt<N, kOptNone>(X, G, out, K, A, D, ldx, ldg, ldo, BaseOptParams{}, st);
+}
+
+// fused K2 + base-optimizer step; X updated in place
+template <int N>
+int launch_apply_fused(float* X, const float* G, const float* K, const float* A, int64_t D, int64_t ldx, int64_t ldg,
+                       const BaseOptParams& o, cudaStream_t st) {
+    if (o.kind == kOptSgd) return launch_apply_opt<N, kOptSgd>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st);
+    return launch_apply_opt<N, kOptAdam>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st);
 }
 
 }  // namespace bde

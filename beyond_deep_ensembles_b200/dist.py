@@ -22,6 +22,18 @@ def allreduce_dist(sc: "ops.SvgdScratch", group=None) -> None:
         dist.all_reduce(sc.dist, op=dist.ReduceOp.SUM, group=group)
 
 
+def svgd_kernel_sharded(X: torch.Tensor, sc: "ops.SvgdScratch", l2_reg: float, kernel_grad_scale: float,
+                        dataset_size: float, h_override: float = 0.0, group=None) -> None:
+    """K1 (local partial distances) -> all-reduce of n*n fp64 -> K1b (identical on every rank): leaves
+    K and A in `sc`.  With a single rank K1b runs in K1's tail (one launch)."""
+    if world(group) == 1:
+        ops.svgd_pairdist_bandwidth(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+        return
+    ops.svgd_pairdist(X, sc)
+    allreduce_dist(sc, group)
+    ops.svgd_bandwidth(sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+
+
 def svgd_step_sharded(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: "ops.SvgdScratch", l2_reg: float,
                       kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0, group=None) -> torch.Tensor:
     """One SVGD posterior update on this rank's [n, D/R] slices.

@@ -13,6 +13,7 @@ from torch.amp.grad_scaler import OptState
 from . import dist as bdist
 from . import ops
 from .algo import BayesianOptimizer
+from .fused_base import FusedBasePlan
 from .layout import ParamLayout
 
 
@@ -39,7 +40,14 @@ class SVGDOptimizer(BayesianOptimizer):
     One param_group per tensor (svgd.py:50); `reset_params_closure` is called
     particle_count - 1 times to initialise the particles (svgd.py:58-63);
     `base_optimizer` must optimise the same parameters.
+
+    `fuse_base_optimizer` (class attribute, default True): when the base optimizer is a stock
+    torch.optim.SGD / Adam / AdamW and no GradScaler is active, its n per-particle steps
+    (svgd.py:92-103) run inside the apply kernel (fused_base.py); set it to False to always call
+    `base_optimizer.step()` per particle.
     """
+
+    fuse_base_optimizer = True
 
     def __init__(self, params, reset_params_closure, base_optimizer, particle_count, dataset_size, l2_reg=0.0,
                  kernel_grad_scale=1.0, process_group=None):
@@ -60,12 +68,15 @@ class SVGDOptimizer(BayesianOptimizer):
         # HBM layout: particles X, their gradients G and the new gradients OUT as [n, size] arenas
         self._X = self._layout.new_arena(n, device)
         self._G = self._layout.new_arena(n, device)
-        self._out = self._layout.new_arena(n, device)
+        self._out_full = None                                # [n, size], only the unfused path needs it
+        self._out_last = self._layout.new_arena(1, device)   # new gradient of the last particle (svgd.py:94)
+        self._fused_plan = None
         self._scratch = ops.SvgdScratch.allocate(n, device)
         self._group = process_group
         self._xviews = [self._layout.views(self._X[i]) for i in range(n)]
         self._gviews = [self._layout.views(self._G[i]) for i in range(n)]
-        self._oviews = [self._layout.views(self._out[i]) for i in range(n)]
+        self._oviews = None
+        self._oviews_last = self._layout.views(self._out_last[0])
 
         for particle_idx in range(n):
             with torch.no_grad():
@@ -95,23 +106,49 @@ class SVGDOptimizer(BayesianOptimizer):
             self._store_grads(particle_idx, plist)
 
         with torch.no_grad():
-            # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b -> K2
-            bdist.svgd_step_sharded(self._X, self._G, self._out, self._scratch, self.state["__l2_reg"],
-                                    self.state["__kernel_grad_scale"], self.state["__dataset_size"], 0.0, self._group)
-
-            # svgd.py:92-103: hand the new gradients to the ORIGINAL parameters, alias them to the
-            # particle and let the (shared) base optimizer step once per particle
-            for particle_idx in range(n):
-                for param, xview, oview in zip(plist, self._xviews[particle_idx], self._oviews[particle_idx]):
+            # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b
+            bdist.svgd_kernel_sharded(self._X, self._scratch, self.state["__l2_reg"], self.state["__kernel_grad_scale"],
+                                      self.state["__dataset_size"], 0.0, self._group)
+            plan = self._plan_for(base, grad_scaler, plist)
+            bound = plan.bind_state() if plan is not None else None
+            if bound is not None:
+                # f1: K2 + the n shared-state base-optimizer steps of svgd.py:92-103 in one pass; X in place
+                plan.launch(self._X, self._G, self._scratch, self._out_last[0], *bound)
+                for param, xview, oview in zip(plist, self._xviews[n - 1], self._oviews_last):
                     param.grad = oview
                     param.data = xview
-                if grad_scaler is not None:
-                    self._set_grad_scaler_state(grad_scaler, OptState.UNSCALED, base)
-                    grad_scaler.step(base)
-                else:
-                    base.step()
+            else:
+                # svgd.py:92-103 literally: hand the new gradients to the ORIGINAL parameters, alias them to
+                # the particle and let the (shared) base optimizer step once per particle
+                ops.svgd_apply(self._X, self._G, self._out, self._scratch)
+                for particle_idx in range(n):
+                    for param, xview, oview in zip(plist, self._xviews[particle_idx], self._oviews[particle_idx]):
+                        param.grad = oview
+                        param.data = xview
+                    if grad_scaler is not None:
+                        self._set_grad_scaler_state(grad_scaler, OptState.UNSCALED, base)
+                        grad_scaler.step(base)
+                    else:
+                        base.step()
 
         return total_loss / n
+
+    @property
+    def _out(self):
+        """[n, size] arena of the new gradients (allocated on first use: the fused path never needs it)."""
+        if self._out_full is None:
+            n = self.state["__particle_count"]
+            self._out_full = self._layout.new_arena(n, self._X.device)
+            self._oviews = [self._layout.views(self._out_full[i]) for i in range(n)]
+        return self._out_full
+
+    def _plan_for(self, base, grad_scaler, plist):
+        if not self.fuse_base_optimizer or (grad_scaler is not None and grad_scaler.is_enabled()):
+            return None
+        plan = self._fused_plan
+        if plan is None or plan.base is not base or not plan.still_valid():
+            plan = self._fused_plan = FusedBasePlan.build(base, plist, self._layout, self._X.device)
+        return plan
 
     def sample_parameters(self):
         """Cycles through the particles (svgd.py:107-112)."""

@@ -46,7 +46,9 @@ int bde_version(void);
 const char* bde_error_string(int code);
 /*
  * Launch-geometry override for tuning sweeps: key is "pairdist_ctas_per_sm",
- * "apply_ctas_per_sm" or "ew_ctas_per_sm"; value 0 restores the automatic choice.
+ * "apply_ctas_per_sm", "ew_ctas_per_sm", or "pairdist_variant" / "apply_variant" /
+ * "ew_variant" (1 = direct-LDG kernels, 2 = TMA-staged kernels); value 0 restores the
+ * automatic choice.
  */
 int bde_tune(const char* key, int value);
 /* number of SMs of the current device (grid sizing is done inside the library) */
@@ -108,6 +110,30 @@ int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, 
                   double l2_reg, double kernel_grad_scale, double dataset_size,
                   double h_override, double* dist, float* K, float* A, double* info,
                   int32_t* sel, void* workspace, size_t workspace_bytes, bde_stream_t stream);
+
+/*
+ * K2 fused with the base optimizer's update.  Replaces svgd.py:92-103: the new
+ * gradient of particle i (row i of K G + A X) is handed to ONE torch.optim optimizer whose state is
+ * shared by all particles and which steps once per particle, in particle order 0..n-1.  Here the
+ * n sequential steps run in registers per column: X is updated IN PLACE, the n*D gradient matrix
+ * never reaches HBM.  out_last (nullable, [D]) receives the new gradient of particle n-1 — what the
+ * reference leaves in param.grad.  X and G must not overlap.
+ *
+ * bde_svgd_apply_sgd  = torch.optim.SGD (weight_decay, momentum, dampening, nesterov; maximize=False):
+ *   momentum_buf [D] is the shared momentum_buffer (NULL iff momentum == 0); buf_initialized == 0 on the
+ *   optimizer's very first step (buffer := clone of particle 0's gradient, torch/optim/sgd.py).
+ * bde_svgd_apply_adam = torch.optim.Adam / AdamW (amsgrad=False, maximize=False): exp_avg, exp_avg_sq [D]
+ *   shared; step0 = the optimizer's step count BEFORE this call (particle i takes step step0+i+1);
+ *   decoupled_weight_decay != 0 selects AdamW's param *= 1 - lr*wd.
+ */
+int bde_svgd_apply_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                       int64_t ld, float* momentum_buf, int buf_initialized, double lr,
+                       double momentum, double dampening, double weight_decay, int nesterov,
+                       float* out_last, bde_stream_t stream);
+int bde_svgd_apply_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                        int64_t ld, float* exp_avg, float* exp_avg_sq, int64_t step0, double lr,
+                        double beta1, double beta2, double eps, double weight_decay,
+                        int decoupled_weight_decay, float* out_last, bde_stream_t stream);
 
 /*
  * Host-buffer entries (the end-to-end path): X_host/G_host/out_host are HOST arrays

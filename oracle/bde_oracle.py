@@ -115,6 +115,29 @@ def svgd_step_reference_order(X: torch.Tensor, G: torch.Tensor, l2_reg: float, k
     return -phi                                                     # :95
 
 
+def svgd_base_optimizer_steps(X: torch.Tensor, new_grads: torch.Tensor, kind: str, hyper: dict, state: dict | None = None):
+    """svgd.py:92-103: ONE torch.optim optimizer (its state shared by all particles) takes one step
+    per particle, in particle order, on `param.data = particle_i`, `param.grad = new_grads[i]`.
+
+    This literally drives torch.optim.SGD / Adam / AdamW on a single CPU parameter, exactly like the
+    reference does with the caller's base optimizer.  `state` carries the optimizer state between
+    SVGD steps ({} on the very first call): momentum_buffer | (step, exp_avg, exp_avg_sq).
+    Returns (X_new [n, D], state).  X and new_grads are not modified.
+    """
+    X = X.detach().clone().float()
+    G = new_grads.detach().float()
+    p = torch.nn.Parameter(X[0].clone())
+    cls = {"sgd": torch.optim.SGD, "adam": torch.optim.Adam, "adamw": torch.optim.AdamW}[kind]
+    opt = cls([p], foreach=False, **hyper)
+    if state:
+        opt.state[p] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in state.items()}
+    for i in range(X.shape[0]):
+        p.data = X[i]            # the particle IS the parameter's storage (svgd.py:96)
+        p.grad = G[i].clone()    # svgd.py:94
+        opt.step()
+    return X, dict(opt.state[p])
+
+
 # --------------------------------------------------------------------------------------
 # SWAG — reference: src/algos/swag.py
 # --------------------------------------------------------------------------------------

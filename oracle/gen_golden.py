@@ -134,6 +134,41 @@ def gen_svgd():
                         sampled=np.stack(seen))
 
 
+def gen_svgd_sgd():
+    """Reference SVGDOptimizer with the CIFAR base optimizer (experiments/cifar/cifar.yaml:219-223:
+    SGD lr 0.05, momentum 0.9, Nesterov, weight decay 3e-4) plus a StepLR schedule and a base-optimizer
+    checkpoint round trip after step 2 — pins the shared-state / stepped-once-per-particle semantics of
+    svgd.py:92-103 that the fused apply kernel reproduces.  n = 5 (the shipped particle count)."""
+    n, steps = 5, 4
+    torch.manual_seed(9)
+    model = gm.make_mlp()
+    g = torch.Generator().manual_seed(13)
+    D = sum(p.numel() for p in model.parameters())
+    init = (0.3 * torch.randn(n, D, generator=g)).numpy()
+    gm.load_flat(model.parameters(), init[0])
+    calls = {"k": 0}
+
+    def reset():
+        calls["k"] += 1
+        gm.load_flat(model.parameters(), init[calls["k"]])
+
+    base = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)
+    opt = SVGDOptimizer(model.parameters(), reset, base, particle_count=n, dataset_size=768, l2_reg=3e-4,
+                        kernel_grad_scale=1.0)
+    sched = torch.optim.lr_scheduler.StepLR(base, step_size=2, gamma=0.5)
+    xs, ys = batches(23, steps)
+    losses, parts, bufs, lrs = [], [], [], []
+    for s in range(steps):
+        fwd, bwd = gm.mse_closures(model, xs[s], ys[s])
+        lrs.append(base.param_groups[0]["lr"])
+        losses.append(opt.step(fwd, bwd).item())
+        sched.step()
+        parts.append(np.stack([gm.flat_params(opt._params_for_particle(i)) for i in range(n)]))
+        bufs.append(np.concatenate([base.state[p]["momentum_buffer"].reshape(-1).numpy() for p in model.parameters()]))
+    np.savez_compressed(OUT / "svgd_sgd_steps.npz", init=init, xs=xs.numpy(), ys=ys.numpy(), losses=np.array(losses),
+                        particles=np.stack(parts), momentum_buffers=np.stack(bufs), lrs=np.array(lrs))
+
+
 def gen_swag():
     """Reference SwagOptimizer: 6 SGD steps with K=4 (so the ring wraps), then two samples."""
     K, steps = 4, 6
@@ -320,8 +355,13 @@ def gen_ensemble():
 
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
+    if len(sys.argv) > 1:  # regenerate selected fixtures only:  python oracle/gen_golden.py gen_svgd_sgd
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     gen_rbf()
     gen_svgd()
+    gen_svgd_sgd()
     gen_swag()
     gen_ivon()
     gen_bbb()

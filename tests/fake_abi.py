@@ -88,6 +88,38 @@ class FakeLib:
         _mat(out, n, D, ld).copy_(res.float())
         return 0
 
+    def bde_svgd_apply_sgd(self, X, G, K, A, n, D, ld, buf, buf_init, lr, momentum, dampening, wd, nesterov, out_last,
+                           stream):
+        self.calls.append("apply_sgd")
+        Km, Am = _f32(K, n * n).view(n, n), _f32(A, n * n).view(n, n)
+        Xm = _mat(X, n, D, ld)
+        res = O.svgd_apply(Xm, _mat(G, n, D, ld), Km, Am).float()
+        state = {"momentum_buffer": _f32(buf, D)} if (momentum != 0 and buf_init) else None
+        Xn, st = O.svgd_base_optimizer_steps(Xm, res, "sgd", dict(lr=lr, momentum=momentum, dampening=dampening,
+                                                                  weight_decay=wd, nesterov=bool(nesterov)), state)
+        Xm.copy_(Xn)
+        if momentum != 0:
+            _f32(buf, D).copy_(st["momentum_buffer"])
+        if out_last:
+            _f32(out_last, D).copy_(res[n - 1])
+        return 0
+
+    def bde_svgd_apply_adam(self, X, G, K, A, n, D, ld, exp_avg, exp_avg_sq, step0, lr, b1, b2, eps, wd, decoupled,
+                            out_last, stream):
+        self.calls.append("apply_adam")
+        Km, Am = _f32(K, n * n).view(n, n), _f32(A, n * n).view(n, n)
+        Xm = _mat(X, n, D, ld)
+        res = O.svgd_apply(Xm, _mat(G, n, D, ld), Km, Am).float()
+        state = {"step": torch.tensor(float(step0)), "exp_avg": _f32(exp_avg, D), "exp_avg_sq": _f32(exp_avg_sq, D)}
+        Xn, st = O.svgd_base_optimizer_steps(Xm, res, "adamw" if decoupled else "adam",
+                                             dict(lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd), state)
+        Xm.copy_(Xn)
+        _f32(exp_avg, D).copy_(st["exp_avg"])
+        _f32(exp_avg_sq, D).copy_(st["exp_avg_sq"])
+        if out_last:
+            _f32(out_last, D).copy_(res[n - 1])
+        return 0
+
     def bde_svgd_step(self, X, G, out, n, D, ld, l2, kgs, N, h_override, dist, K, A, info, sel, ws, wsb, stream):
         self.bde_svgd_pairdist(X, n, D, ld, dist, 0, ws, wsb, stream)
         self.bde_svgd_bandwidth(dist, n, l2, kgs, N, h_override, K, A, info, sel, stream)

@@ -247,6 +247,148 @@ def test_svgd_full_size_properties(ops, D):
     np.testing.assert_allclose(sc.dist.cpu().numpy(), d[perm][:, perm].cpu().numpy(), rtol=1e-12)
 
 
+# ---------------------------------------------------------------- f1: K2 fused with the base optimizer
+OPT_KINDS = {
+    "sgd-cifar": ("sgd", dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)),
+    "sgd-plain": ("sgd", dict(lr=0.1)),
+    "sgd-damp": ("sgd", dict(lr=0.02, momentum=0.8, dampening=0.3)),
+    "adam": ("adam", dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)),
+    "adam-wd": ("adam", dict(lr=1e-2, betas=(0.8, 0.99), eps=1e-6, weight_decay=0.01)),
+    "adamw": ("adamw", dict(lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)),
+}
+
+
+def fused_apply(ops, kind, hyper, dX, dG, sc, s0, s1, initialized, step0, out_last):
+    if kind == "sgd":
+        ops.svgd_apply_sgd(dX, dG, sc, s0 if hyper.get("momentum", 0) != 0 else None, buf_initialized=initialized,
+                           out_last=out_last, **hyper)
+    else:
+        ops.svgd_apply_adam(dX, dG, sc, s0, s1, step0=step0, lr=hyper["lr"], beta1=hyper["betas"][0],
+                            beta2=hyper["betas"][1], eps=hyper["eps"], weight_decay=hyper["weight_decay"],
+                            decoupled_weight_decay=(kind == "adamw"), out_last=out_last)
+
+
+def check_update(x_new, x_old, ref_new, what):
+    """Updated particles within the north-star tolerance, and the UPDATE itself (x_new - x_old, a small
+    correction) to 1e-3 relative + 1e-5 of its largest entry."""
+    np.testing.assert_allclose(x_new, ref_new, rtol=RTOL, atol=ATOL, err_msg=what)
+    upd, upd_ref = x_new.astype(np.float64) - x_old, ref_new.astype(np.float64) - x_old
+    bound = 1e-3 * np.abs(upd_ref) + 1e-5 * np.abs(upd_ref).max() + 6e-8 * np.abs(x_old)  # last term: fp32 rounding of x itself
+    assert (np.abs(upd - upd_ref) <= bound).all(), what
+
+
+@pytest.mark.parametrize("variant", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("opt", list(OPT_KINDS))
+@pytest.mark.parametrize("n,D,ld,mis", [(10, 4099, 4100, 0), (10, 501, 512, 0), (5, 37, 40, 0), (20, 1000, 1000, 0),
+                                        (16, 2051, 2052, 0), (12, 70_001, 70_004, 0), (2, 9, 12, 0), (10, 3, 4, 0),
+                                        (13, 700, 700, 0), (10, 1000, 1001, 0), (10, 1000, 1000, 1), (3, 200_000, 200_000, 0)])
+def test_fused_apply_base_optimizer_vs_oracle(ops, cuda_lib, variant, opt, n, D, ld, mis):
+    """bde_svgd_apply_sgd / _adam against the reference semantics (svgd.py:92-103: one shared torch.optim
+    optimizer stepped once per particle) for two consecutive SVGD steps (first step: uninitialised momentum
+    buffer / step count 0; second: carried state), both kernel forms, ragged and unaligned shapes."""
+    kind, hyper = OPT_KINDS[opt]
+    X, G = particles(n, D, seed=n * 31 + D)
+    X *= 4.0            # O(0.2) particles
+    G *= 50.0           # O(0.05) gradients: the update is well above fp32 rounding of x
+    dX, dG = dev_matrix(X, ld, mis), dev_matrix(G, ld, mis)
+    dOut = dev_matrix(torch.zeros_like(X), ld, mis)
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    # 4-byte-misaligned state vectors in the misaligned case
+    buf0 = torch.zeros(D + 8, device="cuda")
+    s0 = buf0[mis:mis + D]
+    s1 = torch.zeros(D + 8, device="cuda")[mis:mis + D]
+    out_last = torch.zeros(D + 8, device="cuda")[mis:mis + D]
+    state, x_ref = None, X.clone()
+    cuda_lib.bde_tune(b"apply_variant", variant)
+    try:
+        for step in range(2):
+            ops.svgd_pairdist(dX, sc)
+            ops.svgd_bandwidth(sc, 0.01, 1.0, 768.0)
+            x_old = dX.cpu()
+            g_step = G * (1.0 + 0.5 * step)
+            dG.copy_(g_step)
+            ref_out = O.svgd_apply(x_old, g_step, sc.K.cpu(), sc.A.cpu()).float()
+            # the new gradients as the plain K2 computes them: the optimizer arithmetic is checked tightly on
+            # these (Adam's g / (|g| + eps) amplifies last-bit differences of near-zero gradients, which
+            # says nothing about the optimizer step itself)
+            ops.svgd_apply(dX, dG, dOut, sc)
+            k2_out = dOut.cpu()
+            np.testing.assert_allclose(k2_out.numpy(), ref_out.numpy(), rtol=RTOL, atol=ATOL)
+            fused_apply(ops, kind, hyper, dX, dG, sc, s0, s1, step > 0, step * n, out_last)
+            x_ref, state_next = O.svgd_base_optimizer_steps(x_old, k2_out, kind, hyper, state)
+            check_update(dX.cpu().numpy(), x_old.numpy().astype(np.float64), x_ref.numpy(), f"step {step}")
+            x_ref_full, _ = O.svgd_base_optimizer_steps(x_old, ref_out, kind, hyper, state)
+            np.testing.assert_allclose(dX.cpu().numpy(), x_ref_full.numpy(), rtol=RTOL, atol=5 * ATOL)
+            state = state_next
+            assert torch.equal(out_last.cpu(), k2_out[n - 1])  # same arithmetic as the plain K2, bit for bit
+            if kind == "sgd" and hyper.get("momentum", 0) != 0:
+                np.testing.assert_allclose(s0.cpu().numpy(), state["momentum_buffer"].numpy(), rtol=1e-4, atol=1e-6)
+            elif kind != "sgd":
+                np.testing.assert_allclose(s0.cpu().numpy(), state["exp_avg"].numpy(), rtol=1e-4, atol=1e-7)
+                np.testing.assert_allclose(s1.cpu().numpy(), state["exp_avg_sq"].numpy(), rtol=1e-4, atol=1e-9)
+                assert float(state["step"]) == (step + 1) * n
+            assert torch.equal(dG.cpu(), g_step)  # G untouched
+    finally:
+        cuda_lib.bde_tune(b"apply_variant", 0)
+
+
+def test_fused_apply_rejects_bad_arguments(ops):
+    from beyond_deep_ensembles_b200 import _lib
+    n, D = 4, 64
+    X = torch.randn(n, D, device="cuda")
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    with pytest.raises(ValueError):
+        ops.svgd_apply_sgd(X, X.clone(), sc, None, buf_initialized=False, lr=0.1, momentum=0.9)
+    with pytest.raises(_lib.BdeError):  # X and G overlap
+        ops.svgd_apply_sgd(X, X, sc, None, buf_initialized=False, lr=0.1)
+
+
+def test_fused_apply_full_size_properties(ops):
+    """n = 10 x D = 1e8 (the sweep point): lr = 0 leaves X bit-identical while the momentum buffer follows the
+    reference recurrence; a real step matches the oracle on a random column sample; padding columns stay 0."""
+    n, D = 10, 100_000_000
+    g = torch.Generator(device="cuda").manual_seed(11)
+    X = torch.randn(n, D, device="cuda", generator=g)
+    X *= (0.05 * (1 + 0.1 * torch.arange(n, device="cuda", dtype=torch.float32))).unsqueeze(1)
+    G = torch.randn(n, D, device="cuda", generator=g) * 1e-2
+    X[:, -64:] = 0.0
+    G[:, -64:] = 0.0  # arena padding
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    ops.svgd_pairdist_bandwidth(X, sc, 3e-4, 1.0, 50000.0)
+    K, A = sc.K.cpu(), sc.A.cpu()
+    cols = torch.randint(0, D, (4096,), generator=torch.Generator().manual_seed(2))
+    cols = torch.cat([cols, torch.tensor([0, 1, 2, 3, D - 68, D - 65, D - 2, D - 1])]).cuda()
+    x_old, g_cols = X[:, cols].cpu(), G[:, cols].cpu()
+    ref_out = O.svgd_apply(x_old, g_cols, K, A).float()
+    buf = torch.zeros(D, device="cuda")
+    out_last = torch.empty(D, device="cuda")
+    hyper = dict(lr=0.0, momentum=0.9, nesterov=True, weight_decay=3e-4)
+    chk = X[:, ::4097].clone()
+    ops.svgd_apply_sgd(X, G, sc, buf, buf_initialized=False, out_last=out_last, **hyper)
+    assert torch.equal(X[:, ::4097], chk)  # lr = 0: particles bit-identical
+    _, st = O.svgd_base_optimizer_steps(x_old, ref_out, "sgd", hyper)
+    np.testing.assert_allclose(buf[cols].cpu().numpy(), st["momentum_buffer"].numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(out_last[cols].cpu().numpy(), ref_out[n - 1].numpy(), rtol=RTOL, atol=ATOL)
+    hyper["lr"] = 0.05
+    ops.svgd_apply_sgd(X, G, sc, buf, buf_initialized=True, out_last=out_last, **hyper)
+    x_ref, st = O.svgd_base_optimizer_steps(x_old, ref_out, "sgd", hyper, st)
+    check_update(X[:, cols].cpu().numpy(), x_old.numpy().astype(np.float64), x_ref.numpy(), "sgd full size")
+    assert X[:, -64:].eq(0).all() and buf[-64:].eq(0).all()
+    # Adam from step 0 on the updated particles
+    del buf
+    m, v = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.svgd_pairdist_bandwidth(X, sc, 3e-4, 1.0, 50000.0)
+    x_old = X[:, cols].cpu()
+    ref_out = O.svgd_apply(x_old, g_cols, sc.K.cpu(), sc.A.cpu()).float()
+    ah = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0)
+    ops.svgd_apply_adam(X, G, sc, m, v, step0=0, lr=1e-3, out_last=out_last)
+    x_ref, st = O.svgd_base_optimizer_steps(x_old, ref_out, "adam", ah)
+    # the zero-gradient padding columns divide 0 by eps: they must stay exactly 0
+    assert X[:, -64:].eq(0).all() and m[-64:].eq(0).all()
+    live = (cols < D - 64).cpu()
+    check_update(X[:, cols].cpu().numpy()[:, live], x_old.numpy().astype(np.float64)[:, live], x_ref.numpy()[:, live], "adam full size")
+
+
 @pytest.fixture(params=[1, 2], ids=["direct", "tma"])
 def ew_variant(request, cuda_lib):
     """Force the direct-LDG (1) or the TMA-staged (2) form of the elementwise kernels (ew_tma.cuh)."""

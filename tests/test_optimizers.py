@@ -108,10 +108,15 @@ def build_svgd(env, g, base_cls=torch.optim.Adam, **base_kw):
     return model, opt
 
 
-def test_svgd_steps_match_reference(env, golden):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-base", "base-step"])
+def test_svgd_steps_match_reference(env, golden, fused):
+    """Three reference steps with a shared Adam base optimizer (10 Adam steps per SVGD step); fused = the
+    base-optimizer steps run inside the apply kernel (f1), otherwise base.step() per particle."""
     g = golden("svgd_steps.npz")
     n, D = g["init"].shape
     model, opt = build_svgd(env, g)
+    opt.fuse_base_optimizer = fused
+    base = opt.get_base_optimizer()
     assert len(opt.param_groups) == 4  # one group per tensor (svgd.py:50)
     for s in range(g["losses"].size):
         fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
@@ -119,24 +124,129 @@ def test_svgd_steps_match_reference(env, golden):
         np.testing.assert_allclose(loss.item(), g["losses"][s], rtol=1e-5)
         parts = np.stack([flat(opt._params_for_particle(i)) for i in range(n)])
         np.testing.assert_allclose(parts, g["particles"][s], rtol=3e-5, atol=3e-6)
-        # the model's parameters alias the LAST particle after a step (svgd.py:96)
+        # the model's parameters alias the LAST particle after a step (svgd.py:96) and carry its new gradient (:94)
         assert all(p.data_ptr() == v.data_ptr() for p, v in zip(model.parameters(), opt._params_for_particle(n - 1)))
+        np.testing.assert_allclose(flat(p.grad for p in model.parameters()), g["new_grads"][s][n - 1], rtol=1e-4, atol=ATOL)
+        # the shared optimizer has stepped once per particle
+        assert all(float(base.state[p]["step"]) == n * (s + 1) for p in model.parameters())
     # cursor semantics of sample_parameters (svgd.py:107-112)
     for k in range(n + 2):
         opt.sample_parameters()
         np.testing.assert_allclose(flat(model.parameters()), g["sampled"][k], rtol=3e-5, atol=3e-6)
     if env.fake:
-        assert env.calls("pairdist") == g["losses"].size and env.calls("apply") == g["losses"].size
+        steps = g["losses"].size
+        assert env.calls("pairdist") == steps
+        assert env.calls("apply_adam") == (steps if fused else 0) and env.calls("apply") == (0 if fused else steps)
 
 
-def test_svgd_new_gradients_match_reference_first_step(env, golden):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-base", "base-step"])
+def test_svgd_sgd_nesterov_schedule_and_checkpoint_match_reference(env, golden, fused):
+    """CIFAR base optimizer (SGD momentum 0.9, Nesterov, weight decay) with a StepLR schedule; after step 2
+    the base optimizer is checkpointed and restored into a FRESH optimizer object (state tensors no longer
+    alias the arena) — the run must still follow the reference's trajectory (svgd.py:92-103)."""
+    g = golden("svgd_sgd_steps.npz")
+    n, D = g["init"].shape
+    kw = dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)
+    model = gm.make_mlp().to(env.dev)
+    gm.load_flat(model.parameters(), g["init"][0])
+    k = {"k": 0}
+
+    def reset():
+        k["k"] += 1
+        gm.load_flat(model.parameters(), g["init"][k["k"]])
+
+    base = torch.optim.SGD(model.parameters(), **kw)
+    opt = bde.SVGDOptimizer(model.parameters(), reset, base, particle_count=n, dataset_size=768, l2_reg=3e-4,
+                            kernel_grad_scale=1.0)
+    opt.fuse_base_optimizer = fused
+    sched = torch.optim.lr_scheduler.StepLR(base, step_size=2, gamma=0.5)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")  # e.g. "lr_scheduler.step() before optimizer.step()"
+        for s in range(g["losses"].size):
+            if s == 2:  # checkpoint round trip of the caller's base optimizer
+                sd = copy.deepcopy(base.state_dict())
+                assert set(sd["state"][0].keys()) == {"momentum_buffer"}
+                base.load_state_dict(sd)
+            assert base.param_groups[0]["lr"] == pytest.approx(g["lrs"][s])
+            fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+            loss = opt.step(fwd, bwd)
+            sched.step()
+            np.testing.assert_allclose(loss.item(), g["losses"][s], rtol=1e-5)
+            parts = np.stack([flat(opt._params_for_particle(i)) for i in range(n)])
+            np.testing.assert_allclose(parts, g["particles"][s], rtol=3e-5, atol=3e-6)
+            bufs = flat(base.state[p]["momentum_buffer"] for p in model.parameters())
+            np.testing.assert_allclose(bufs, g["momentum_buffers"][s], rtol=1e-4, atol=1e-6)
+    if env.fake:
+        assert env.calls("apply_sgd") == (g["losses"].size if fused else 0)
+
+
+def test_svgd_fused_plan_recognition(env, golden):
+    """What is fused and what goes through base.step(): stock SGD/Adam/AdamW only, no scaler, no hooks."""
+    g = golden("svgd_steps.npz")
+    model, opt = build_svgd(env, g)
+    plist = list(model.parameters())
+
+    def plan(base, scaler=None):
+        opt._fused_plan = None
+        return opt._plan_for(base, scaler, plist)
+
+    assert plan(torch.optim.SGD(plist, lr=0.1, momentum=0.9)).kind == "sgd"
+    assert plan(torch.optim.Adam(plist, lr=0.1)).kind == "adam"
+    assert plan(torch.optim.AdamW(plist, lr=0.1)).kind == "adamw"
+    assert plan(torch.optim.Adam(plist, lr=0.1, amsgrad=True)) is None
+    assert plan(torch.optim.SGD(plist, lr=0.1, maximize=True)) is None
+    assert plan(torch.optim.RMSprop(plist, lr=0.1)) is None
+    assert plan(torch.optim.SGD(plist[:2], lr=0.1)) is None  # does not cover every particle tensor
+
+    class MySGD(torch.optim.SGD):
+        pass
+
+    assert plan(MySGD(plist, lr=0.1)) is None  # subclasses may override step()
+    hooked = torch.optim.SGD(plist, lr=0.1)
+    hooked.register_step_post_hook(lambda *a: None)
+    assert plan(hooked) is None
+    # two groups with different hyper-parameters -> two column segments
+    two = torch.optim.SGD([{"params": plist[:2], "lr": 0.1}, {"params": plist[2:], "lr": 0.01, "weight_decay": 0.1}], lr=1.0)
+    p2 = plan(two)
+    assert [(c0, c1) for c0, c1, _ in p2.segments] == [(0, opt._layout.offsets[2]), (opt._layout.offsets[2], opt._layout.size)]
+    opt.fuse_base_optimizer = False
+    assert plan(torch.optim.SGD(plist, lr=0.1)) is None
+
+
+def test_svgd_fused_two_param_groups_equal_base_step(env, golden):
+    """Per-group hyper-parameters: the fused path (one launch per column segment) against base.step()."""
+    g = golden("svgd_steps.npz")
+    results = []
+    for fused in (True, False):
+        model, opt = build_svgd(env, g)
+        plist = list(model.parameters())
+        base = torch.optim.AdamW([{"params": plist[:2], "lr": 1e-2, "weight_decay": 0.05},
+                                  {"params": plist[2:], "lr": 3e-3, "betas": (0.8, 0.99)}], lr=1.0)
+        opt.state["__base_optimizer"] = base
+        opt.fuse_base_optimizer = fused
+        for s in range(2):
+            fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+            opt.step(fwd, bwd)
+        results.append(np.stack([flat(opt._params_for_particle(i)) for i in range(10)]))
+    np.testing.assert_allclose(results[0], results[1], rtol=3e-5, atol=3e-6)
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-base", "base-step"])
+def test_svgd_new_gradients_match_reference_first_step(env, golden, fused):
     """Tight check of one posterior update: the gradients handed to the base optimizer."""
     g = golden("svgd_steps.npz")
     model, opt = build_svgd(env, g, base_cls=torch.optim.SGD, lr=0.0)
+    opt.fuse_base_optimizer = fused
     fwd, bwd = gm.mse_closures(model, env.t(g["xs"][0]), env.t(g["ys"][0]))
     opt.step(fwd, bwd)
-    out = opt._layout.to_logical(opt._out).cpu().numpy()
-    np.testing.assert_allclose(out, g["new_grads"][0], rtol=RTOL, atol=ATOL)
+    if fused:  # only the last particle's new gradient leaves the kernel (what svgd.py:94 leaves in param.grad)
+        out = opt._layout.to_logical(opt._out_last).cpu().numpy()
+        np.testing.assert_allclose(out[0], g["new_grads"][0][-1], rtol=RTOL, atol=ATOL)
+        assert opt._out_full is None
+    else:
+        out = opt._layout.to_logical(opt._out).cpu().numpy()
+        np.testing.assert_allclose(out, g["new_grads"][0], rtol=RTOL, atol=ATOL)
 
 
 def test_svgd_state_dict_roundtrip_and_keys(env, golden):
