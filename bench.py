@@ -270,6 +270,48 @@ def other_paths(ops, peak_gbs, dev):
         time_kernel(lambda: ops.l2_term(body, 0.01, value=val, grad=gbody, accumulate=True, ws=ws), 20, 3),
         12 * Dd, f"DistilBERT body D={Dd}")
     del body, gbody
+    # f1: K2 fused with the base optimizer (shared state, one step per particle), n = 10 x D = 1e8,
+    # next to what the reference's structure costs on the same GPU: K2 + n x torch.optim step()
+    nf, Df = N_PARTICLES, D_PER_GPU
+    Xf = torch.randn(nf, Df, device=dev, generator=g)
+    Xf *= (0.05 * (1 + 0.1 * torch.arange(nf, device=dev, dtype=torch.float32))).unsqueeze(1)
+    Gf = torch.randn(nf, Df, device=dev, generator=g) * 1e-3
+    scf = ops.SvgdScratch.allocate(nf, dev)
+    ops.svgd_pairdist_bandwidth(Xf, scf, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+    buf, buf2, olast = (torch.zeros(Df, device=dev) for _ in range(3))
+    sgd_kw = dict(lr=1e-4, momentum=0.9, nesterov=True, weight_decay=3e-4)
+    rec("svgd_apply_fused_sgd",
+        time_kernel(lambda: ops.svgd_apply_sgd(Xf, Gf, scf, buf, buf_initialized=True, out_last=olast, **sgd_kw), 10, 3),
+        (12 * nf + 12) * Df, f"n={nf} x D={Df}: K2 + {nf} SGD(momentum, nesterov, wd) steps in one pass, X in place")
+    st0 = [0]
+
+    def fused_adam():
+        ops.svgd_apply_adam(Xf, Gf, scf, buf, buf2, step0=st0[0], lr=1e-5, out_last=olast)
+        st0[0] += nf
+
+    rec("svgd_apply_fused_adam", time_kernel(fused_adam, 10, 3), (12 * nf + 20) * Df,
+        f"n={nf} x D={Df}: K2 + {nf} Adam steps in one pass, X in place")
+    del buf2
+    Of = torch.empty_like(Xf)
+    param = torch.nn.Parameter(Xf[0])
+    base = torch.optim.SGD([param], **sgd_kw)
+
+    def unfused():
+        ops.svgd_apply(Xf, Gf, Of, scf)
+        for i in range(nf):     # svgd.py:92-103 with a single flat parameter (the best case for torch.optim)
+            param.data = Xf[i]
+            param.grad = Of[i]
+            base.step()
+
+    ms_unfused = time_kernel(unfused, 5, 2)
+    ms_fused = res["svgd_apply_fused_sgd"]["ms"]
+    res["svgd_apply_plus_base_optimizer"] = {
+        "fused_ms": ms_fused, "k2_plus_torch_optim_ms": ms_unfused, "speedup": ms_unfused / ms_fused,
+        "config": f"n={nf} x D={Df}, SGD momentum 0.9 nesterov wd 3e-4; unfused = bde K2 + {nf} x torch.optim.SGD.step() (foreach) on the same GPU"}
+    log(f"[bench] K2 + base optimizer: fused {ms_fused:.3f} ms vs K2 + {nf} x torch.optim.SGD.step() {ms_unfused:.3f} ms "
+        f"({ms_unfused / ms_fused:.2f}x)")
+    del Xf, Gf, Of, buf, olast, param, base
+    torch.cuda.empty_cache()
     # C2 CIFAR ResNet-20 SVGD, n = 20 (small D: latency-bound, reported as time)
     n2, D2 = 20, 273_610
     D2p = (D2 + 63) // 64 * 64

@@ -181,16 +181,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 //   ws layout: [0] ticket (unsigned, padded to 16 B), then gridDim.x*count doubles.
 // Returns true in every thread of the LAST CTA to arrive, after which total[k] = sum over all
 // CTAs is available in `total` (shared, count doubles).  The order of the additions depends only
-// on (gridDim, blockDim, count): the CTA list is cut into S = threads/count interleaved slices
-// summed in parallel, then the S slice sums are added in slice order.  The ticket is reset so the
-// workspace can be reused by the next launch.
+// on (gridDim, count): every warp of the last CTA owns groups of 4 consecutive values k (one 32-byte
+// sector per CTA), its lanes walk the CTA list with stride 32 keeping 4 x 8 independent loads in
+// flight, and the 32 lane sums are combined by the fixed xor-shuffle tree.  The ticket is reset so
+// the workspace can be reused by the next launch.
 __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int count, void* ws, double* total) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
     double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     __shared__ bool is_last;
-    __shared__ double slice_sum[1024];
     for (int k = tid; k < count; k += nthreads) parts[(size_t)blockIdx.x * count + k] = cta_vals[k];
     __threadfence();
     __syncthreads();
@@ -201,25 +201,31 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    if (count <= nthreads) {
-        const int S = nthreads / count;
-        const int k = tid % count, sl = tid / count;
-        if (sl < S) {
-            double s = 0.0;
-            for (unsigned int b = sl; b < gridDim.x; b += S) s += __ldcg(&parts[(size_t)b * count + k]);
-            slice_sum[sl * count + k] = s;
+    constexpr int KU = 4, BU = 8;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;  // CTA sizes are multiples of 32
+    const unsigned int G = gridDim.x;
+    for (int k0 = warp * KU; k0 < count; k0 += nwarps * KU) {
+        double s[KU];
+#pragma unroll
+        for (int u = 0; u < KU; ++u) s[u] = 0.0;
+        for (unsigned int b0 = lane; b0 < G; b0 += 32 * BU) {
+            double v[BU][KU];
+#pragma unroll
+            for (int r = 0; r < BU; ++r) {
+                const unsigned int b = b0 + 32u * r;
+#pragma unroll
+                for (int u = 0; u < KU; ++u)
+                    v[r][u] = (b < G && k0 + u < count) ? __ldcg(&parts[(size_t)b * count + k0 + u]) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < BU; ++r)
+#pragma unroll
+                for (int u = 0; u < KU; ++u) s[u] += v[r][u];
         }
-        __syncthreads();
-        if (tid < count) {
-            double s = 0.0;
-            for (int j = 0; j < S; ++j) s += slice_sum[j * count + tid];
-            total[tid] = s;
-        }
-    } else {
-        for (int k = tid; k < count; k += nthreads) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&parts[(size_t)b * count + k]);
-            total[k] = s;
+#pragma unroll
+        for (int u = 0; u < KU; ++u) {
+            const double t = warp_sum(s[u]);
+            if (lane == 0 && k0 + u < count) total[k0 + u] = t;
         }
     }
     if (tid == 0) *ticket = 0u;

@@ -42,7 +42,7 @@ svgd_pairdist_scalar_kernel(const float* __restrict__ X, int n, int64_t D, int64
 __global__ void __launch_bounds__(256) svgd_bandwidth_kernel(const double* __restrict__ dist, int n, BandwidthParams bp) {
     __shared__ double sd[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
     __shared__ double sk[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
-    bandwidth_device(dist, n, bp, sd, sk);
+    bandwidth_device<BDE_MAX_PARTICLES * BDE_MAX_PARTICLES>(dist, n, bp, sd, sk);
 }
 
 __global__ void __launch_bounds__(256)

@@ -57,16 +57,40 @@ __device__ __forceinline__ void pair_accumulate(const V4 (&v)[N], f32x2 (&acc)[p
     }
 }
 
-// fp32 lane pairs -> warp sum -> this warp's fp64 accumulators (lane k%32 owns pair k)
+// fp32 lane pairs -> warp sums -> this warp's fp64 accumulators (lane k%32 owns pair k).
+// Transposing butterfly: 32 values held by every lane are reduced with 31 shuffles (16 + 8 + 4 + 2 + 1)
+// instead of 32 five-step trees; after the last step lane L holds the warp total of value L.
+// The summation order is fixed by the lane ids -> deterministic.
 template <int PG>
 __device__ __forceinline__ void flush_pairs(f32x2 (&acc)[PG > 0 ? PG : 1], double* __restrict__ wacc, int lane) {
+    constexpr int NB = (PG + 31) / 32;
 #pragma unroll
-    for (int k = 0; k < PG; ++k) {
-        float lo, hi;
-        unpack2(acc[k], lo, hi);
-        const float s = warp_sum(lo + hi);
-        if (lane == (k & 31)) wacc[k] += static_cast<double>(s);
-        acc[k] = 0ull;
+    for (int blk = 0; blk < NB; ++blk) {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int k = blk * 32 + i;
+            if (k < PG) {
+                float lo, hi;
+                unpack2(acc[k], lo, hi);
+                v[i] = lo + hi;
+                acc[k] = 0ull;
+            } else {
+                v[i] = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+                const float send = upper ? v[i] : v[i + off];
+                const float keep = upper ? v[i + off] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+        }
+        const int k = blk * 32 + lane;
+        if (k < PG) wacc[k] += static_cast<double>(v[0]);
     }
 }
 
@@ -84,37 +108,38 @@ __device__ __forceinline__ void pairdist_body(const float* __restrict__ X, int64
 
     const int64_t nquads = D >> 2;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * TPB;
-    int iter = 0;
-    // block-uniform trip count so that the warp shuffles in flush() stay convergent
-    for (int64_t q0 = static_cast<int64_t>(blockIdx.x) * TPB; q0 < nquads; q0 += stride) {
-        const int64_t q = q0 + threadIdx.x;
-        V4 v[N];
-        if (q < nquads) {
-            const float* p = X + 4 * q;
+    // block-uniform trip count so that the warp shuffles in flush() stay convergent; one flush site:
+    // every kFlushIters column quads, and once more after the ragged tail
+    int64_t q0 = static_cast<int64_t>(blockIdx.x) * TPB;
+    bool more = true;
+    while (more) {
+        for (int iter = 0; iter < kFlushIters && q0 < nquads; ++iter, q0 += stride) {
+            const int64_t q = q0 + threadIdx.x;
+            V4 v[N];
+            if (q < nquads) {
+                const float* p = X + 4 * q;
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i] = (NG > 1) ? ldg_cached_v4(p + i * ld) : ldg_stream_v4(p + i * ld);
-        } else {
+                for (int i = 0; i < N; ++i) v[i] = (NG > 1) ? ldg_cached_v4(p + i * ld) : ldg_stream_v4(p + i * ld);
+            } else {
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+            }
+            pair_accumulate<N, G>(v, acc);
         }
-        pair_accumulate<N, G>(v, acc);
-        if (++iter == kFlushIters) {
-            flush_pairs<PG>(acc, wacc, lane);
-            iter = 0;
+        more = q0 < nquads;
+        // ragged tail: columns 4*nquads .. D-1, one per thread of CTA 0
+        if (!more && blockIdx.x == 0 && (D & 3)) {
+            V4 v[N];
+            const int64_t c = 4 * nquads + threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                v[i].lo = (threadIdx.x < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+                v[i].hi = 0ull;
+            }
+            pair_accumulate<N, G>(v, acc);
         }
+        flush_pairs<PG>(acc, wacc, lane);
     }
-    // ragged tail: columns 4*nquads .. D-1, one per thread of CTA 0
-    if (blockIdx.x == 0) {
-        V4 v[N];
-        const int64_t c = 4 * nquads + threadIdx.x;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            v[i].lo = (threadIdx.x < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
-            v[i].hi = 0ull;
-        }
-        pair_accumulate<N, G>(v, acc);
-    }
-    flush_pairs<PG>(acc, wacc, lane);
 }
 
 template <int N, int G>
@@ -132,40 +157,68 @@ __device__ __forceinline__ void group_dispatch(int g, const float* X, int64_t D,
 // ---------------------------------------------------------------------------------
 // Block-cooperative; sd/sk are n*n doubles of shared scratch.  Mirrors svgd.py:15-21:
 // d = (sqrt(sum))^2 as torch.cdist(p=2)**2 does, torch.quantile(d, 0.5) over all n*n
-// entries (stable order statistic + lerp), h = sqrt(0.5*med/ln(n+1)) + 1e-8,
-// K = exp(-d / (2 h^2)); then A = (l2/2 + c) K - c diag(rowsum K), c = s/(N h^2).
+// entries (order statistics of the (value, flat index)-sorted list + lerp),
+// h = sqrt(0.5*med/ln(n+1)) + 1e-8, K = exp(-d / (2 h^2)); then
+// A = (l2/2 + c) K - c diag(rowsum K), c = s/(N h^2).
+// The n*n entries are sorted with a shared-memory bitonic network (padded with +inf to MAXPAD >= n*n,
+// a power of two): ~45 compare-exchange stages at n = 20 instead of an O(n^4) rank count.
+__host__ __device__ constexpr int pow2_ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+template <int MAXPAD>
 __device__ __forceinline__ void bandwidth_device(const double* dist, int n, const BandwidthParams& bp, double* sd, double* sk) {
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     const int nn = n * n;
+    __shared__ double s_key[MAXPAD];
+    __shared__ int s_ord[MAXPAD];
     __shared__ double s_sel[2];
     __shared__ int s_idx[2];
     __shared__ double s_h;
+    int npad = 1;
+    while (npad < nn) npad <<= 1;
 
-    for (int e = tid; e < nn; e += nthreads) {
-        const double r = sqrt(dist[e]);
-        sd[e] = r * r;
+    for (int e = tid; e < npad; e += nthreads) {
+        double v = __longlong_as_double(0x7ff0000000000000LL);  // +inf padding sorts last
+        if (e < nn) {
+            const double r = sqrt(dist[e]);
+            v = r * r;
+            sd[e] = v;
+        }
+        s_key[e] = v;
+        s_ord[e] = e;
     }
     __syncthreads();
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < (npad >> 1); t += nthreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const double a = s_key[i], b = s_key[l];
+                const int ia = s_ord[i], ib = s_ord[l];
+                const bool gt = (a > b) || (a == b && ia > ib);  // total order: value, then flat index
+                if (gt == up) {
+                    s_key[i] = b;
+                    s_key[l] = a;
+                    s_ord[i] = ib;
+                    s_ord[l] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
     const int pos_lo = (nn - 1) / 2;
     const int pos_hi = nn / 2;
-    for (int e = tid; e < nn; e += nthreads) {
-        const double de = sd[e];
-        int rank = 0;
-        for (int k = 0; k < nn; ++k) {
-            const double dk = sd[k];
-            rank += (dk < de || (dk == de && k < e)) ? 1 : 0;
-        }
+    if (tid < 2) {
+        const int pos = tid == 0 ? pos_lo : pos_hi;
+        const int e = s_ord[pos];
         const int i = e / n, j = e - i * n;
-        const int canon = i <= j ? e : j * n + i;
-        if (rank == pos_lo) {
-            s_sel[0] = de;
-            s_idx[0] = canon;
-        }
-        if (rank == pos_hi) {
-            s_sel[1] = de;
-            s_idx[1] = canon;
-        }
+        s_sel[tid] = s_key[pos];
+        s_idx[tid] = i <= j ? e : j * n + i;
     }
     __syncthreads();
     if (tid == 0) {
@@ -257,7 +310,7 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
     }
     if (fuse_bandwidth) {
         __syncthreads();
-        bandwidth_device(dist, N, bp, sd, sk);
+        bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
     }
 }
 
@@ -267,12 +320,15 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
 // one column quad per thread per tile.  Besides keeping ~200 KB per SM in flight, this leaves
 // only gridDim = #SMs partial sets for the deterministic last-CTA reduction.
 // ---------------------------------------------------------------------------------
-__host__ __device__ constexpr int pd_tile_cols(int n) { return 1024 / pair_groups(n); }
+__host__ __device__ constexpr int pd_tile_cols(int n) {
+    return pair_groups(n) == 1 ? 1024 : (pair_groups(n) == 2 ? 512 : (pair_groups(n) <= 4 ? 256 : 128));
+}
 __host__ __device__ constexpr int pd_stage_bytes(int n) { return n * pd_tile_cols(n) * 4; }
 __host__ __device__ constexpr int pd_stages(int n) {
     return (200 * 1024) / pd_stage_bytes(n) > 8 ? 8 : (200 * 1024) / pd_stage_bytes(n);
 }
-constexpr int kPdConsumers = 256;  // pair_groups(n) * pd_tile_cols(n) / 4
+// consumer threads: one column quad of the tile per thread and pair group (256; 192 at n = 16)
+__host__ __device__ constexpr int pd_consumers(int n) { return pair_groups(n) * pd_tile_cols(n) / 4; }
 constexpr int kFlushTiles = 64;
 
 template <int N, int G>
@@ -288,41 +344,42 @@ __device__ __forceinline__ void pairdist_tma_consumer(const float* __restrict__ 
     const int lane = threadIdx.x & 31;
     const int64_t d4 = D & ~static_cast<int64_t>(3);
     const int64_t ntiles = (d4 + TC - 1) / TC;
-    int it = 0, since_flush = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        const uint32_t use = static_cast<uint32_t>(it / STAGES);
-        const int64_t col0 = t * TC;
-        const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
-        mbar_wait(&full_bar[s], use & 1u);
-        const float* sx = tiles + static_cast<size_t>(s) * N * TC + 4 * qi;
-        V4 v[N];
-        if (4 * qi < w) {
+    int it = 0;
+    int64_t t = blockIdx.x;
+    bool more = true;
+    while (more) {  // one flush site: every kFlushTiles tiles, and once more after the ragged tail
+        for (int f = 0; f < kFlushTiles && t < ntiles; ++f, t += gridDim.x, ++it) {
+            const int s = it % STAGES;
+            const uint32_t use = static_cast<uint32_t>(it / STAGES);
+            const int64_t col0 = t * TC;
+            const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
+            mbar_wait(&full_bar[s], use & 1u);
+            const float* sx = tiles + static_cast<size_t>(s) * N * TC + 4 * qi;
+            V4 v[N];
+            if (4 * qi < w) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i] = lds_v4(sx + i * TC);
-        } else {
+                for (int i = 0; i < N; ++i) v[i] = lds_v4(sx + i * TC);
+            } else {
 #pragma unroll
-            for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);  // data is in registers: release the stage
+            pair_accumulate<N, G>(v, acc);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);  // data is in registers: release the stage
-        pair_accumulate<N, G>(v, acc);
-        if (++since_flush == kFlushTiles) {
-            flush_pairs<PG>(acc, wacc, lane);
-            since_flush = 0;
+        more = t < ntiles;
+        if (!more && blockIdx.x == 0 && (D & 3)) {  // ragged tail columns (D % 4)
+            V4 v[N];
+            const int64_t c = d4 + qi;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                v[i].lo = (qi < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+                v[i].hi = 0ull;
+            }
+            pair_accumulate<N, G>(v, acc);
         }
+        flush_pairs<PG>(acc, wacc, lane);
     }
-    if (blockIdx.x == 0) {  // ragged tail columns (D % 4)
-        V4 v[N];
-        const int64_t c = d4 + qi;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            v[i].lo = (qi < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
-            v[i].hi = 0ull;
-        }
-        pair_accumulate<N, G>(v, acc);
-    }
-    flush_pairs<PG>(acc, wacc, lane);
 }
 
 template <int N, int G>
@@ -336,7 +393,7 @@ __device__ __forceinline__ void pairdist_tma_dispatch(int g, const float* X, int
 }
 
 template <int N>
-__global__ void __launch_bounds__(kPdConsumers + 32, 1)
+__global__ void __launch_bounds__(pd_consumers(N) + 32, 1)
 svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double* __restrict__ dist, int accumulate,
                          void* ws, int fuse_bandwidth, BandwidthParams bp) {
     constexpr int P = pair_count(N);
@@ -345,8 +402,9 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
     constexpr int TC = pd_tile_cols(N);
     constexpr int QT = TC / 4;  // consumer threads per pair group
     constexpr int STAGES = pd_stages(N);
+    constexpr int kPdConsumers = pd_consumers(N);
     constexpr int CWARPS = kPdConsumers / 32;
-    static_assert(NG * QT == kPdConsumers, "consumer layout");
+    static_assert(QT % 32 == 0 && kPdConsumers <= 992, "consumer layout");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][N][TC]
     __shared__ double wacc[CWARPS][PG];
@@ -412,7 +470,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
     }
     if (fuse_bandwidth) {
         __syncthreads();
-        bandwidth_device(dist, N, bp, sd, sk);
+        bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
     }
 }
 
@@ -796,7 +854,7 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
                     const BandwidthParams& bp, cudaStream_t st) {
     constexpr int TPB = pairdist_tpb(N);
     constexpr int NG = pair_groups(N);
-    if constexpr (N <= 12) {
+    {
         constexpr int TC = pd_tile_cols(N);
         const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
         int variant = tuning().pairdist_variant;
@@ -811,7 +869,7 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
             int64_t grid = sm_count_cached();
             if (grid > ntiles) grid = ntiles;
             if (grid < 1) grid = 1;
-            svgd_pairdist_tma_kernel<N><<<static_cast<unsigned>(grid), kPdConsumers + 32, smem, st>>>(X, D, ld, dist, accumulate,
+            svgd_pairdist_tma_kernel<N><<<static_cast<unsigned>(grid), pd_consumers(N) + 32, smem, st>>>(X, D, ld, dist, accumulate,
                                                                                                  ws, fuse, bp);
             BDE_CHECK_LAUNCH();
             return BDE_OK;
@@ -828,6 +886,8 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     int per_sm = ctas_per_sm;
     if (tuning().pairdist_ctas_per_sm > 0 && tuning().pairdist_ctas_per_sm < per_sm) per_sm = tuning().pairdist_ctas_per_sm;
     int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
+    // small D: the deterministic last-CTA reduction costs O(grid * pairs); one CTA per SM keeps it short
+    if (tuning().pairdist_ctas_per_sm == 0 && want <= 16 * static_cast<int64_t>(sm_count_cached())) cap = sm_count_cached();
     if (cap > kMaxCtasPairdist) cap = kMaxCtasPairdist;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
