@@ -291,6 +291,20 @@ def other_paths(ops, peak_gbs, dev):
 
     rec("svgd_apply_fused_adam", time_kernel(fused_adam, 10, 3), (12 * nf + 20) * Df,
         f"n={nf} x D={Df}: K2 + {nf} Adam steps in one pass, X in place")
+    # training-step form: the same pass also yields the NEXT step's pair distances + K1b, so a steady-state
+    # SVGD training step (posterior update + n base-optimizer steps) is this ONE launch
+    nk = ops.NextKernel(True, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+    rec("svgd_train_step_fused_sgd",
+        time_kernel(lambda: ops.svgd_apply_sgd(Xf, Gf, scf, buf, buf_initialized=True, out_last=olast, next_kernel=nk, **sgd_kw), 10, 3),
+        (12 * nf + 12) * Df, f"n={nf} x D={Df}: K2 + {nf} SGD steps + next step's K1/K1b in one pass "
+        f"(bytes moved; the reference structure needs {16 * nf + 12 * nf} x D bytes for the same work)")
+
+    def train_adam():
+        ops.svgd_apply_adam(Xf, Gf, scf, buf, buf2, step0=st0[0], lr=1e-5, out_last=olast, next_kernel=nk)
+        st0[0] += nf
+
+    rec("svgd_train_step_fused_adam", time_kernel(train_adam, 10, 3), (12 * nf + 20) * Df,
+        f"n={nf} x D={Df}: K2 + {nf} Adam steps + next step's K1/K1b in one pass")
     del buf2
     Of = torch.empty_like(Xf)
     param = torch.nn.Parameter(Xf[0])

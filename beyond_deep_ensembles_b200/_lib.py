@@ -31,6 +31,10 @@ SIGNATURES = {
     "bde_svgd_apply": [_p, _p, _p, _p, _p, _i, _i64, _i64, _p],
     "bde_svgd_apply_sgd": [_p, _p, _p, _p, _i, _i64, _i64, _p, _i, _d, _d, _d, _d, _i, _p, _p],
     "bde_svgd_apply_adam": [_p, _p, _p, _p, _i, _i64, _i64, _p, _p, _i64, _d, _d, _d, _d, _d, _i, _p, _p],
+    "bde_svgd_train_step_sgd": [_p, _p, _p, _p, _i, _i64, _i64, _p, _i, _d, _d, _d, _d, _i, _p,
+                                _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _p, _sz, _p],
+    "bde_svgd_train_step_adam": [_p, _p, _p, _p, _i, _i64, _i64, _p, _p, _i64, _d, _d, _d, _d, _d, _i, _p,
+                                 _p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _p, _sz, _p],
     "bde_svgd_pairdist_bandwidth": [_p, _i, _i64, _i64, _d, _d, _d, _d, _p, _p, _p, _p, _p, _p, _sz, _p],
     "bde_svgd_host_pairdist": [_p, _i, _i64, _i64, _i64, _p, _p, _p, _sz],
     "bde_svgd_host_apply": [_p, _p, _i, _i64, _i64, _d, _d, _d, _d, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],

@@ -64,6 +64,51 @@ __device__ __forceinline__ float resolve_scale(float host_scale, const float* de
     return dev_scale ? __fmul_rn(host_scale, __ldg(dev_scale)) : host_scale;
 }
 
+// per-element arithmetic shared by the single-tensor and the multi-tensor kernels ------------
+// bbb.py:20  0.5*(2*log(sp/s) - 1 + (s/sp)^2 + ((mp - m)/sp)^2), s = softplus(rho); analytic gradient
+template <bool GRAD>
+__device__ __forceinline__ float kl_gauss_elem(float mv, float rv, float prior_mu, float prior_sigma, float inv_var_p,
+                                               float& dmu, float& drho) {
+    const float sigma = softplus_ref(rv);
+    const float a = __fmul_rn(2.0f, logf(__fdiv_rn(prior_sigma, sigma)));
+    const float ratio = __fdiv_rn(sigma, prior_sigma);
+    const float dm = __fdiv_rn(__fsub_rn(prior_mu, mv), prior_sigma);
+    float kl = __fadd_rn(__fadd_rn(__fsub_rn(a, 1.0f), __fmul_rn(ratio, ratio)), __fmul_rn(dm, dm));
+    kl = __fmul_rn(0.5f, kl);
+    if (GRAD) {
+        dmu = __fmul_rn(__fsub_rn(mv, prior_mu), inv_var_p);
+        const float dsig = __fadd_rn(__fdiv_rn(-1.0f, sigma), __fmul_rn(sigma, inv_var_p));
+        drho = __fmul_rn(dsig, softplus_grad_ref(rv));
+    }
+    return kl;
+}
+
+struct MixtureConsts {
+    float log_pi, log_1mpi;
+    float inv_var1, inv_var2;      // 1/sigma^2
+    float lognorm1, lognorm2;      // -log(sigma) - 0.5*log(2*pi)
+};
+
+// bbb.py:31-34: returns logaddexp(...) (the KL term is its negative) and d(-lse)/dmu
+template <bool GRAD>
+__device__ __forceinline__ float mixture_lse_elem(float mv, const MixtureConsts& c, float& dkl) {
+    // Normal(0, s).log_prob(v) = -v^2/(2 s^2) - log s - log sqrt(2 pi)
+    const float l1 = __fadd_rn(__fmul_rn(-0.5f * c.inv_var1, __fmul_rn(mv, mv)), c.lognorm1);
+    const float l2 = __fadd_rn(__fmul_rn(-0.5f * c.inv_var2, __fmul_rn(mv, mv)), c.lognorm2);
+    const float c1 = fminf(fmaxf(l1, -23.0f), 0.0f);
+    const float c2 = fminf(fmaxf(l2, -23.0f), 0.0f);
+    const float p1 = __fadd_rn(c.log_pi, c1), p2 = __fadd_rn(c.log_1mpi, c2);
+    const float mx = fmaxf(p1, p2), mn = fminf(p1, p2);
+    const float lse = __fadd_rn(mx, log1pf(expf(__fsub_rn(mn, mx))));
+    if (GRAD) {
+        const float w1 = expf(__fsub_rn(p1, lse)), w2 = expf(__fsub_rn(p2, lse));
+        const float d1 = (l1 >= -23.0f && l1 <= 0.0f) ? __fmul_rn(-mv, c.inv_var1) : 0.0f;
+        const float d2 = (l2 >= -23.0f && l2 <= 0.0f) ? __fmul_rn(-mv, c.inv_var2) : 0.0f;
+        dkl = -__fadd_rn(__fmul_rn(w1, d1), __fmul_rn(w2, d2));
+    }
+    return lse;
+}
+
 // K9: Gaussian prior ------------------------------------------------------------------------
 template <bool VEC, bool GRAD, bool ACC>
 __global__ void __launch_bounds__(kEwThreads)
@@ -83,18 +128,10 @@ kl_gauss_kernel(const float* __restrict__ mu, const float* __restrict__ rho, int
             gr = load_quad<VEC, false>(grad_rho, b, P);
         }
         auto f = [&](float mv, float rv, float& gmv, float& grv, bool valid) {
-            const float sigma = softplus_ref(rv);
-            // bbb.py:20  0.5*(2*log(sp/s) - 1 + (s/sp)^2 + ((mp - m)/sp)^2)
-            const float a = __fmul_rn(2.0f, logf(__fdiv_rn(prior_sigma, sigma)));
-            const float ratio = __fdiv_rn(sigma, prior_sigma);
-            const float dm = __fdiv_rn(__fsub_rn(prior_mu, mv), prior_sigma);
-            float kl = __fadd_rn(__fadd_rn(__fsub_rn(a, 1.0f), __fmul_rn(ratio, ratio)), __fmul_rn(dm, dm));
-            kl = __fmul_rn(0.5f, kl);
+            float dmu = 0.0f, drho = 0.0f;
+            const float kl = kl_gauss_elem<GRAD>(mv, rv, prior_mu, prior_sigma, inv_var_p, dmu, drho);
             if (valid) local += static_cast<double>(kl);
             if (GRAD) {
-                const float dmu = __fmul_rn(__fsub_rn(mv, prior_mu), inv_var_p);
-                const float dsig = __fadd_rn(__fdiv_rn(-1.0f, sigma), __fmul_rn(sigma, inv_var_p));
-                const float drho = __fmul_rn(dsig, softplus_grad_ref(rv));
                 gmv = ACC ? fmaf(scale, dmu, gmv) : __fmul_rn(scale, dmu);
                 grv = ACC ? fmaf(scale, drho, grv) : __fmul_rn(scale, drho);
             }
@@ -112,11 +149,6 @@ kl_gauss_kernel(const float* __restrict__ mu, const float* __restrict__ rho, int
 }
 
 // K9b: scale-mixture prior --------------------------------------------------------------------
-struct MixtureConsts {
-    float log_pi, log_1mpi;
-    float inv_var1, inv_var2;      // 1/sigma^2
-    float lognorm1, lognorm2;      // -log(sigma) - 0.5*log(2*pi)
-};
 
 template <bool VEC, bool GRAD, bool ACC>
 __global__ void __launch_bounds__(kEwThreads)
@@ -130,22 +162,10 @@ kl_mixture_kernel(const float* __restrict__ mu, int64_t P, MixtureConsts c, doub
         float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
         if (GRAD && ACC) gm = load_quad<VEC, false>(grad_mu, b, P);
         auto f = [&](float mv, float& gmv, bool valid) {
-            // Normal(0, s).log_prob(v) = -v^2/(2 s^2) - log s - log sqrt(2 pi);  bbb.py:31-34
-            const float l1 = __fadd_rn(__fmul_rn(-0.5f * c.inv_var1, __fmul_rn(mv, mv)), c.lognorm1);
-            const float l2 = __fadd_rn(__fmul_rn(-0.5f * c.inv_var2, __fmul_rn(mv, mv)), c.lognorm2);
-            const float c1 = fminf(fmaxf(l1, -23.0f), 0.0f);
-            const float c2 = fminf(fmaxf(l2, -23.0f), 0.0f);
-            const float p1 = __fadd_rn(c.log_pi, c1), p2 = __fadd_rn(c.log_1mpi, c2);
-            const float mx = fmaxf(p1, p2), mn = fminf(p1, p2);
-            const float lse = __fadd_rn(mx, log1pf(expf(__fsub_rn(mn, mx))));
+            float dkl = 0.0f;
+            const float lse = mixture_lse_elem<GRAD>(mv, c, dkl);
             if (valid) local -= static_cast<double>(lse);
-            if (GRAD) {
-                const float w1 = expf(__fsub_rn(p1, lse)), w2 = expf(__fsub_rn(p2, lse));
-                const float d1 = (l1 >= -23.0f && l1 <= 0.0f) ? __fmul_rn(-mv, c.inv_var1) : 0.0f;
-                const float d2 = (l2 >= -23.0f && l2 <= 0.0f) ? __fmul_rn(-mv, c.inv_var2) : 0.0f;
-                const float dkl = -__fadd_rn(__fmul_rn(w1, d1), __fmul_rn(w2, d2));
-                gmv = ACC ? fmaf(scale, dkl, gmv) : __fmul_rn(scale, dkl);
-            }
+            if (GRAD) gmv = ACC ? fmaf(scale, dkl, gmv) : __fmul_rn(scale, dkl);
         };
         f(m.x, gm.x, b + 0 < P);
         f(m.y, gm.y, b + 1 < P);
@@ -177,6 +197,117 @@ l2_kernel(const float* __restrict__ theta, int64_t D, float l2_scale, double val
         }
     }
     finish_value(local, value_factor, value, ws);
+}
+
+// K9/K10 over a list of tensors: bbb.py:69-76 in ONE launch ------------------------------------
+// The reference walks every parameter of every group and adds its KL (Gaussian parameters) or its
+// l2_scale/2 * ||theta||^2 (deterministic parameters) to one scalar; autograd then runs ~8 backward
+// nodes per tensor.  Here the whole list is one virtual vector of column quads: segment t owns the quads
+// [qoff[t], qoff[t+1]) (each tensor padded to a multiple of 4 elements), a thread finds its segment by
+// binary search and evaluates that segment's term; the value is one deterministic fp64 grid sum.
+constexpr int kPtChunk = 56;
+constexpr int kPtGauss = 0, kPtMixture = 1, kPtL2 = 2;
+struct PriorTable {
+    uint64_t a[kPtChunk];        // mu | theta
+    uint64_t b[kPtChunk];        // rho | 0
+    uint64_t ga[kPtChunk];       // grad of a (0: none)
+    uint64_t gb[kPtChunk];       // grad of b (0: none)
+    int64_t qoff[kPtChunk + 1];  // first quad of every segment
+    int64_t size[kPtChunk];
+    float l2[kPtChunk];          // l2_scale of a deterministic tensor
+    unsigned char kind[kPtChunk];
+    int count;
+};
+
+template <bool GRAD, bool ACC>
+__global__ void __launch_bounds__(kEwThreads)
+prior_terms_kernel(const __grid_constant__ PriorTable tab, float prior_mu, float prior_sigma, MixtureConsts mc, double* value,
+                   int accumulate_value, float host_scale, const float* __restrict__ dev_scale, void* ws) {
+    const float scale = resolve_scale(host_scale, dev_scale);
+    const float inv_var_p = __fdiv_rn(1.0f, __fmul_rn(prior_sigma, prior_sigma));
+    double local = 0.0;
+    const int64_t nq = tab.qoff[tab.count];
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nq;
+         q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        int lo = 0, hi = tab.count - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tab.qoff[mid] <= q)
+                lo = mid;
+            else
+                hi = mid - 1;
+        }
+        const int t = lo;
+        const int64_t P = tab.size[t];
+        const int64_t b = (q - tab.qoff[t]) << 2;
+        const int kind = tab.kind[t];
+        const float* pa = reinterpret_cast<const float*>(tab.a[t]);
+        const float* pb = reinterpret_cast<const float*>(tab.b[t]);
+        float* ga = reinterpret_cast<float*>(tab.ga[t]);
+        float* gb = reinterpret_cast<float*>(tab.gb[t]);
+        const bool vec = ((tab.a[t] | tab.b[t] | tab.ga[t] | tab.gb[t]) & 15u) == 0;
+        const bool want_grad = GRAD && ga != nullptr;
+        float4 m, r = make_float4(0.f, 0.f, 0.f, 0.f), gm = r, gr = r;
+        m = vec ? load_quad<true, true>(pa, b, P) : load_quad<false, true>(pa, b, P);
+        if (kind == kPtGauss) r = vec ? load_quad<true, true>(pb, b, P) : load_quad<false, true>(pb, b, P);
+        if (want_grad && ACC) {
+            gm = vec ? load_quad<true, false>(ga, b, P) : load_quad<false, false>(ga, b, P);
+            if (kind == kPtGauss) gr = vec ? load_quad<true, false>(gb, b, P) : load_quad<false, false>(gb, b, P);
+        }
+        const float mv[4] = {m.x, m.y, m.z, m.w}, rv[4] = {r.x, r.y, r.z, r.w};
+        float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, grv[4] = {gr.x, gr.y, gr.z, gr.w};
+        if (kind == kPtGauss) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float dmu = 0.0f, drho = 0.0f;
+                const float kl = kl_gauss_elem<GRAD>(mv[e], rv[e], prior_mu, prior_sigma, inv_var_p, dmu, drho);
+                if (b + e < P) local += static_cast<double>(kl);
+                if (GRAD) {
+                    gmv[e] = ACC ? fmaf(scale, dmu, gmv[e]) : __fmul_rn(scale, dmu);
+                    grv[e] = ACC ? fmaf(scale, drho, grv[e]) : __fmul_rn(scale, drho);
+                }
+            }
+        } else if (kind == kPtMixture) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float dkl = 0.0f;
+                const float lse = mixture_lse_elem<GRAD>(mv[e], mc, dkl);
+                if (b + e < P) local -= static_cast<double>(lse);
+                if (GRAD) gmv[e] = ACC ? fmaf(scale, dkl, gmv[e]) : __fmul_rn(scale, dkl);
+            }
+        } else {
+            const float l2 = tab.l2[t];
+            const float sl = __fmul_rn(scale, l2);
+            double sq = 0.0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                sq += static_cast<double>(__fmul_rn(mv[e], mv[e]));  // padding lanes are 0
+                if (GRAD) gmv[e] = ACC ? fmaf(sl, mv[e], gmv[e]) : __fmul_rn(sl, mv[e]);
+            }
+            local += 0.5 * static_cast<double>(l2) * sq;
+        }
+        if (want_grad) {
+            const float4 o1 = make_float4(gmv[0], gmv[1], gmv[2], gmv[3]);
+            if (vec)
+                store_quad<true>(ga, b, P, o1);
+            else
+                store_quad<false>(ga, b, P, o1);
+            if (kind == kPtGauss) {
+                const float4 o2 = make_float4(grv[0], grv[1], grv[2], grv[3]);
+                if (vec)
+                    store_quad<true>(gb, b, P, o2);
+                else
+                    store_quad<false>(gb, b, P, o2);
+            }
+        }
+    }
+    __shared__ double cta_val;
+    __shared__ double total;
+    block_sum_fp64(local, &cta_val);
+    if (value == nullptr) return;
+    if (grid_reduce_fp64(&cta_val, 1, ws, &total)) {
+        if (threadIdx.x == 0) *value = accumulate_value ? *value + total : total;
+    }
 }
 
 }  // namespace bde

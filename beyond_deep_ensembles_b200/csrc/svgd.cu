@@ -121,7 +121,7 @@ svgd_apply_opt_scalar_kernel(float* X, const float* __restrict__ G, const float*
     extern template int launch_apply<N_>(const float*, const float*, float*, const float*, const float*, int64_t, \
                                          int64_t, int64_t, int64_t, cudaStream_t);                           \
     extern template int launch_apply_fused<N_>(float*, const float*, const float*, const float*, int64_t, int64_t, \
-                                               int64_t, const BaseOptParams&, cudaStream_t);
+                                               int64_t, const BaseOptParams&, cudaStream_t, const NextDistParams*);
 BDE_FOR_EACH_N(X_)
 #undef X_
 
@@ -212,11 +212,27 @@ int apply_impl(const float* X, const float* G, float* out, const float* K, const
 }
 
 int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ldx,
-                   int64_t ldg, const BaseOptParams& o, cudaStream_t st) {
+                   int64_t ldg, const BaseOptParams& o, cudaStream_t st, const NextDistParams* next, size_t ws_bytes) {
     if (!X || !G || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ldx < D || ldg < D) return BDE_ERR_INVALID_ARG;
     if (o.kind != kOptSgd && o.kind != kOptAdam) return BDE_ERR_INVALID_ARG;
     const bool needs_s0 = o.kind == kOptAdam || o.momentum != 0.0f;
     if ((needs_s0 && !o.state0) || (o.kind == kOptAdam && !o.state1)) return BDE_ERR_INVALID_ARG;
+    if (next) {
+        if (!next->dist || (next->fuse_bandwidth && (!next->bp.K || !next->bp.A || !(next->bp.dataset_size > 0.0))))
+            return BDE_ERR_INVALID_ARG;
+        size_t need = 0;
+        bde_svgd_workspace_bytes(n, &need);
+        if (!next->ws || ws_bytes < need) return BDE_ERR_WORKSPACE;
+    }
+    const bool vec_all = aligned16(X) && aligned16(G) && (ldx % 4 == 0) && (ldg % 4 == 0) &&
+                         (!needs_s0 || aligned16(o.state0)) && (o.kind != kOptAdam || aligned16(o.state1)) &&
+                         (!o.out_last || aligned16(o.out_last));
+    if (next && (D == 0 || n < 2 || n > kNextDistMaxParticles || !vec_all || !has_fast_path(n))) {
+        // no single-pass form for this shape: fused update, then K1 (+K1b) on the updated particles
+        const int rc = apply_opt_impl(X, G, K, A, n, D, ldx, ldg, o, st, nullptr, 0);
+        if (rc != BDE_OK) return rc;
+        return pairdist_impl(X, n, D, ldx, next->dist, 0, next->ws, ws_bytes, next->fuse_bandwidth, next->bp, st);
+    }
     if (D == 0) return BDE_OK;
     const size_t span_x = sizeof(float) * (static_cast<size_t>(n - 1) * ldx + D);
     const size_t span_g = sizeof(float) * (static_cast<size_t>(n - 1) * ldg + D);
@@ -238,7 +254,7 @@ int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int
     switch (n) {
 #define X_(N_) \
     case N_:   \
-        return launch_apply_fused<N_>(X, G, K, A, D, ldx, ldg, o, st);
+        return launch_apply_fused<N_>(X, G, K, A, D, ldx, ldg, o, st, next);
         BDE_FOR_EACH_N(X_)
 #undef X_
         default:
@@ -300,9 +316,8 @@ extern "C" int bde_svgd_step(const float* X, const float* G, float* out, int n, 
     return apply_impl(X, G, out, K, A, n, D, ld, ld, ld, st);
 }
 
-extern "C" int bde_svgd_apply_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
-                                  float* momentum_buf, int buf_initialized, double lr, double momentum, double dampening,
-                                  double weight_decay, int nesterov, float* out_last, bde_stream_t stream) {
+static BaseOptParams sgd_params(float* momentum_buf, int buf_initialized, double lr, double momentum, double dampening,
+                                double weight_decay, int nesterov, float* out_last) {
     BaseOptParams o;
     o.kind = kOptSgd;
     o.lr = static_cast<float>(lr);
@@ -313,14 +328,19 @@ extern "C" int bde_svgd_apply_sgd(float* X, const float* G, const float* K, cons
     o.buf_initialized = buf_initialized ? 1 : 0;
     o.state0 = momentum_buf;
     o.out_last = out_last;
+    return o;
+}
+
+extern "C" int bde_svgd_apply_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
+                                  float* momentum_buf, int buf_initialized, double lr, double momentum, double dampening,
+                                  double weight_decay, int nesterov, float* out_last, bde_stream_t stream) {
+    const BaseOptParams o = sgd_params(momentum_buf, buf_initialized, lr, momentum, dampening, weight_decay, nesterov, out_last);
     return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int bde_svgd_apply_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
-                                   float* exp_avg, float* exp_avg_sq, int64_t step0, double lr, double beta1,
-                                   double beta2, double eps, double weight_decay, int decoupled_weight_decay,
-                                   float* out_last, bde_stream_t stream) {
-    if (n < 1 || n > BDE_MAX_PARTICLES || step0 < 0) return BDE_ERR_INVALID_ARG;
+static BaseOptParams adam_params(int n, float* exp_avg, float* exp_avg_sq, int64_t step0, double lr, double beta1,
+                                 double beta2, double eps, double weight_decay, int decoupled_weight_decay,
+                                 float* out_last) {
     BaseOptParams o;
     o.kind = kOptAdam;
     o.lr = static_cast<float>(lr);
@@ -342,5 +362,54 @@ extern "C" int bde_svgd_apply_adam(float* X, const float* G, const float* K, con
     o.state0 = exp_avg;
     o.state1 = exp_avg_sq;
     o.out_last = out_last;
+    return o;
+}
+
+extern "C" int bde_svgd_apply_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ld,
+                                   float* exp_avg, float* exp_avg_sq, int64_t step0, double lr, double beta1,
+                                   double beta2, double eps, double weight_decay, int decoupled_weight_decay,
+                                   float* out_last, bde_stream_t stream) {
+    if (n < 1 || n > BDE_MAX_PARTICLES || step0 < 0) return BDE_ERR_INVALID_ARG;
+    const BaseOptParams o = adam_params(n, exp_avg, exp_avg_sq, step0, lr, beta1, beta2, eps, weight_decay,
+                                        decoupled_weight_decay, out_last);
     return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream));
+}
+
+static NextDistParams next_params(double* dist_next, int fuse_bandwidth, double l2_reg, double kernel_grad_scale,
+                                  double dataset_size, double h_override, float* K_next, float* A_next, double* info,
+                                  int32_t* sel, void* workspace) {
+    NextDistParams nd;
+    nd.dist = dist_next;
+    nd.ws = workspace;
+    nd.fuse_bandwidth = fuse_bandwidth ? 1 : 0;
+    nd.bp = BandwidthParams{l2_reg, kernel_grad_scale, dataset_size, h_override, K_next, A_next, info, sel};
+    return nd;
+}
+
+extern "C" int bde_svgd_train_step_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                                       int64_t ld, float* momentum_buf, int buf_initialized, double lr, double momentum,
+                                       double dampening, double weight_decay, int nesterov, float* out_last,
+                                       double* dist_next, int fuse_bandwidth, double l2_reg, double kernel_grad_scale,
+                                       double dataset_size, double h_override, float* K_next, float* A_next,
+                                       double* info, int32_t* sel, void* workspace, size_t workspace_bytes,
+                                       bde_stream_t stream) {
+    const BaseOptParams o = sgd_params(momentum_buf, buf_initialized, lr, momentum, dampening, weight_decay, nesterov, out_last);
+    const NextDistParams nd = next_params(dist_next, fuse_bandwidth, l2_reg, kernel_grad_scale, dataset_size, h_override,
+                                          K_next, A_next, info, sel, workspace);
+    return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream), &nd, workspace_bytes);
+}
+
+extern "C" int bde_svgd_train_step_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                                        int64_t ld, float* exp_avg, float* exp_avg_sq, int64_t step0, double lr,
+                                        double beta1, double beta2, double eps, double weight_decay,
+                                        int decoupled_weight_decay, float* out_last, double* dist_next,
+                                        int fuse_bandwidth, double l2_reg, double kernel_grad_scale, double dataset_size,
+                                        double h_override, float* K_next, float* A_next, double* info, int32_t* sel,
+                                        void* workspace, size_t workspace_bytes, bde_stream_t stream) {
+    if (n < 1 || n > BDE_MAX_PARTICLES || step0 < 0) return BDE_ERR_INVALID_ARG;
+    const BaseOptParams o = adam_params(n, exp_avg, exp_avg_sq, step0, lr, beta1, beta2, eps, weight_decay,
+                                        decoupled_weight_decay, out_last);
+    const NextDistParams nd = next_params(dist_next, fuse_bandwidth, l2_reg, kernel_grad_scale, dataset_size, h_override,
+                                          K_next, A_next, info, sel, workspace);
+    return apply_opt_impl(X, G, K, A, n, D, ld, ld, o, static_cast<cudaStream_t>(stream), &nd, workspace_bytes);
 }

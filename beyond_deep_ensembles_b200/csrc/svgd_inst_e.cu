@@ -3,5 +3,5 @@
 namespace bde {
 template int launch_pairdist<16>(const float*, int64_t, int64_t, double*, int, void*, int, const BandwidthParams&, cudaStream_t);
 template int launch_apply<16>(const float*, const float*, float*, const float*, const float*, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
-template int launch_apply_fused<16>(float*, const float*, const float*, const float*, int64_t, int64_t, int64_t, const BaseOptParams&, cudaStream_t);
+template int launch_apply_fused<16>(float*, const float*, const float*, const float*, int64_t, int64_t, int64_t, const BaseOptParams&, cudaStream_t, const NextDistParams*);
 }  // namespace bde

@@ -35,12 +35,24 @@ struct BaseOptParams {
     float* out_last = nullptr;   // optional: new gradient of the LAST particle (what svgd.py:94 leaves in param.grad)
 };
 
+// Training-step form of the fused kernel: the same pass also accumulates the pair distances of the UPDATED
+// particles (the K1 of the next SVGD step), reduces them over the grid like K1 does and, with fuse_bandwidth,
+// lets the last CTA run K1b for the next step (bp.K / bp.A may alias the K / A this launch reads).
+struct NextDistParams {
+    double* dist = nullptr;   // [n*n], written (not accumulated)
+    void* ws = nullptr;       // grid-reduction workspace (bde_svgd_workspace_bytes)
+    int fuse_bandwidth = 0;
+    BandwidthParams bp{};
+};
+constexpr int kNextDistMaxParticles = 10;  // all pairs of a column quad in one thread's registers
+
 int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, int accumulate, void* ws,
                   size_t ws_bytes, int fuse, const BandwidthParams& bp, cudaStream_t st);
 int apply_impl(const float* X, const float* G, float* out, const float* K, const float* A, int n, int64_t D,
                int64_t ldx, int64_t ldg, int64_t ldo, cudaStream_t st);
 // fused form: X is updated in place, `out` is not written (o.out_last receives row n-1 if non-null)
 int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ldx,
-                   int64_t ldg, const BaseOptParams& o, cudaStream_t st);
+                   int64_t ldg, const BaseOptParams& o, cudaStream_t st, const NextDistParams* next = nullptr,
+                   size_t ws_bytes = 0);
 
 }  // namespace bde

@@ -571,7 +571,7 @@ __device__ __forceinline__ float opt_update_scalar(const BaseOptParams& o, int i
 template <int N, int OPT>
 __device__ __forceinline__ void apply_tail_column(const float* X, const float* G, float* out, const float (*sKT)[(N + 3) & ~3],
                                                   const float (*sAT)[(N + 3) & ~3], int64_t c, int64_t ldx, int64_t ldg,
-                                                  int64_t ldo, const BaseOptParams& o) {
+                                                  int64_t ldo, const BaseOptParams& o, float* xnew = nullptr) {
     float res[N];
     for (int i = 0; i < N; ++i) {
         float sacc = 0.0f;
@@ -590,28 +590,72 @@ __device__ __forceinline__ void apply_tail_column(const float* X, const float* G
         if (has_s0) s0 = o.state0[c];
         if (OPT == kOptAdam) s1 = o.state1[c];
         if (o.out_last) o.out_last[c] = res[N - 1];
-        for (int i = 0; i < N; ++i) Xw[i * ldx + c] = opt_update_scalar<OPT>(o, i, res[i], X[i * ldx + c], s0, s1);
+        for (int i = 0; i < N; ++i) {
+            const float xv = opt_update_scalar<OPT>(o, i, res[i], X[i * ldx + c], s0, s1);
+            Xw[i * ldx + c] = xv;
+            if (xnew) xnew[i] = xv;
+        }
         if (OPT == kOptAdam || o.momentum != 0.0f) o.state0[c] = s0;
         if (OPT == kOptAdam) o.state1[c] = s1;
     }
 }
 
-template <int N, int OPT>
+// Tail of the training-step kernels (NEXT): per-warp fp64 pair sums -> CTA sums -> deterministic grid
+// reduction -> the last CTA writes the n*n distance matrix of the updated particles and (optionally) runs K1b.
+template <int N, int WARPS>
+__device__ __forceinline__ void next_dist_epilogue(double (*wacc)[pair_count(N) > 0 ? pair_count(N) : 1],
+                                                   const NextDistParams& nd) {
+    constexpr int P = pair_count(N);
+    __shared__ double cta_vals[P > 0 ? P : 1];
+    __shared__ double total[P > 0 ? P : 1];
+    __shared__ double sd[N * N];
+    __shared__ double sk[N * N];
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    __syncthreads();
+    for (int p = tid; p < P; p += nthreads) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) sacc += wacc[w][p];
+        cta_vals[p] = sacc;
+    }
+    __syncthreads();
+    if (!grid_reduce_fp64(cta_vals, P, nd.ws, total)) return;
+    for (int e = tid; e < N * N; e += nthreads) {
+        const int i = e / N, j = e - i * N;
+        nd.dist[e] = (i != j) ? total[i < j ? pair_index(i, j, N) : pair_index(j, i, N)] : 0.0;
+    }
+    if (nd.fuse_bandwidth) {
+        __syncthreads();
+        bandwidth_device<pow2_ceil(N * N)>(nd.dist, N, nd.bp, sd, sk);
+    }
+}
+
+template <int N, int OPT, bool NEXT = false>
 __global__ void __launch_bounds__(128)
 svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
                   const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
-                  const __grid_constant__ BaseOptParams o) {
+                  const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
     constexpr int NP = (N + 3) & ~3;
     constexpr int JC = apply_row_chunk(N);
+    constexpr int PN = NEXT ? pair_count(N) : 1;  // pair accumulators of the updated particles
+    static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
     // transposed coefficients: sKT[j][i] = K[i][j] so that the i-loop reads contiguous words
     __shared__ __align__(16) float sKT[N][NP];
     __shared__ __align__(16) float sAT[N][NP];
+    __shared__ double wacc[NEXT ? 4 : 1][NEXT ? pair_count(N) : 1];
     for (int e = threadIdx.x; e < N * NP; e += blockDim.x) {
         const int j = e / NP, i = e - j * NP;
         sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
         sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
     }
+    if constexpr (NEXT) {
+        for (int k = threadIdx.x; k < 4 * pair_count(N); k += blockDim.x) (&wacc[0][0])[k] = 0.0;
+    }
     __syncthreads();
+    f32x2 pacc[PN];
+#pragma unroll
+    for (int k = 0; k < PN; ++k) pacc[k] = 0ull;
 
     const int64_t nquads = D >> 2;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -671,19 +715,38 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
                 v.hi = acc[N - 1][1];
                 stg_stream_v4(o.out_last + 4 * q, v);
             }
+            V4 xn[NEXT ? N : 1];
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 V4 x = ld_coherent_v4(xp + i * ldx);
                 opt_update_quad<OPT>(o, i, acc[i][0], acc[i][1], x, s0, s1);
                 stg_stream_v4(xw + i * ldx, x);
+                if constexpr (NEXT) xn[i] = x;
             }
             if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + 4 * q, s0);
             if (OPT == kOptAdam) stg_stream_v4(o.state1 + 4 * q, s1);
+            // this kernel only runs when every thread sees a handful of quads: fp32 partials until the end
+            if constexpr (NEXT) pair_accumulate<N, 0>(xn, pacc);
         }
     }
     // ragged tail columns
-    if (blockIdx.x == 0 && threadIdx.x < (D & 3))
-        apply_tail_column<N, OPT>(X, G, out, sKT, sAT, 4 * nquads + threadIdx.x, ldx, ldg, ldo, o);
+    if constexpr (NEXT) {
+        V4 xt[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) xt[i].lo = xt[i].hi = 0ull;
+        if (blockIdx.x == 0 && threadIdx.x < (D & 3)) {
+            float xnew[N];
+            apply_tail_column<N, OPT>(X, G, out, sKT, sAT, 4 * nquads + threadIdx.x, ldx, ldg, ldo, o, xnew);
+#pragma unroll
+            for (int i = 0; i < N; ++i) xt[i].lo = pack2(xnew[i], 0.0f);
+        }
+        pair_accumulate<N, 0>(xt, pacc);
+        flush_pairs<PN>(pacc, wacc[threadIdx.x >> 5], threadIdx.x & 31);
+        next_dist_epilogue<N, 4>(wacc, nd);
+    } else {
+        if (blockIdx.x == 0 && threadIdx.x < (D & 3))
+            apply_tail_column<N, OPT>(X, G, out, sKT, sAT, 4 * nquads + threadIdx.x, ldx, ldg, ldo, o);
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -704,11 +767,13 @@ __host__ __device__ constexpr int apply_stages(int n, int opt = 0) {
     return (200 * 1024) / apply_stage_bytes(n, opt) > 8 ? 8 : (200 * 1024) / apply_stage_bytes(n, opt);
 }
 
-template <int N, int OPT>
+template <int N, int OPT, bool NEXT = false>
 __global__ void __launch_bounds__(apply_tile_cols(N) / 4 + 32, 1)
 svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
                       const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
-                      const __grid_constant__ BaseOptParams o) {
+                      const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
+    static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
+    constexpr int PN = NEXT ? pair_count(N) : 1;
     constexpr int NP = (N + 3) & ~3;
     constexpr int TC = apply_tile_cols(N);
     constexpr int STAGES = apply_stages(N, OPT);
@@ -721,12 +786,16 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
     __shared__ __align__(16) float sAT[N][NP];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ double wacc[NEXT ? CWARPS : 1][NEXT ? pair_count(N) : 1];
 
     const int tid = threadIdx.x;
     for (int e = tid; e < N * NP; e += blockDim.x) {
         const int j = e / NP, i = e - j * NP;
         sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
         sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
+    }
+    if constexpr (NEXT) {
+        for (int k = tid; k < CWARPS * pair_count(N); k += blockDim.x) (&wacc[0][0])[k] = 0.0;
     }
     if (tid == 0) {
 #pragma unroll
@@ -770,6 +839,9 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
         }
     } else {
         const int lane = tid & 31;
+        f32x2 pacc[PN];
+#pragma unroll
+        for (int k = 0; k < PN; ++k) pacc[k] = 0ull;
         int it = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int s = it % STAGES;
@@ -816,6 +888,11 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
             } else {
                 V4 s0, s1;
                 s0.lo = s0.hi = s1.lo = s1.hi = 0ull;
+                V4 xn[NEXT ? N : 1];
+                if constexpr (NEXT) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) xn[i].lo = xn[i].hi = 0ull;
+                }
                 if (active) {
                     float* xw = const_cast<float*>(X) + col0 + 4 * tid;
                     if (has_s0) s0 = lds_v4(sg + N * TC);
@@ -831,6 +908,7 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                         V4 x = lds_v4(sx + i * TC);
                         opt_update_quad<OPT>(o, i, acc[i][0], acc[i][1], x, s0, s1);
                         stg_stream_v4(xw + i * ldx, x);
+                        if constexpr (NEXT) xn[i] = x;
                     }
                 }
                 __syncwarp();
@@ -839,11 +917,31 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                     if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + col0 + 4 * tid, s0);
                     if (OPT == kOptAdam) stg_stream_v4(o.state1 + col0 + 4 * tid, s1);
                 }
+                if constexpr (NEXT) {
+                    // the K1 of the next step, on the updated particles while they are still in registers
+                    pair_accumulate<N, 0>(xn, pacc);
+                    if ((it % kFlushTiles) == kFlushTiles - 1) flush_pairs<PN>(pacc, wacc[tid >> 5], lane);  // `it` is CTA-uniform
+                }
             }
         }
         // ragged tail columns (D % 4), CTA 0 only
-        if (blockIdx.x == 0 && tid < (D & 3)) apply_tail_column<N, OPT>(X, G, out, sKT, sAT, d4 + tid, ldx, ldg, ldo, o);
+        if constexpr (NEXT) {
+            V4 xt[N];
+#pragma unroll
+            for (int i = 0; i < N; ++i) xt[i].lo = xt[i].hi = 0ull;
+            if (blockIdx.x == 0 && tid < (D & 3)) {
+                float xnew[N];
+                apply_tail_column<N, OPT>(X, G, out, sKT, sAT, d4 + tid, ldx, ldg, ldo, o, xnew);
+#pragma unroll
+                for (int i = 0; i < N; ++i) xt[i].lo = pack2(xnew[i], 0.0f);
+            }
+            pair_accumulate<N, 0>(xt, pacc);
+            flush_pairs<PN>(pacc, wacc[tid >> 5], lane);
+        } else {
+            if (blockIdx.x == 0 && tid < (D & 3)) apply_tail_column<N, OPT>(X, G, out, sKT, sAT, d4 + tid, ldx, ldg, ldo, o);
+        }
     }
+    if constexpr (NEXT) next_dist_epilogue<N, CWARPS>(wacc, nd);
 }
 
 // ---------------------------------------------------------------------------------
@@ -897,9 +995,10 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     return BDE_OK;
 }
 
-template <int N, int OPT>
+template <int N, int OPT, bool NEXT = false>
 int launch_apply_opt(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
-                     int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st) {
+                     int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st,
+                     const NextDistParams& nd = NextDistParams{}) {
     const int64_t nquads = D >> 2;
     constexpr int TC = apply_tile_cols(N);
     const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
@@ -912,28 +1011,31 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
         static_assert(apply_stages(N, OPT) >= 2, "ring too shallow");
         static bool configured = false;
         if (!configured) {
-            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             configured = true;
         }
         int64_t grid = sm_count_cached();
         if (grid > ntiles) grid = ntiles;
         if (grid < 1) grid = 1;
-        svgd_apply_tma_kernel<N, OPT><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o);
+        svgd_apply_tma_kernel<N, OPT, NEXT><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
         BDE_CHECK_LAUNCH();
         return BDE_OK;
     }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         int v = 0;
-        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N, OPT>, 128, 0));
+        BDE_RETURN_IF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, svgd_apply_kernel<N, OPT, NEXT>, 128, 0));
         ctas_per_sm = v > 0 ? v : 1;
     }
     int64_t want = (nquads + 127) / 128;
     const int per_sm = tuning().apply_ctas_per_sm > 0 ? tuning().apply_ctas_per_sm : ctas_per_sm;
-    const int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
+    int64_t cap = static_cast<int64_t>(sm_count_cached()) * per_sm;
+    // training-step form: the deterministic last-CTA reduction costs O(grid * pairs) -> one CTA per SM at small D
+    if (NEXT && tuning().apply_ctas_per_sm == 0 && want <= 16 * static_cast<int64_t>(sm_count_cached())) cap = sm_count_cached();
+    if (NEXT && cap > kMaxCtasPairdist) cap = kMaxCtasPairdist;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    svgd_apply_kernel<N, OPT><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o);
+    svgd_apply_kernel<N, OPT, NEXT><<<static_cast<unsigned>(want), 128, 0, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }
@@ -944,10 +1046,19 @@ int launch_apply(const float* X, const float* G, float* out, const float* K, con
     return launch_apply_opt<N, kOptNone>(X, G, out, K, A, D, ldx, ldg, ldo, BaseOptParams{}, st);
 }
 
-// fused K2 + base-optimizer step; X updated in place
+// fused K2 + base-optimizer step; X updated in place.  next != nullptr (n <= kNextDistMaxParticles): the
+// training-step form that also produces the pair distances of the updated particles.
 template <int N>
 int launch_apply_fused(float* X, const float* G, const float* K, const float* A, int64_t D, int64_t ldx, int64_t ldg,
-                       const BaseOptParams& o, cudaStream_t st) {
+                       const BaseOptParams& o, cudaStream_t st, const NextDistParams* next) {
+    if constexpr (N <= kNextDistMaxParticles) {
+        if (next) {
+            if (o.kind == kOptSgd) return launch_apply_opt<N, kOptSgd, true>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st, *next);
+            return launch_apply_opt<N, kOptAdam, true>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st, *next);
+        }
+    } else {
+        if (next) return BDE_ERR_UNSUPPORTED_N;
+    }
     if (o.kind == kOptSgd) return launch_apply_opt<N, kOptSgd>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st);
     return launch_apply_opt<N, kOptAdam>(X, G, nullptr, K, A, D, ldx, ldg, 0, o, st);
 }

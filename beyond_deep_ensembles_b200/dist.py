@@ -23,13 +23,18 @@ def allreduce_dist(sc: "ops.SvgdScratch", group=None) -> None:
 
 
 def svgd_kernel_sharded(X: torch.Tensor, sc: "ops.SvgdScratch", l2_reg: float, kernel_grad_scale: float,
-                        dataset_size: float, h_override: float = 0.0, group=None) -> None:
+                        dataset_size: float, h_override: float = 0.0, group=None, have_partial: bool = False) -> None:
     """K1 (local partial distances) -> all-reduce of n*n fp64 -> K1b (identical on every rank): leaves
-    K and A in `sc`.  With a single rank K1b runs in K1's tail (one launch)."""
+    K and A in `sc`.  With a single rank K1b runs in K1's tail (one launch).  have_partial: sc.dist
+    already holds this rank's partial sums for the current X (left by the previous training-step launch)."""
     if world(group) == 1:
-        ops.svgd_pairdist_bandwidth(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+        if have_partial:
+            ops.svgd_bandwidth(sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+        else:
+            ops.svgd_pairdist_bandwidth(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
         return
-    ops.svgd_pairdist(X, sc)
+    if not have_partial:
+        ops.svgd_pairdist(X, sc)
     allreduce_dist(sc, group)
     ops.svgd_bandwidth(sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
 

@@ -158,20 +158,26 @@ class FusedBasePlan:
         return True, int(steps.pop())
 
     # ------------------------------------------------------------------ launch
-    def launch(self, X: torch.Tensor, G: torch.Tensor, sc, out_last: torch.Tensor, initialized: bool, step0: int) -> None:
+    def launch(self, X: torch.Tensor, G: torch.Tensor, sc, out_last: torch.Tensor, initialized: bool, step0: int,
+               next_kernel: "ops.NextKernel | None" = None) -> bool:
+        """Run the fused K2 + base-optimizer launch(es).  With `next_kernel` and a single column segment
+        the training-step form is used; returns True when sc.dist then holds the pair distances of the
+        updated particles."""
         n = X.shape[0]
+        nk = next_kernel if (next_kernel is not None and len(self.segments) == 1) else None
         for c0, c1, g in self.segments:
             Xs, Gs, ol = X[:, c0:c1], G[:, c0:c1], out_last[c0:c1]
             if self.kind == _SGD:
                 ops.svgd_apply_sgd(Xs, Gs, sc, self.state0[c0:c1] if g["momentum"] != 0 else None,
                                    buf_initialized=initialized, lr=g["lr"], momentum=g["momentum"],
                                    dampening=g["dampening"], weight_decay=g["weight_decay"], nesterov=g["nesterov"],
-                                   out_last=ol)
+                                   out_last=ol, next_kernel=nk)
             else:
                 decoupled = self.kind == _ADAMW or bool(g.get("decoupled_weight_decay"))
                 ops.svgd_apply_adam(Xs, Gs, sc, self.state0[c0:c1], self.state1[c0:c1], step0=step0, lr=g["lr"],
                                     beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"],
-                                    weight_decay=g["weight_decay"], decoupled_weight_decay=decoupled, out_last=ol)
+                                    weight_decay=g["weight_decay"], decoupled_weight_decay=decoupled, out_last=ol,
+                                    next_kernel=nk)
         state = self.base.state
         if self.kind == _SGD:
             if self._uses_state0 and not initialized:
@@ -181,3 +187,4 @@ class FusedBasePlan:
             torch._foreach_add_([state[p]["step"] for p in self.plist], float(n))
         # lr_scheduler's "step() before optimizer.step()" check looks at this flag
         self.base._opt_called = True
+        return nk is not None

@@ -110,10 +110,31 @@ def svgd_apply(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScra
     return out
 
 
+NEXT_KERNEL_MAX_PARTICLES = 10  # single-pass training-step form (kNextDistMaxParticles in csrc/svgd_internal.h)
+
+
+@dataclass
+class NextKernel:
+    """Ask the fused apply kernels for the training-step form: the same pass leaves the pair distances
+    of the UPDATED particles in sc.dist (this rank's partial sums) and, with fuse_bandwidth, the next
+    step's K / A / info / sel in `sc` (K1b in the tail of the launch; single-rank jobs)."""
+    fuse_bandwidth: bool
+    l2_reg: float
+    kernel_grad_scale: float
+    dataset_size: float
+    h_override: float = 0.0
+
+    def args(self, sc: "SvgdScratch"):
+        return (sc.dist.data_ptr(), int(self.fuse_bandwidth), float(self.l2_reg), float(self.kernel_grad_scale),
+                float(self.dataset_size), float(self.h_override or 0.0), sc.K.data_ptr(), sc.A.data_ptr(),
+                sc.info.data_ptr(), sc.sel.data_ptr(), sc.ws.data_ptr(), sc.ws_bytes)
+
+
 def svgd_apply_sgd(X: torch.Tensor, G: torch.Tensor, sc: SvgdScratch, momentum_buf, *, buf_initialized: bool, lr: float,
                    momentum: float = 0.0, dampening: float = 0.0, weight_decay: float = 0.0, nesterov: bool = False,
-                   out_last=None) -> None:
-    """K2 fused with n shared-state torch.optim.SGD steps (svgd.py:92-103); X is updated in place."""
+                   out_last=None, next_kernel: NextKernel | None = None) -> None:
+    """K2 fused with n shared-state torch.optim.SGD steps (svgd.py:92-103); X is updated in place.
+    With `next_kernel` the launch also produces the next step's pair distances (see NextKernel)."""
     require_cuda(X, G, momentum_buf, out_last)
     _lib.require_f32(X, G, momentum_buf, out_last)
     n, D, ld = _rows(X)
@@ -124,15 +145,20 @@ def svgd_apply_sgd(X: torch.Tensor, G: torch.Tensor, sc: SvgdScratch, momentum_b
             raise ValueError("optimizer state / out_last must be [D]")
     if momentum != 0.0 and momentum_buf is None:
         raise ValueError("momentum needs a momentum buffer")
-    _lib.call("bde_svgd_apply_sgd", X.data_ptr(), G.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(), n, D, ld,
-              _lib.ptr(momentum_buf), int(buf_initialized), float(lr), float(momentum), float(dampening),
-              float(weight_decay), int(bool(nesterov)), _lib.ptr(out_last), _s(X))
+    args = (X.data_ptr(), G.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(), n, D, ld,
+            _lib.ptr(momentum_buf), int(buf_initialized), float(lr), float(momentum), float(dampening),
+            float(weight_decay), int(bool(nesterov)), _lib.ptr(out_last))
+    if next_kernel is None:
+        _lib.call("bde_svgd_apply_sgd", *args, _s(X))
+    else:
+        _lib.call("bde_svgd_train_step_sgd", *args, *next_kernel.args(sc), _s(X))
 
 
 def svgd_apply_adam(X: torch.Tensor, G: torch.Tensor, sc: SvgdScratch, exp_avg, exp_avg_sq, *, step0: int, lr: float,
                     beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0,
-                    decoupled_weight_decay: bool = False, out_last=None) -> None:
-    """K2 fused with n shared-state torch.optim.Adam / AdamW steps; particle i takes step step0+i+1."""
+                    decoupled_weight_decay: bool = False, out_last=None, next_kernel: NextKernel | None = None) -> None:
+    """K2 fused with n shared-state torch.optim.Adam / AdamW steps; particle i takes step step0+i+1.
+    With `next_kernel` the launch also produces the next step's pair distances (see NextKernel)."""
     require_cuda(X, G, exp_avg, exp_avg_sq, out_last)
     _lib.require_f32(X, G, exp_avg, exp_avg_sq, out_last)
     n, D, ld = _rows(X)
@@ -141,9 +167,13 @@ def svgd_apply_adam(X: torch.Tensor, G: torch.Tensor, sc: SvgdScratch, exp_avg, 
     for t in (exp_avg, exp_avg_sq, out_last):
         if t is not None and _vec(t).numel() != D:
             raise ValueError("optimizer state / out_last must be [D]")
-    _lib.call("bde_svgd_apply_adam", X.data_ptr(), G.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(), n, D, ld,
-              exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(step0), float(lr), float(beta1), float(beta2), float(eps),
-              float(weight_decay), int(bool(decoupled_weight_decay)), _lib.ptr(out_last), _s(X))
+    args = (X.data_ptr(), G.data_ptr(), sc.K.data_ptr(), sc.A.data_ptr(), n, D, ld,
+            exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(step0), float(lr), float(beta1), float(beta2), float(eps),
+            float(weight_decay), int(bool(decoupled_weight_decay)), _lib.ptr(out_last))
+    if next_kernel is None:
+        _lib.call("bde_svgd_apply_adam", *args, _s(X))
+    else:
+        _lib.call("bde_svgd_train_step_adam", *args, *next_kernel.args(sc), _s(X))
 
 
 def svgd_pairdist_bandwidth(X: torch.Tensor, sc: SvgdScratch, l2_reg: float, kernel_grad_scale: float,

@@ -45,9 +45,17 @@ class SVGDOptimizer(BayesianOptimizer):
     torch.optim.SGD / Adam / AdamW and no GradScaler is active, its n per-particle steps
     (svgd.py:92-103) run inside the apply kernel (fused_base.py); set it to False to always call
     `base_optimizer.step()` per particle.
+
+    `reuse_pair_distances` (class attribute, default True): the fused launch also computes the pair
+    distances of the particles it has just updated (n <= 10), which are exactly what `rbf` needs at the
+    next step() — so a training loop reads the particles once per step.  The cached kernel is only valid
+    while nothing but this optimizer writes the particles; load_state_dict() and every unfused step drop
+    it, and code that edits `state[param]["particle_i"]` in place between steps must call
+    `invalidate_kernel_cache()` (or set the attribute to False).
     """
 
     fuse_base_optimizer = True
+    reuse_pair_distances = True
 
     def __init__(self, params, reset_params_closure, base_optimizer, particle_count, dataset_size, l2_reg=0.0,
                  kernel_grad_scale=1.0, process_group=None):
@@ -73,6 +81,10 @@ class SVGDOptimizer(BayesianOptimizer):
         self._fused_plan = None
         self._scratch = ops.SvgdScratch.allocate(n, device)
         self._group = process_group
+        # what self._scratch holds for the CURRENT particles: None, "partial" (this rank's pair-distance sums,
+        # not yet all-reduced) or "kernel" (K, A, info, sel ready)
+        self._cached = None
+        self._cached_hyper = None
         self._xviews = [self._layout.views(self._X[i]) for i in range(n)]
         self._gviews = [self._layout.views(self._G[i]) for i in range(n)]
         self._oviews = None
@@ -106,14 +118,25 @@ class SVGDOptimizer(BayesianOptimizer):
             self._store_grads(particle_idx, plist)
 
         with torch.no_grad():
-            # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b
-            bdist.svgd_kernel_sharded(self._X, self._scratch, self.state["__l2_reg"], self.state["__kernel_grad_scale"],
-                                      self.state["__dataset_size"], 0.0, self._group)
+            hyper = (self.state["__l2_reg"], self.state["__kernel_grad_scale"], self.state["__dataset_size"])
+            cached = self._cached if (self.reuse_pair_distances and self._cached_hyper == hyper) else None
+            self._cached = None
+            if cached != "kernel":
+                # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b
+                bdist.svgd_kernel_sharded(self._X, self._scratch, *hyper, 0.0, self._group,
+                                          have_partial=(cached == "partial"))
             plan = self._plan_for(base, grad_scaler, plist)
             bound = plan.bind_state() if plan is not None else None
             if bound is not None:
-                # f1: K2 + the n shared-state base-optimizer steps of svgd.py:92-103 in one pass; X in place
-                plan.launch(self._X, self._G, self._scratch, self._out_last[0], *bound)
+                # f1: K2 + the n shared-state base-optimizer steps of svgd.py:92-103 in one pass; X in place.
+                # Training-step form (n <= 10): the pass also leaves the next step's pair distances in the
+                # scratch; a single rank finishes K1b in the same launch, D-sharded ranks all-reduce next step.
+                nk = None
+                if self.reuse_pair_distances and 2 <= n <= ops.NEXT_KERNEL_MAX_PARTICLES:
+                    nk = ops.NextKernel(bdist.world(self._group) == 1, *hyper)
+                if plan.launch(self._X, self._G, self._scratch, self._out_last[0], *bound, next_kernel=nk):
+                    self._cached = "kernel" if nk.fuse_bandwidth else "partial"
+                    self._cached_hyper = hyper
                 for param, xview, oview in zip(plist, self._xviews[n - 1], self._oviews_last):
                     param.grad = oview
                     param.data = xview
@@ -150,6 +173,10 @@ class SVGDOptimizer(BayesianOptimizer):
             plan = self._fused_plan = FusedBasePlan.build(base, plist, self._layout, self._X.device)
         return plan
 
+    def invalidate_kernel_cache(self):
+        """Forget the pair distances computed by the last fused launch (see `reuse_pair_distances`)."""
+        self._cached = None
+
     def sample_parameters(self):
         """Cycles through the particles (svgd.py:107-112)."""
         self._use_particle(self.state["__current_particle"])
@@ -184,6 +211,7 @@ class SVGDOptimizer(BayesianOptimizer):
         """Accepts reference-written state dicts: per-parameter `particle_i` tensors are copied
         into the arena rows and the state keeps pointing at the arena views."""
         super().load_state_dict(state_dict)
+        self._cached = None
         n = self.state["__particle_count"]
         if n != self._X.shape[0]:
             raise ValueError("particle_count of the checkpoint differs from this optimizer")

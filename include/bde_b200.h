@@ -136,6 +136,32 @@ int bde_svgd_apply_adam(float* X, const float* G, const float* K, const float* A
                         int decoupled_weight_decay, float* out_last, bde_stream_t stream);
 
 /*
+ * Training-step form of the two entries above: the SAME pass also accumulates the squared pair
+ * distances of the UPDATED particles — the K1 of the next SVGD step (svgd.py:15 on the next call of
+ * step()), so that a training loop reads X once per step instead of twice.  dist_next [n*n] fp64 is
+ * written (symmetric, zero diagonal; under D-sharding it is this rank's partial sum, to be all-reduced).
+ * fuse_bandwidth != 0 additionally runs K1b on dist_next in the tail of the same launch and writes the
+ * NEXT step's K_next / A_next / info / sel (K_next / A_next may alias K / A: every CTA has consumed the
+ * current coefficients before the last CTA writes the new ones).  workspace as for bde_svgd_pairdist.
+ * One launch for n <= 10 on 16-byte-aligned rows; any other shape runs the fused update followed by K1.
+ */
+int bde_svgd_train_step_sgd(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                            int64_t ld, float* momentum_buf, int buf_initialized, double lr,
+                            double momentum, double dampening, double weight_decay, int nesterov,
+                            float* out_last, double* dist_next, int fuse_bandwidth, double l2_reg,
+                            double kernel_grad_scale, double dataset_size, double h_override,
+                            float* K_next, float* A_next, double* info, int32_t* sel, void* workspace,
+                            size_t workspace_bytes, bde_stream_t stream);
+int bde_svgd_train_step_adam(float* X, const float* G, const float* K, const float* A, int n, int64_t D,
+                             int64_t ld, float* exp_avg, float* exp_avg_sq, int64_t step0, double lr,
+                             double beta1, double beta2, double eps, double weight_decay,
+                             int decoupled_weight_decay, float* out_last, double* dist_next,
+                             int fuse_bandwidth, double l2_reg, double kernel_grad_scale,
+                             double dataset_size, double h_override, float* K_next, float* A_next,
+                             double* info, int32_t* sel, void* workspace, size_t workspace_bytes,
+                             bde_stream_t stream);
+
+/*
  * Host-buffer entries (the end-to-end path): X_host/G_host/out_host are HOST arrays
  * [n, D] with row stride ld_host (pinned memory gives full PCIe bandwidth).  The
  * columns are streamed through the device in `chunk_cols`-wide pieces (a multiple of 4)

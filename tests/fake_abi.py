@@ -120,6 +120,32 @@ class FakeLib:
             _f32(out_last, D).copy_(res[n - 1])
         return 0
 
+    def _next(self, X, n, D, ld, dist_next, fuse, l2, kgs, N, h_override, K_next, A_next, info, sel, ws, wsb, stream):
+        self.bde_svgd_pairdist(X, n, D, ld, dist_next, 0, ws, wsb, stream)
+        if fuse:
+            self.bde_svgd_bandwidth(dist_next, n, l2, kgs, N, h_override, K_next, A_next, info, sel, stream)
+        return 0
+
+    def bde_svgd_train_step_sgd(self, X, G, K, A, n, D, ld, buf, buf_init, lr, momentum, dampening, wd, nesterov,
+                                out_last, *rest):
+        self.bde_svgd_apply_sgd(X, G, K, A, n, D, ld, buf, buf_init, lr, momentum, dampening, wd, nesterov, out_last,
+                                rest[-1])
+        self.calls[-1] = "train_step_sgd"
+        n_calls = len(self.calls)
+        rc = self._next(X, n, D, ld, *rest)
+        del self.calls[n_calls:]
+        return rc
+
+    def bde_svgd_train_step_adam(self, X, G, K, A, n, D, ld, exp_avg, exp_avg_sq, step0, lr, b1, b2, eps, wd, decoupled,
+                                 out_last, *rest):
+        self.bde_svgd_apply_adam(X, G, K, A, n, D, ld, exp_avg, exp_avg_sq, step0, lr, b1, b2, eps, wd, decoupled,
+                                 out_last, rest[-1])
+        self.calls[-1] = "train_step_adam"
+        n_calls = len(self.calls)
+        rc = self._next(X, n, D, ld, *rest)
+        del self.calls[n_calls:]
+        return rc
+
     def bde_svgd_step(self, X, G, out, n, D, ld, l2, kgs, N, h_override, dist, K, A, info, sel, ws, wsb, stream):
         self.bde_svgd_pairdist(X, n, D, ld, dist, 0, ws, wsb, stream)
         self.bde_svgd_bandwidth(dist, n, l2, kgs, N, h_override, K, A, info, sel, stream)

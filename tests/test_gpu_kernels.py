@@ -332,6 +332,108 @@ def test_fused_apply_base_optimizer_vs_oracle(ops, cuda_lib, variant, opt, n, D,
         cuda_lib.bde_tune(b"apply_variant", 0)
 
 
+@pytest.mark.parametrize("variant", [1, 2], ids=["direct", "tma"])
+@pytest.mark.parametrize("opt", ["sgd-cifar", "sgd-plain", "adam", "adamw"])
+@pytest.mark.parametrize("n,D,ld,mis", [(10, 4099, 4100, 0), (10, 501, 512, 0), (5, 37, 40, 0), (2, 9, 12, 0), (10, 3, 4, 0),
+                                        (7, 70_001, 70_004, 0), (10, 300_000, 300_000, 0), (3, 200_000, 200_000, 0),
+                                        (9, 1000, 1001, 0), (10, 1000, 1000, 1), (12, 5003, 5004, 0), (20, 1000, 1000, 0),
+                                        (13, 700, 700, 0)])
+def test_train_step_next_distances(ops, cuda_lib, variant, opt, n, D, ld, mis):
+    """bde_svgd_train_step_*: the particles are updated exactly as by bde_svgd_apply_* (bit for bit), and the
+    same launch leaves the pair distances / K / A / selection of the UPDATED particles — what K1 + K1b
+    return when run on them afterwards.  n > 10, unaligned rows: the documented two-launch form."""
+    kind, hyper = OPT_KINDS[opt]
+    X, G = particles(n, D, seed=n * 17 + D)
+    X *= 4.0
+    G *= 50.0
+    dG = dev_matrix(G, ld, mis)
+    dXa, dXb, dXc = dev_matrix(X, ld, mis), dev_matrix(X, ld, mis), dev_matrix(X, ld, mis)
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    scb, scc, scr = (ops.SvgdScratch.allocate(n, "cuda") for _ in range(3))
+    ops.svgd_pairdist_bandwidth(dXa, sc, 0.01, 1.0, 768.0)
+    for t in (scb, scc):
+        t.K.copy_(sc.K)
+        t.A.copy_(sc.A)
+
+    def state():
+        return tuple(torch.zeros(D + 8, device="cuda")[mis:mis + D] for _ in range(3))
+
+    cuda_lib.bde_tune(b"apply_variant", variant)
+    try:
+        for step in range(2):
+            if step == 0:
+                sa, sb, s_c = state(), state(), state()
+            args = dict(initialized=step > 0, step0=step * n)
+            fused_apply(ops, kind, hyper, dXa, dG, sc, sa[0], sa[1], out_last=sa[2], **args)
+            nk = ops.NextKernel(True, 0.01, 1.0, 768.0)
+            if kind == "sgd":
+                ops.svgd_apply_sgd(dXb, dG, scb, sb[0] if hyper.get("momentum", 0) != 0 else None, buf_initialized=step > 0,
+                                   out_last=sb[2], next_kernel=nk, **hyper)
+                ops.svgd_apply_sgd(dXc, dG, scc, s_c[0] if hyper.get("momentum", 0) != 0 else None, buf_initialized=step > 0,
+                                   out_last=s_c[2], next_kernel=ops.NextKernel(False, 0.01, 1.0, 768.0), **hyper)
+            else:
+                akw = dict(step0=step * n, lr=hyper["lr"], beta1=hyper["betas"][0], beta2=hyper["betas"][1], eps=hyper["eps"],
+                           weight_decay=hyper["weight_decay"], decoupled_weight_decay=(kind == "adamw"))
+                ops.svgd_apply_adam(dXb, dG, scb, sb[0], sb[1], out_last=sb[2], next_kernel=nk, **akw)
+                ops.svgd_apply_adam(dXc, dG, scc, s_c[0], s_c[1], out_last=s_c[2],
+                                    next_kernel=ops.NextKernel(False, 0.01, 1.0, 768.0), **akw)
+            # (1) same update, bit for bit, as the launch without the distance pass
+            assert torch.equal(dXb, dXa) and torch.equal(dXc, dXa)
+            for a, b in zip(sa, sb):
+                assert torch.equal(a, b)
+            # (2) distances of the updated particles: fp64 oracle, and K1 run on them afterwards
+            d_ref = O.svgd_pairdist(dXb.cpu())
+            np.testing.assert_allclose(scb.dist.cpu().numpy(), d_ref.numpy(), rtol=2e-6, atol=1e-12)
+            np.testing.assert_allclose(scc.dist.cpu().numpy(), scb.dist.cpu().numpy(), rtol=1e-12, atol=1e-15)
+            ops.svgd_pairdist_bandwidth(dXb, scr, 0.01, 1.0, 768.0)
+            np.testing.assert_allclose(scb.dist.cpu().numpy(), scr.dist.cpu().numpy(), rtol=1e-9, atol=1e-12)
+            # (3) K1b of the next step ran in the tail: same selection, same coefficients
+            bw = O.svgd_bandwidth(d_ref, 0.01, 1.0, 768.0)
+            assert tuple(scb.sel.cpu().tolist()) == bw["sel"]
+            np.testing.assert_allclose(scb.K.cpu().numpy(), bw["K"].numpy(), rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(scb.A.cpu().numpy(), bw["A"].numpy(), rtol=1e-5, atol=1e-9)
+            np.testing.assert_allclose(scb.info.cpu().numpy()[0], bw["h"], rtol=1e-6)
+            # (4) without fuse_bandwidth the coefficients are left alone; refresh them for the next round
+            assert torch.equal(scc.K, sc.K) and torch.equal(scc.A, sc.A)
+            sc.K.copy_(scb.K)
+            sc.A.copy_(scb.A)
+            scc.K.copy_(scb.K)
+            scc.A.copy_(scb.A)
+    finally:
+        cuda_lib.bde_tune(b"apply_variant", 0)
+
+
+def test_train_step_full_size(ops):
+    """n = 10 x D = 1e8: the single training-step launch against fused apply + K1 run one after the other."""
+    n, D = 10, 100_000_000
+    g = torch.Generator(device="cuda").manual_seed(5)
+    X = torch.randn(n, D, device="cuda", generator=g)
+    X *= (0.05 * (1 + 0.1 * torch.arange(n, device="cuda", dtype=torch.float32))).unsqueeze(1)
+    G = torch.randn(n, D, device="cuda", generator=g) * 1e-2
+    X2 = X.clone()
+    sc, sc2, scr = (ops.SvgdScratch.allocate(n, "cuda") for _ in range(3))
+    ops.svgd_pairdist_bandwidth(X, sc, 3e-4, 1.0, 50000.0)
+    sc2.K.copy_(sc.K)
+    sc2.A.copy_(sc.A)
+    hyper = dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)
+    buf, buf2 = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.svgd_apply_sgd(X, G, sc, buf, buf_initialized=False, **hyper)
+    ops.svgd_apply_sgd(X2, G, sc2, buf2, buf_initialized=False, next_kernel=ops.NextKernel(True, 3e-4, 1.0, 50000.0), **hyper)
+    assert torch.equal(X2, X) and torch.equal(buf2, buf)
+    del X2, buf2, G
+    ops.svgd_pairdist_bandwidth(X, scr, 3e-4, 1.0, 50000.0)
+    np.testing.assert_allclose(sc2.dist.cpu().numpy(), scr.dist.cpu().numpy(), rtol=1e-8)
+    assert torch.equal(sc2.sel, scr.sel)
+    np.testing.assert_allclose(sc2.K.cpu().numpy(), scr.K.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(sc2.A.cpu().numpy(), scr.A.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    # chunked fp64 distances on the device as the accuracy reference
+    d = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    for c0 in range(0, D, 1 << 22):
+        x = X[:, c0:c0 + (1 << 22)].double()
+        d += (x.unsqueeze(1) - x.unsqueeze(0)).square().sum(dim=2)
+    np.testing.assert_allclose(sc2.dist.cpu().numpy(), d.cpu().numpy(), rtol=2e-6)
+
+
 def test_fused_apply_rejects_bad_arguments(ops):
     from beyond_deep_ensembles_b200 import _lib
     n, D = 4, 64

@@ -108,14 +108,17 @@ def build_svgd(env, g, base_cls=torch.optim.Adam, **base_kw):
     return model, opt
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused-base", "base-step"])
-def test_svgd_steps_match_reference(env, golden, fused):
-    """Three reference steps with a shared Adam base optimizer (10 Adam steps per SVGD step); fused = the
-    base-optimizer steps run inside the apply kernel (f1), otherwise base.step() per particle."""
+@pytest.mark.parametrize("mode", ["train-step", "fused-base", "base-step"])
+def test_svgd_steps_match_reference(env, golden, mode):
+    """Three reference steps with a shared Adam base optimizer (10 Adam steps per SVGD step); fused-base = the
+    base-optimizer steps run inside the apply kernel (f1), train-step = that launch also produces the next
+    step's pair distances (K1 runs once, on the first step only), base-step = base.step() per particle."""
     g = golden("svgd_steps.npz")
     n, D = g["init"].shape
     model, opt = build_svgd(env, g)
+    fused = mode != "base-step"
     opt.fuse_base_optimizer = fused
+    opt.reuse_pair_distances = mode == "train-step"
     base = opt.get_base_optimizer()
     assert len(opt.param_groups) == 4  # one group per tensor (svgd.py:50)
     for s in range(g["losses"].size):
@@ -135,8 +138,10 @@ def test_svgd_steps_match_reference(env, golden, fused):
         np.testing.assert_allclose(flat(model.parameters()), g["sampled"][k], rtol=3e-5, atol=3e-6)
     if env.fake:
         steps = g["losses"].size
-        assert env.calls("pairdist") == steps
-        assert env.calls("apply_adam") == (steps if fused else 0) and env.calls("apply") == (0 if fused else steps)
+        assert env.calls("pairdist") == (1 if mode == "train-step" else steps)
+        assert env.calls("train_step_adam") == (steps if mode == "train-step" else 0)
+        assert env.calls("apply_adam") == (steps if mode == "fused-base" else 0)
+        assert env.calls("apply") == (0 if fused else steps)
 
 
 @pytest.mark.parametrize("fused", [True, False], ids=["fused-base", "base-step"])
@@ -177,8 +182,40 @@ def test_svgd_sgd_nesterov_schedule_and_checkpoint_match_reference(env, golden, 
             np.testing.assert_allclose(parts, g["particles"][s], rtol=3e-5, atol=3e-6)
             bufs = flat(base.state[p]["momentum_buffer"] for p in model.parameters())
             np.testing.assert_allclose(bufs, g["momentum_buffers"][s], rtol=1e-4, atol=1e-6)
+    if env.fake:  # default reuse_pair_distances: the training-step launch; K1 only on the first step
+        assert env.calls("train_step_sgd") == (g["losses"].size if fused else 0)
+        assert env.calls("pairdist") == (1 if fused else g["losses"].size)
+
+
+def test_svgd_kernel_cache_invalidation(env, golden):
+    """The pair distances cached by the training-step launch are dropped by load_state_dict(), by
+    invalidate_kernel_cache(), by a change of l2_reg / dataset_size, and never used by an unfused step."""
+    g = golden("svgd_steps.npz")
+    model, opt = build_svgd(env, g)
+    fwd, bwd = gm.mse_closures(model, env.t(g["xs"][0]), env.t(g["ys"][0]))
+    opt.step(fwd, bwd)
+    assert opt._cached == "kernel"
+    opt.load_state_dict(opt.state_dict())
+    assert opt._cached is None
+    opt.step(fwd, bwd)
+    assert opt._cached == "kernel"
+    opt.invalidate_kernel_cache()
+    assert opt._cached is None
+    opt.step(fwd, bwd)
+    opt.state["__l2_reg"] = 0.5       # hyper-parameters enter K1b: the cached K / A no longer apply
+    before = env.calls("pairdist")
+    opt.step(fwd, bwd)
     if env.fake:
-        assert env.calls("apply_sgd") == (g["losses"].size if fused else 0)
+        assert env.calls("pairdist") == before + 1
+    opt.fuse_base_optimizer = False   # base.step() moves the particles outside the kernels
+    opt.step(fwd, bwd)
+    assert opt._cached is None
+    # two column segments (per-group hyper-parameters): no single-pass form, K1 runs every step
+    plist = list(model.parameters())
+    opt.fuse_base_optimizer = True
+    opt.state["__base_optimizer"] = torch.optim.SGD([{"params": plist[:2], "lr": 0.1}, {"params": plist[2:], "lr": 0.01}], lr=1.0)
+    opt.step(fwd, bwd)
+    assert opt._cached is None
 
 
 def test_svgd_fused_plan_recognition(env, golden):
