@@ -51,6 +51,7 @@ SIGNATURES = {
     "bde_kl_gauss_value_and_grad": [_p, _p, _i64, _d, _d, _p, _p, _p, _d, _p, _i, _p, _sz, _p],
     "bde_kl_mixture_value_and_grad": [_p, _i64, _d, _d, _d, _p, _p, _d, _p, _i, _p, _sz, _p],
     "bde_l2_value_and_grad": [_p, _i64, _d, _p, _p, _d, _p, _i, _p, _sz, _p],
+    "bde_prior_terms_value_and_grad": [_i, _p, _p, _p, _p, _p, _p, _p, _d, _d, _d, _p, _d, _p, _i, _p, _sz, _p],
     "bde_philox_normal": [_p, _i64, _u64, _u64, _i64, _p],
     "bde_multi_tensor_copy": [_p, _p, _p, _p, _i, _i, _p],
 }

@@ -83,18 +83,36 @@ class BBBOptimizer(BayesianOptimizer):
             else:
                 total_data_loss += forward_closure()
 
-        # KL and L2 are collected once per step (bbb.py:69-76)
+        # KL and L2 are collected once per step (bbb.py:69-76).  Every tensor the fused kernels understand
+        # goes into ONE multi-tensor launch per prior (value) + one in backward (all gradients); anything
+        # else — a foreign prior object, a parameter whose KL is a user-supplied callable, non-contiguous
+        # storage — is evaluated per tensor through its own get_parameter_kl.
         total_kl_loss = torch.tensor(0.0, device=self._params_device())
+        batches = {}   # id(prior) -> (prior, [(mean, rho)])
+        deterministic = []
         for group in self.param_groups:
             l2_scale = group["l2_scale"]
+            prior = group["prior"]
             for param in group["params"]:
                 if hasattr(param, "get_parameter_kl"):
-                    total_kl_loss += param.get_parameter_kl(group["prior"])
+                    pair = self._gaussian_pair(param, prior) if self.batch_prior_terms else None
+                    if pair is None:
+                        total_kl_loss += param.get_parameter_kl(prior)
+                    else:
+                        batches.setdefault(id(prior), (prior, []))[1].append(pair)
                 elif not getattr(param, "_is_gaussian_mean", False) and not getattr(param, "_is_gaussian_rho", False):
                     # the reference adds 0 * ||theta||^2 when l2_scale == 0; skipping the pass over
                     # D parameters is identical for finite weights
                     if l2_scale != 0:
-                        total_kl_loss += util.l2_penalty(param, l2_scale)
+                        if self.batch_prior_terms and param.is_contiguous() and param.dtype == torch.float32:
+                            deterministic.append((param, l2_scale))
+                        else:
+                            total_kl_loss += util.l2_penalty(param, l2_scale)
+        for prior, pairs in batches.values():
+            total_kl_loss += util.prior_terms(pairs, prior, deterministic)
+            deterministic = []
+        if deterministic:
+            total_kl_loss += util.prior_terms([], None, deterministic)
 
         pi = self.kl_rescaling / self.dataset_size
         # the KL is not divided by the MC sample count: it was collected once (bbb.py:79-80)
@@ -108,6 +126,25 @@ class BBBOptimizer(BayesianOptimizer):
                 base.step()
 
         return loss
+
+    # one launch for the whole prior term (class attribute; False: one K9 / K10 launch per tensor)
+    batch_prior_terms = True
+
+    @staticmethod
+    def _gaussian_pair(mean_param, prior):
+        """(mean, rho) when `mean_param` belongs to a GaussianParameter whose KL against `prior` is the
+        stock one (util.gaussian_kl), else None."""
+        owner = getattr(mean_param.get_parameter_kl, "__self__", None)
+        rho = getattr(owner, "rho", None)
+        if rho is None or getattr(owner, "mean", None) is not mean_param or util.prior_kind(prior) is None:
+            return None
+        func = getattr(mean_param.get_parameter_kl, "__func__", None)
+        if func is not getattr(type(owner), "kl_divergence", None) or not getattr(type(owner), "_bde_fused_kl", False):
+            return None
+        if not (mean_param.is_contiguous() and rho.is_contiguous() and rho.shape == mean_param.shape
+                and mean_param.dtype == torch.float32 and rho.dtype == torch.float32):
+            return None
+        return mean_param, rho
 
     def sample_parameters(self):
         """The Bayesian layers sample in their forward pass (bbb.py:92-96)."""

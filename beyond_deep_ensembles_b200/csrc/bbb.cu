@@ -314,6 +314,8 @@ prior_terms_kernel(const __grid_constant__ PriorTable tab, float prior_mu, float
 
 using namespace bde;
 
+static MixtureConsts mixture_consts(double pi, double sigma1, double sigma2);
+
 extern "C" int bde_gauss_sample_fwd(const float* mu, const float* rho, float* w, int64_t P, const float* eps,
                                     uint64_t seed, uint64_t stream_id, int64_t elem0, bde_stream_t stream) {
     if (!mu || !rho || !w || P < 0 || elem0 < 0 || (elem0 & 3)) return BDE_ERR_INVALID_ARG;
@@ -400,15 +402,7 @@ extern "C" int bde_kl_mixture_value_and_grad(const float* mu, int64_t P, double 
         if (value) BDE_RETURN_IF_CUDA(cudaMemsetAsync(value, 0, sizeof(double), st));
         return BDE_OK;
     }
-    MixtureConsts c;
-    // torch.log(torch.tensor(pi)) is an fp32 log of the fp32-rounded pi
-    c.log_pi = logf(static_cast<float>(pi));
-    c.log_1mpi = logf(1.0f - static_cast<float>(pi));
-    c.inv_var1 = static_cast<float>(1.0 / (sigma1 * sigma1));
-    c.inv_var2 = static_cast<float>(1.0 / (sigma2 * sigma2));
-    const double half_log_2pi = 0.91893853320467274178;
-    c.lognorm1 = static_cast<float>(-log(sigma1) - half_log_2pi);
-    c.lognorm2 = static_cast<float>(-log(sigma2) - half_log_2pi);
+    const MixtureConsts c = mixture_consts(pi, sigma1, sigma2);
     const bool grad = grad_mu != nullptr;
     const bool vec = aligned16(mu) && (!grad || aligned16(grad_mu));
     BDE_DISPATCH3(kl_mixture_kernel, P, vec, grad, accumulate != 0, mu, P, c, value, grad_mu,
@@ -432,4 +426,77 @@ extern "C" int bde_l2_value_and_grad(const float* theta, int64_t D, double l2_sc
     BDE_DISPATCH3(l2_kernel, D, vec, has_grad, accumulate != 0, theta, D, static_cast<float>(l2_scale), 0.5 * l2_scale, value,
                   grad, static_cast<float>(grad_scale), grad_scale_dev, workspace);
     return rc;
+}
+
+static MixtureConsts mixture_consts(double pi, double sigma1, double sigma2) {
+    MixtureConsts c;
+    // torch.log(torch.tensor(pi)) is an fp32 log of the fp32-rounded pi
+    c.log_pi = logf(static_cast<float>(pi));
+    c.log_1mpi = logf(1.0f - static_cast<float>(pi));
+    c.inv_var1 = static_cast<float>(1.0 / (sigma1 * sigma1));
+    c.inv_var2 = static_cast<float>(1.0 / (sigma2 * sigma2));
+    const double half_log_2pi = 0.91893853320467274178;
+    c.lognorm1 = static_cast<float>(-log(sigma1) - half_log_2pi);
+    c.lognorm2 = static_cast<float>(-log(sigma2) - half_log_2pi);
+    return c;
+}
+
+extern "C" int bde_prior_terms_value_and_grad(int count, const int32_t* kinds_host, const uint64_t* a_host,
+                                              const uint64_t* b_host, const uint64_t* grad_a_host,
+                                              const uint64_t* grad_b_host, const int64_t* sizes_host,
+                                              const double* l2_scales_host, double prior_p0, double prior_p1,
+                                              double prior_p2, double* value, double grad_scale,
+                                              const float* grad_scale_dev, int accumulate_grad, void* workspace,
+                                              size_t workspace_bytes, bde_stream_t stream) {
+    if (count < 0 || (count > 0 && (!kinds_host || !a_host || !sizes_host))) return BDE_ERR_INVALID_ARG;
+    int rc = check_value_ws(value, workspace, workspace_bytes);
+    if (rc != BDE_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool grad = grad_a_host != nullptr;
+    bool any_gauss = false, any_mix = false;
+    for (int i = 0; i < count; ++i) {
+        const int k = kinds_host[i];
+        if (k < kPtGauss || k > kPtL2 || sizes_host[i] < 0 || (sizes_host[i] > 0 && !a_host[i])) return BDE_ERR_INVALID_ARG;
+        if (k == kPtGauss && sizes_host[i] > 0 && (!b_host || !b_host[i])) return BDE_ERR_INVALID_ARG;
+        if (k == kPtGauss && grad && grad_a_host[i] && (!grad_b_host || !grad_b_host[i])) return BDE_ERR_INVALID_ARG;
+        if (k == kPtL2 && !l2_scales_host) return BDE_ERR_INVALID_ARG;
+        any_gauss |= k == kPtGauss;
+        any_mix |= k == kPtMixture;
+    }
+    if (any_gauss && any_mix) return BDE_ERR_INVALID_ARG;  // one prior per call
+    if (any_gauss && !(prior_p1 > 0.0)) return BDE_ERR_INVALID_ARG;
+    if (any_mix && (!(prior_p0 > 0.0 && prior_p0 < 1.0) || !(prior_p1 > 0.0) || !(prior_p2 > 0.0))) return BDE_ERR_INVALID_ARG;
+    if (value) BDE_RETURN_IF_CUDA(cudaMemsetAsync(value, 0, sizeof(double), st));
+    const MixtureConsts mc = any_mix ? mixture_consts(prior_p0, prior_p1, prior_p2) : MixtureConsts{};
+    const float pmu = any_gauss ? static_cast<float>(prior_p0) : 0.0f;
+    const float psig = any_gauss ? static_cast<float>(prior_p1) : 1.0f;
+    for (int c0 = 0; c0 < count; c0 += kPtChunk) {
+        PriorTable tab;
+        tab.count = 0;
+        int64_t q = 0;
+        for (int i = c0; i < count && tab.count < kPtChunk; ++i) {
+            if (sizes_host[i] == 0) continue;
+            const int t = tab.count++;
+            tab.a[t] = a_host[i];
+            tab.b[t] = (kinds_host[i] == kPtGauss) ? b_host[i] : 0;
+            tab.ga[t] = grad ? grad_a_host[i] : 0;
+            tab.gb[t] = (grad && kinds_host[i] == kPtGauss && grad_a_host[i]) ? grad_b_host[i] : 0;
+            tab.size[t] = sizes_host[i];
+            tab.l2[t] = (kinds_host[i] == kPtL2) ? static_cast<float>(l2_scales_host[i]) : 0.0f;
+            tab.kind[t] = static_cast<unsigned char>(kinds_host[i]);
+            tab.qoff[t] = q;
+            q += (sizes_host[i] + 3) >> 2;
+        }
+        if (tab.count == 0) continue;
+        tab.qoff[tab.count] = q;
+        const float hs = static_cast<float>(grad_scale);
+        if (!grad)
+            rc = launch_ew(prior_terms_kernel<false, false>, q << 2, st, tab, pmu, psig, mc, value, 1, hs, grad_scale_dev, workspace);
+        else if (accumulate_grad)
+            rc = launch_ew(prior_terms_kernel<true, true>, q << 2, st, tab, pmu, psig, mc, value, 1, hs, grad_scale_dev, workspace);
+        else
+            rc = launch_ew(prior_terms_kernel<true, false>, q << 2, st, tab, pmu, psig, mc, value, 1, hs, grad_scale_dev, workspace);
+        if (rc != BDE_OK) return rc;
+    }
+    return BDE_OK;
 }

@@ -49,6 +49,7 @@ def install(reference_root: str | None = None) -> list[str]:
         gp = ref_util.GaussianParameter
         gp.sample = lambda self: util.gaussian_sample(self.mean, self.rho)
         gp.kl_divergence = lambda self, prior: util.gaussian_kl(self.mean, self.rho, prior)
+        gp._bde_fused_kl = True
         patched.append("src.algos.util.GaussianParameter.{sample,kl_divergence}")
     except Exception:
         pass

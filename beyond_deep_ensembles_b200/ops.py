@@ -316,6 +316,52 @@ def kl_mixture(mu, pi: float, sigma1: float, sigma2: float, *, value=None, grad_
               _lib.ptr(ws), 0 if ws is None else ws.numel() * 8, _s(mu))
 
 
+PRIOR_GAUSS, PRIOR_MIXTURE, PRIOR_L2 = 0, 1, 2
+
+
+def prior_terms(kinds, a, b, sizes=None, *, l2_scales=None, prior=(0.0, 1.0, 0.0), value=None, grad_a=None, grad_b=None,
+                grad_scale: float = 1.0, grad_scale_dev=None, accumulate: bool = False, ws=None) -> None:
+    """K9 + K10 over a list of tensors in one launch (bbb.py:69-76).
+
+    kinds[i]: PRIOR_GAUSS (a[i] = mu, b[i] = rho), PRIOR_MIXTURE (a[i] = mu) or PRIOR_L2 (a[i] = theta,
+    l2_scales[i]); prior = (mu_p, sigma_p, -) or (pi, sigma1, sigma2); grad_a / grad_b: lists of output
+    tensors (None entries: no gradient for that tensor) or None for the value only."""
+    count = len(kinds)
+    if count == 0:
+        if value is not None:
+            value.zero_()
+        return
+    tensors = [t for t in list(a) + list(b or []) + list(grad_a or []) + list(grad_b or []) if t is not None]
+    require_cuda(*tensors, value, grad_scale_dev)
+    _lib.require_f32(*tensors, grad_scale_dev)
+    for t in tensors:
+        if not t.is_contiguous():
+            raise ValueError("prior_terms needs contiguous tensors")
+    if value is not None:
+        assert value.dtype == torch.float64 and ws is not None
+    u64, i64 = C.c_uint64 * count, C.c_int64 * count
+
+    def table(ts):
+        return u64(*[0 if t is None else t.data_ptr() for t in ts])
+
+    b_list = list(b) if b is not None else [None] * count
+    sizes_arr = i64(*[t.numel() for t in a])
+    for i, k in enumerate(kinds):
+        if k == PRIOR_GAUSS and (b_list[i] is None or b_list[i].numel() != a[i].numel()):
+            raise ValueError("a Gaussian parameter needs a rho tensor of the same size")
+        for g in (grad_a, grad_b):
+            if g is not None and g[i] is not None and g[i].numel() != a[i].numel():
+                raise ValueError("gradient tensor size mismatch")
+    l2 = (C.c_double * count)(*[float(x) for x in (l2_scales if l2_scales is not None else [0.0] * count)])
+    p0, p1, p2 = (float(x) for x in prior)
+    _lib.call("bde_prior_terms_value_and_grad", count, C.cast((C.c_int32 * count)(*[int(k) for k in kinds]), C.c_void_p),
+              C.cast(table(a), C.c_void_p), C.cast(table(b_list), C.c_void_p),
+              None if grad_a is None else C.cast(table(grad_a), C.c_void_p),
+              None if grad_b is None else C.cast(table(grad_b), C.c_void_p),
+              C.cast(sizes_arr, C.c_void_p), C.cast(l2, C.c_void_p), p0, p1, p2, _lib.ptr(value), float(grad_scale),
+              _lib.ptr(grad_scale_dev), int(accumulate), _lib.ptr(ws), 0 if ws is None else ws.numel() * 8, _s(a[0]))
+
+
 def l2_term(theta, l2_scale: float, *, value=None, grad=None, grad_scale: float = 1.0, grad_scale_dev=None,
             accumulate: bool = False, ws=None) -> None:
     """K10 (bbb.py:75-76)."""

@@ -103,6 +103,83 @@ class _L2(torch.autograd.Function):
         return g, None
 
 
+class _PriorTerms(torch.autograd.Function):
+    """The whole prior term of one BBB step — KL of every Gaussian parameter plus the L2 penalty of every
+    deterministic parameter (bbb.py:69-76) — as ONE autograd node: one launch for the value, one for all
+    gradients (written into a single flat buffer the per-tensor gradients are views of)."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        kinds, l2_scales, prior, n_seg = spec
+        a = [t.detach() for t in tensors[:n_seg]]
+        b_iter = iter(t.detach() for t in tensors[n_seg:])
+        b = [next(b_iter) if k == ops.PRIOR_GAUSS else None for k in kinds]
+        dev = a[0].device
+        value = torch.zeros((), dtype=torch.float64, device=dev)
+        ops.prior_terms(kinds, a, b, l2_scales=l2_scales, prior=prior, value=value, ws=ops.value_workspace(dev))
+        ctx.spec, ctx.a, ctx.b = spec, a, b
+        return value.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        kinds, l2_scales, prior, n_seg = ctx.spec
+        a, b = ctx.a, ctx.b
+        # one flat gradient buffer, every tensor's slice starting on a 16-byte boundary
+        offs, total = [], 0
+        for t in a + [t for t in b if t is not None]:
+            offs.append(total)
+            total += (t.numel() + 3) // 4 * 4
+        flat = torch.empty(total, dtype=torch.float32, device=a[0].device)
+        views = [flat[o:o + t.numel()] for o, t in zip(offs, a + [t for t in b if t is not None])]
+        ga = views[:n_seg]
+        gb_iter = iter(views[n_seg:])
+        gb = [next(gb_iter) if t is not None else None for t in b]
+        scale = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        ops.prior_terms(kinds, a, b, l2_scales=l2_scales, prior=prior, grad_a=ga, grad_b=gb, grad_scale_dev=scale)
+        grads = [g.view_as(t) for g, t in zip(ga, a)] + [g.view_as(t) for g, t in zip(gb, b) if t is not None]
+        return (None, *grads)
+
+
+def prior_kind(prior):
+    """("gauss", (mu, sigma, 0)) / ("mixture", (pi, s1, s2)) for the priors of bbb.py, else None."""
+    kind = getattr(prior, "_bde_kind", None)
+    cls = type(prior).__name__
+    if kind == "gauss" or (kind is None and cls == "GaussianPrior"):
+        if all(isinstance(getattr(prior, x, None), (int, float)) for x in ("mu", "sigma")):
+            return "gauss", (float(prior.mu), float(prior.sigma), 0.0)
+    if kind == "mixture" or (kind is None and cls == "MixturePrior"):
+        if hasattr(prior, "pi") and hasattr(prior, "sigma1") and hasattr(prior, "sigma2"):
+            return "mixture", (float(prior.pi), float(prior.sigma1), float(prior.sigma2))
+    return None
+
+
+def prior_terms(gaussians, prior, deterministic) -> torch.Tensor:
+    """sum_i KL(N(mean_i, softplus(rho_i)^2) || prior) + sum_j l2_j/2 ||theta_j||^2 as one autograd node.
+
+    gaussians: list of (mean, rho); deterministic: list of (theta, l2_scale); prior: GaussianPrior /
+    MixturePrior of bbb.py (required when `gaussians` is not empty)."""
+    kinds, a, b, l2 = [], [], [], []
+    ptuple = (0.0, 1.0, 0.0)
+    if gaussians:
+        pk = prior_kind(prior)
+        if pk is None:
+            raise ValueError("prior_terms handles the Gaussian and scale-mixture priors of bbb.py")
+        code = ops.PRIOR_GAUSS if pk[0] == "gauss" else ops.PRIOR_MIXTURE
+        ptuple = pk[1]
+        for mean, rho in gaussians:
+            kinds.append(code)
+            a.append(mean)
+            l2.append(0.0)
+            if code == ops.PRIOR_GAUSS:
+                b.append(rho)
+    for theta, scale in deterministic:
+        kinds.append(ops.PRIOR_L2)
+        a.append(theta)
+        l2.append(float(scale))
+    spec = (tuple(kinds), tuple(l2), ptuple, len(a))
+    return _PriorTerms.apply(spec, *a, *b)
+
+
 def l2_penalty(param: torch.Tensor, l2_scale: float) -> torch.Tensor:
     return _L2.apply(param, float(l2_scale))
 
@@ -134,6 +211,8 @@ class GaussianParameter(nn.Module):
     The mean parameter carries `get_parameter_kl` and `_is_gaussian_mean`, the rho parameter
     `_is_gaussian_rho`, which is how BBBOptimizer tells them apart (bbb.py:73-75).
     """
+
+    _bde_fused_kl = True  # kl_divergence is util.gaussian_kl: BBBOptimizer may batch it with the other tensors
 
     def __init__(self, size, device=None):
         super().__init__()

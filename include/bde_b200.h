@@ -278,6 +278,30 @@ int bde_l2_value_and_grad(const float* theta, int64_t D, double l2_scale, double
                           int accumulate, void* workspace, size_t workspace_bytes,
                           bde_stream_t stream);
 
+/*
+ * K9 + K10 over a LIST of tensors in one launch: the whole prior term of BBBOptimizer.step,
+ * bbb.py:69-76 — sum over the Gaussian parameters of their KL plus sum over the deterministic
+ * parameters of l2_scale/2 * ||theta||^2 — and its gradient.  All *_host arguments are HOST arrays of
+ * `count` entries (the table travels in the kernel parameters, like bde_multi_tensor_copy):
+ *   kinds_host[i]   0 = Gaussian parameter under the Gaussian prior N(prior_p0, prior_p1^2):
+ *                       a = mu, b = rho, gradients to grad_a / grad_b;
+ *                   1 = Gaussian parameter under the scale-mixture prior (pi = prior_p0,
+ *                       sigma1 = prior_p1, sigma2 = prior_p2): a = mu, gradient to grad_a only;
+ *                   2 = deterministic tensor: a = theta, l2_scales_host[i], gradient to grad_a.
+ *   a_host/b_host/grad_a_host/grad_b_host   device pointers as integers (grad_a_host == NULL: value only;
+ *                   a zero entry: no gradient for that tensor); sizes_host: element counts.
+ * Kinds 0 and 1 cannot be mixed in one call (one prior per call).  *value (device double, may be NULL) is
+ * overwritten with the fp64 sum; gradients are multiplied by grad_scale * *grad_scale_dev and written
+ * (accumulate_grad == 0) or added.  Per-element arithmetic is that of the single-tensor entries above.
+ */
+int bde_prior_terms_value_and_grad(int count, const int32_t* kinds_host, const uint64_t* a_host,
+                                   const uint64_t* b_host, const uint64_t* grad_a_host,
+                                   const uint64_t* grad_b_host, const int64_t* sizes_host,
+                                   const double* l2_scales_host, double prior_p0, double prior_p1,
+                                   double prior_p2, double* value, double grad_scale,
+                                   const float* grad_scale_dev, int accumulate_grad, void* workspace,
+                                   size_t workspace_bytes, bde_stream_t stream);
+
 /* ---- utilities ------------------------------------------------------------ */
 
 /* out = standard normals from the library's Philox stream (for tests/diagnostics). */

@@ -248,6 +248,41 @@ class FakeLib:
             self._emit(gmu, P, g, self._scale(gs, gsd), accumulate)
         return 0
 
+    def bde_prior_terms_value_and_grad(self, count, kinds, a, b, ga, gb, sizes, l2s, p0, p1, p2, value, gs, gsd, accumulate,
+                                       ws, wsb, stream):
+        self.calls.append("prior_terms")
+        kinds_ = np.ctypeslib.as_array((C.c_int32 * count).from_address(_addr(kinds)))
+        sizes_ = np.ctypeslib.as_array((C.c_int64 * count).from_address(_addr(sizes)))
+        l2_ = np.ctypeslib.as_array((C.c_double * count).from_address(_addr(l2s)))
+
+        def tab(p):
+            return None if not p else np.ctypeslib.as_array((C.c_uint64 * count).from_address(_addr(p)))
+
+        a_, b_, ga_, gb_ = tab(a), tab(b), tab(ga), tab(gb)
+        s = self._scale(gs, gsd) if ga_ is not None else None
+        total = 0.0
+        for i in range(count):
+            P = int(sizes_[i])
+            if P == 0:
+                continue
+            mu = _f32(int(a_[i]), P)
+            if kinds_[i] == 0:
+                val, g1, g2 = O.kl_gauss(mu, _f32(int(b_[i]), P), p0, p1)
+            elif kinds_[i] == 1:
+                val, g1 = O.kl_mixture(mu, p0, p1, p2)
+                g2 = None
+            else:
+                val, g1 = O.l2_term(mu, float(l2_[i]))
+                g2 = None
+            total += float(val)
+            if ga_ is not None and ga_[i]:
+                self._emit(int(ga_[i]), P, g1, s, accumulate)
+                if g2 is not None:
+                    self._emit(int(gb_[i]), P, g2, s, accumulate)
+        if value:
+            _f64(value, 1)[0] = total
+        return 0
+
     def bde_l2_value_and_grad(self, theta, D, l2, value, grad, gs, gsd, accumulate, ws, wsb, stream):
         self.calls.append("l2")
         val, g = O.l2_term(_f32(theta, D), l2)

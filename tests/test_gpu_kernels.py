@@ -680,6 +680,89 @@ def test_kl_and_l2_values_vs_oracle_sizes(ops, P):
     np.testing.assert_allclose(grad.cpu().numpy(), 1.0 + 3.0 * lg_ref.numpy(), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("prior_kind", ["gauss", "mixture"])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_prior_terms_multi_tensor_vs_oracle(ops, prior_kind, accumulate):
+    """bde_prior_terms_value_and_grad over a list of 130 tensors (three table chunks): Gaussian parameters of
+    ragged sizes, 4-byte-misaligned views, deterministic tensors with their own l2 scales, tensors without a
+    gradient target — value and gradients against the oracle, and bit for bit against the per-tensor kernels."""
+    g = torch.Generator().manual_seed(7)
+    sizes = [1, 3, 4, 5, 768 * 2, 592_130 // 8, 17, 64, 1001] + [int(x) for x in torch.randint(1, 3000, (121,), generator=g)]
+    kinds, a, b, l2, ga, gb = [], [], [], [], [], []
+    code = ops.PRIOR_GAUSS if prior_kind == "gauss" else ops.PRIOR_MIXTURE
+    prior = (0.3, 0.8, 0.0) if prior_kind == "gauss" else (0.4, 1.5, 0.1)
+
+    def dev(t, mis):
+        buf = torch.zeros(t.numel() + 4, device="cuda")
+        v = buf[mis:mis + t.numel()]
+        v.copy_(t)
+        return v
+
+    for i, P in enumerate(sizes):
+        mis = 1 if i % 7 == 3 else 0
+        if i % 3 == 2:
+            kinds.append(ops.PRIOR_L2)
+            a.append(dev(0.05 * torch.randn(P, generator=g), mis))
+            b.append(None)
+            l2.append(0.01 * (1 + i % 4))
+        else:
+            kinds.append(code)
+            a.append(dev(0.3 * torch.randn(P, generator=g), mis))
+            b.append(dev(-3 + 0.5 * torch.randn(P, generator=g), mis) if code == ops.PRIOR_GAUSS else None)
+            l2.append(0.0)
+        want = i % 11 != 5   # some tensors get no gradient
+        init = 0.1 * torch.randn(P, generator=g)
+        ga.append(dev(init, mis) if want else None)
+        gb.append(dev(init * 2, mis) if (want and kinds[-1] == ops.PRIOR_GAUSS) else None)
+    ga0 = [None if t is None else t.clone() for t in ga]
+    gb0 = [None if t is None else t.clone() for t in gb]
+    value = torch.zeros((), dtype=torch.float64, device="cuda")
+    scale_dev = torch.tensor([0.25], device="cuda")
+    ws = ops.value_workspace("cuda")
+    ops.prior_terms(kinds, a, b, l2_scales=l2, prior=prior, value=value, grad_a=ga, grad_b=gb, grad_scale=2.0,
+                    grad_scale_dev=scale_dev, accumulate=accumulate, ws=ws)
+    total = 0.0
+    v1 = torch.zeros((), dtype=torch.float64, device="cuda")
+    for i, P in enumerate(sizes):
+        x = a[i].cpu()
+        if kinds[i] == ops.PRIOR_GAUSS:
+            val, g1, g2 = O.kl_gauss(x, b[i].cpu(), prior[0], prior[1])
+        elif kinds[i] == ops.PRIOR_MIXTURE:
+            val, g1 = O.kl_mixture(x, *prior)
+            g2 = None
+        else:
+            val, g1 = O.l2_term(x, l2[i])
+            g2 = None
+        total += float(val)
+        if ga[i] is None:
+            continue
+        base1 = ga0[i].cpu() if accumulate else 0.0
+        np.testing.assert_allclose(ga[i].cpu().numpy(), (base1 + 0.5 * g1).numpy(), rtol=RTOL, atol=ATOL, err_msg=f"tensor {i}")
+        if g2 is not None:
+            base2 = gb0[i].cpu() if accumulate else 0.0
+            np.testing.assert_allclose(gb[i].cpu().numpy(), (base2 + 0.5 * g2).numpy(), rtol=RTOL, atol=30 * ATOL, err_msg=f"tensor {i}")
+        # the per-tensor kernels do the same arithmetic
+        r1 = ga0[i].clone()
+        if kinds[i] == ops.PRIOR_GAUSS:
+            r2 = gb0[i].clone()
+            ops.kl_gauss(a[i], b[i], prior[0], prior[1], value=v1, grad_mu=r1, grad_rho=r2, grad_scale=2.0,
+                         grad_scale_dev=scale_dev, accumulate=accumulate, ws=ws)
+            assert torch.equal(r2, gb[i])
+        elif kinds[i] == ops.PRIOR_MIXTURE:
+            ops.kl_mixture(a[i], *prior, value=v1, grad_mu=r1, grad_scale=2.0, grad_scale_dev=scale_dev,
+                           accumulate=accumulate, ws=ws)
+        else:
+            ops.l2_term(a[i], l2[i], value=v1, grad=r1, grad_scale=2.0, grad_scale_dev=scale_dev, accumulate=accumulate, ws=ws)
+        assert torch.equal(r1, ga[i]), f"tensor {i}"
+    np.testing.assert_allclose(value.item(), total, rtol=1e-6)
+    # value only, and an empty list
+    v2 = torch.ones((), dtype=torch.float64, device="cuda")
+    ops.prior_terms(kinds, a, b, l2_scales=l2, prior=prior, value=v2, ws=ws)
+    assert v2.item() == value.item()   # deterministic reduction
+    ops.prior_terms([], [], [], value=v2, ws=ws)
+    assert v2.item() == 0.0
+
+
 def test_gauss_sample_philox_fwd_bwd_consistent(ops):
     P = 100_001
     mu, rho = torch.zeros(P, device="cuda"), torch.full((P,), 0.5413, device="cuda")  # softplus = 1.0000

@@ -481,7 +481,11 @@ def test_ivon_philox_sampling_statistics(env):
 
 
 # ---------------------------------------------------------------- BBB / Rank-1
-def test_bbb_rank1_matches_reference(env, golden):
+@pytest.mark.parametrize("batched", [True, False], ids=["one-launch", "per-tensor"])
+def test_bbb_rank1_matches_reference(env, golden, batched):
+    """Three reference Rank-1 steps (Gaussian prior, l2_scale on the deterministic weights).  one-launch: the
+    whole prior term (4 Gaussian tensors + 4 deterministic tensors) is ONE multi-tensor launch for the value
+    and one for the gradients; per-tensor: a K9 / K10 launch pair per tensor."""
     g = golden("bbb_steps.npz")
     model = gm.Rank1MLP(bde.GaussianParameter).to(env.dev)
     init = {k[len("init/"):]: g[k] for k in g.files if k.startswith("init/")}
@@ -490,6 +494,7 @@ def test_bbb_rank1_matches_reference(env, golden):
     base = torch.optim.Adam(model.parameters(), lr=1e-2)
     opt = bde.BBBOptimizer(model.parameters(), base, prior, dataset_size=100, mc_samples=2, kl_rescaling=0.5,
                            components=1, l2_scale=0.01)
+    opt.batch_prior_terms = batched
     with noise.inject(tape(g["eps"], g["eps_sizes"])):
         for s in range(g["losses"].size):
             fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
@@ -499,7 +504,10 @@ def test_bbb_rank1_matches_reference(env, golden):
                 np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"step{s}/{name}"], rtol=1e-4, atol=1e-5,
                                            err_msg=f"{name} after step {s}")
     if env.fake:
-        assert env.calls("kl_gauss") == 2 * 4 * g["losses"].size  # value + grad, 4 Gaussian tensors
+        steps = g["losses"].size
+        assert env.calls("prior_terms") == (2 * steps if batched else 0)       # value + all gradients
+        assert env.calls("kl_gauss") == (0 if batched else 2 * 4 * steps)     # value + grad, 4 Gaussian tensors
+        assert env.calls("l2") == (0 if batched else 2 * 4 * steps)
     assert opt.sample_parameters() is None
 
 
