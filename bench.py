@@ -155,7 +155,8 @@ def workload_config(n_gpus):
         "l2_reg": L2_REG, "dataset_size": DATASET_SIZE, "kernel_grad_scale": KERNEL_GRAD_SCALE,
         "algorithmic_bytes_per_step_per_gpu": 16 * N_PARTICLES * D_PER_GPU,
         "l2_flush": "inputs (12 GB per GPU) are larger than the 126 MB L2",
-        "parallelism": f"D-shard x{n_gpus}; all-reduce of the 10x10 fp64 partial distances only",
+        "parallelism": f"D-shard x{n_gpus}; only the 10x10 fp64 partial distances cross NVLink (summed inside K1's tail "
+                       "over peer memory, or by one NCCL all-reduce)",
     }
 
 
@@ -361,6 +362,11 @@ def main():
         run_reference_arm(args)
         return
 
+    # stdout carries exactly ONE JSON line: everything else that might print there (NCCL's version banner,
+    # library chatter) is sent to stderr by re-pointing fd 1; the line itself goes to the saved descriptor
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     D_PER_GPU = args.d_per_gpu
     import torch.distributed as dist
     from beyond_deep_ensembles_b200 import _lib, ops
@@ -392,11 +398,16 @@ def main():
     out = torch.empty_like(X)
     sc = ops.SvgdScratch.allocate(n, dev)
 
+    # N > 1: the n*n partial distances are summed across ranks inside K1's tail over peer memory (CUDA IPC +
+    # NVLink) when the ranks can map each other; otherwise K1 -> NCCL all-reduce -> K1b
+    peer = world > 1 and bdist.enable_peer_exchange(sc)
+    in_kernel = [world == 1 or peer]
+
     def step(events=None):
         """One posterior update; `events` collects (K1 start, K1 end / K2 start, K2 end)."""
         if events is not None:
             events[0].record()
-        if world == 1:
+        if in_kernel[0]:
             ops.svgd_pairdist_bandwidth(X, sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
         else:
             ops.svgd_pairdist(X, sc)
@@ -439,6 +450,36 @@ def main():
     ms_per_step = total_ms / steps
     value = 16.0 * n * D * world / (ms_per_step * 1e-3) / 1e9
 
+    # N > 1 with the peer exchange: also time the portable form (K1 -> NCCL all-reduce -> K1b -> K2) for comparison
+    exchange = None
+    if world > 1:
+        exchange = {"form": "in-kernel peer exchange (P2P stores + epoch flags in K1's tail)" if peer else
+                    "NCCL all-reduce of n*n fp64 between K1 and K1b", "launches_per_step": 2 if peer else 4}
+        if peer:
+            sc_nccl = ops.SvgdScratch.allocate(n, dev)
+            sc_peer, sc = sc, sc_nccl
+            in_kernel[0] = False
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(steps):
+                step()
+            a1.record()
+            torch.cuda.synchronize()
+            tn = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(tn, op=dist.ReduceOp.MAX)
+            exchange["nccl_form_ms_per_step"] = tn.item() / steps
+            exchange["peer_form_ms_per_step"] = ms_per_step
+            same = torch.equal(sc_nccl.sel, sc_peer.sel) and torch.allclose(sc_nccl.dist, sc_peer.dist, rtol=1e-12, atol=0)
+            exchange["peer_equals_nccl"] = bool(same)
+            exchange["peer_status_epochs_timeouts"] = list(sc_peer.peers.status())
+            sc = sc_peer
+            in_kernel[0] = True
+
     # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
     e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
     paths, cpu_base = None, None
@@ -459,9 +500,10 @@ def main():
             torch.cuda.empty_cache()
             st = ops.HostStaging.allocate(n, D, 4_000_000, dev, dX=X if D % 4 == 0 else None)
             e2e_steps = min(steps, 5)
+            sc_host = ops.SvgdScratch.allocate(n, dev) if sc.peers is not None else sc   # host path: all-reduce form
 
             def e2e_step():
-                ops.svgd_step_host(Xh, Gh, Oh, st, sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+                ops.svgd_step_host(Xh, Gh, Oh, st, sc_host, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
 
             e2e_step()  # warm-up (page-locks, stream creation)
             torch.cuda.synchronize()
@@ -519,21 +561,22 @@ def main():
                 "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
                                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,
                                                "algorithmic_bytes": k1_bytes,
-                                               "includes": "n*n all-reduce + K1b" if world > 1 else "fused K1b tail"},
+                                               "includes": ("in-kernel peer exchange + fused K1b tail" if peer else
+                                                            "n*n all-reduce + K1b") if world > 1 else "fused K1b tail"},
                 "svgd_apply": {"ms": k2_ms, "GBps": k2_gbs, "frac": k2_gbs / peak_gbs, "algorithmic_bytes": k2_bytes},
             },
             "step_frac_of_measured_peak": value / world / peak_gbs,
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
-            "cpu_baseline": cpu_base, "paths": paths,
+            "cpu_baseline": cpu_base, "paths": paths, "exchange": exchange,
         }
-        sys.stdout.write(json.dumps(line) + "\n")
-        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
         try:
-            os.fsync(sys.stdout.fileno())
+            os.fsync(json_fd)
         except OSError:
             pass
     if world > 1:
         dist.barrier()
+        bdist.shutdown_peer_exchange()
         dist.destroy_process_group()
 
 

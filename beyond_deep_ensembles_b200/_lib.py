@@ -26,6 +26,15 @@ SIGNATURES = {
     "bde_device_sm_count": [_p],
     "bde_tune": [C.c_char_p, _i],
     "bde_svgd_workspace_bytes": [_i, C.POINTER(_sz)],
+    "bde_value_workspace_bytes": [C.POINTER(_sz)],
+    "bde_peer_buffer_bytes": [C.POINTER(_sz)],
+    "bde_peer_alloc": [C.POINTER(_p), C.c_char_p],
+    "bde_peer_open": [C.c_char_p, C.POINTER(_p)],
+    "bde_peer_close": [_p],
+    "bde_peer_free": [_p],
+    "bde_peer_attach": [_p, _sz, _i, _i, C.POINTER(_u64), _p],
+    "bde_peer_detach": [_p, _sz, _p],
+    "bde_peer_status": [_p, C.POINTER(_u64), C.POINTER(_u64)],
     "bde_svgd_pairdist": [_p, _i, _i64, _i64, _p, _i, _p, _sz, _p],
     "bde_svgd_bandwidth": [_p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _p],
     "bde_svgd_apply": [_p, _p, _p, _p, _p, _i, _i64, _i64, _p],

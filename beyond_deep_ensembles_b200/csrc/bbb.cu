@@ -345,6 +345,12 @@ extern "C" int bde_gauss_sample_bwd(const float* grad_w, const float* rho, float
     return rc_;
 }
 
+extern "C" int bde_value_workspace_bytes(size_t* bytes) {
+    if (!bytes) return BDE_ERR_INVALID_ARG;
+    *bytes = grid_reduce_ws_bytes(kMaxCtasEw, 1);
+    return BDE_OK;
+}
+
 static int check_value_ws(double* value, void* ws, size_t ws_bytes) {
     if (value && (!ws || ws_bytes < grid_reduce_ws_bytes(kMaxCtasEw, 1))) return BDE_ERR_WORKSPACE;
     return BDE_OK;

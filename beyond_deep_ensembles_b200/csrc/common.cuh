@@ -176,18 +176,119 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// ----------------------------------------------------------------------------
+// Peer exchange over NVLink (D-sharded jobs).  A reduction workspace that has been
+// attached to a peer set (bde_peer_attach) makes the LAST CTA of a grid reduction finish the sum
+// across the R ranks inside the same launch: it stores its `count` fp64 totals into slot [rank] of
+// every peer's exchange buffer (plain P2P stores through NVLink / NVSwitch), publishes a per-rank
+// epoch flag with release.sys semantics, waits for the R flags in its own buffer and adds the R
+// slots in rank order — so every rank obtains the bit-identical global sums without a separate
+// all-reduce launch.  Buffers are double-buffered by epoch parity: a rank can only reach epoch e+2
+// after every peer has published e+1, i.e. after it finished reading e.
+// ----------------------------------------------------------------------------
+constexpr int kPeerMaxRanks = 16;
+constexpr int kPeerMaxVals = 512;   // >= pair_count(BDE_MAX_PARTICLES) = 496
+struct PeerBuf {                    // one per rank, cudaMalloc'ed (IPC-shareable), zero-filled
+    unsigned long long epoch;       // exchanges completed on this rank (device-side counter)
+    unsigned long long timeouts;    // exchanges abandoned after kPeerTimeoutNs (results poisoned with NaN)
+    unsigned long long pad[14];
+    unsigned long long flags[2][kPeerMaxRanks][4];   // [parity][writer rank], one 32-byte sector each
+    double slots[2][kPeerMaxRanks][kPeerMaxVals];    // [parity][writer rank][value]
+};
+struct WsHeader {                   // first kWsHeaderBytes of every reduction workspace
+    unsigned int ticket;            // CTA arrival counter (left at zero by every launch)
+    int peer_world;                 // 0 / 1: workspace not attached, plain single-GPU reduction
+    int peer_rank;
+    int pad;
+    PeerBuf* peer[kPeerMaxRanks];   // peer[r] = rank r's exchange buffer mapped into this process
+};
+constexpr size_t kWsHeaderBytes = 256;
+static_assert(sizeof(WsHeader) <= kWsHeaderBytes, "workspace header");
+constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Called by every thread of the last CTA with the local sums in total[0..count): on return total holds
+// the sums over all ranks (same bits on every rank).  No-op for an unattached workspace.
+__device__ __forceinline__ void peer_allreduce_fp64(const WsHeader* h, double* total, int count) {
+    const int world = h->peer_world;
+    if (world <= 1) return;
+    const int rank = h->peer_rank;
+    const int tid = threadIdx.x + threadIdx.y * blockDim.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    PeerBuf* me = h->peer[rank];
+    __shared__ unsigned long long s_epoch;
+    __shared__ int s_timed_out;
+    if (tid == 0) {
+        s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
+        s_timed_out = 0;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
+    const int b = static_cast<int>(epoch & 1ull);
+    for (int idx = tid; idx < world * count; idx += nthreads) {
+        const int r = idx / count, k = idx - r * count;
+        st_relaxed_sys_f64(&h->peer[r]->slots[b][rank][k], total[k]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < world) {
+        st_release_sys_u64(&h->peer[tid]->flags[b][rank][0], epoch);
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys_u64(&me->flags[b][tid][0]) < epoch) {
+            if (globaltimer_ns() - t0 > kPeerTimeoutNs) {  // a peer never arrived: poison instead of hanging the GPU
+                s_timed_out = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const bool bad = s_timed_out != 0;
+    for (int k = tid; k < count; k += nthreads) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(&me->slots[b][r][k]);
+        total[k] = bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
+    }
+    if (tid == 0) {
+        *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = epoch;
+        if (bad) *reinterpret_cast<volatile unsigned long long*>(&me->timeouts) = me->timeouts + 1ull;
+    }
+    __syncthreads();
+}
+
 // Deterministic grid-wide fp64 sum of `count` values per CTA.
 //   cta_vals: this CTA's values in shared memory (count doubles), valid after __syncthreads.
-//   ws layout: [0] ticket (unsigned, padded to 16 B), then gridDim.x*count doubles.
+//   ws layout: WsHeader (ticket + optional peer table, kWsHeaderBytes), then gridDim.x*count doubles.
 // Returns true in every thread of the LAST CTA to arrive, after which total[k] = sum over all
-// CTAs is available in `total` (shared, count doubles).  The order of the additions depends only
+// CTAs (and, for a workspace attached to a peer set, over all ranks) is available in `total`
+// (shared, count doubles).  The order of the additions depends only
 // on (gridDim, count): every warp of the last CTA owns groups of 4 consecutive values k (one 32-byte
 // sector per CTA), its lanes walk the CTA list with stride 32 keeping 4 x 8 independent loads in
 // flight, and the 32 lane sums are combined by the fixed xor-shuffle tree.  The ticket is reset so
 // the workspace can be reused by the next launch.
 __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int count, void* ws, double* total) {
     unsigned int* ticket = reinterpret_cast<unsigned int*>(ws);
-    double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + 16);
+    double* parts = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + kWsHeaderBytes);
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     __shared__ bool is_last;
@@ -230,10 +331,11 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     }
     if (tid == 0) *ticket = 0u;
     __syncthreads();
+    if (count <= kPeerMaxVals) peer_allreduce_fp64(reinterpret_cast<const WsHeader*>(ws), total, count);
     return true;
 }
 
-inline size_t grid_reduce_ws_bytes(int max_ctas, int count) { return 16 + sizeof(double) * (size_t)max_ctas * count; }
+inline size_t grid_reduce_ws_bytes(int max_ctas, int count) { return kWsHeaderBytes + sizeof(double) * (size_t)max_ctas * count; }
 
 // ----------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011) + Box-Muller.  counter = (q_lo, q_hi, sid_lo, sid_hi)

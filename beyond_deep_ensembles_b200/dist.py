@@ -1,15 +1,26 @@
 """D-sharded execution: every rank holds a column slice of every particle.
 
-Only the n*n partial squared-distance matrix crosses NVLink (one sum all-reduce of n*n
-doubles per SVGD step); every other kernel on the path is local to its slice
-(SURVEY.md §8e).  Rank r of R owns the columns layout.shard_bounds(D, R, r).
+Only the n*n partial squared-distance matrix crosses NVLink; every other kernel on the path is
+local to its slice.  Rank r of R owns the columns layout.shard_bounds(D, R, r).
+
+Two forms of the exchange:
+  * portable: one NCCL (or gloo) sum all-reduce of n*n doubles between K1 and K1b (3 launches + the
+    collective per step);
+  * peer exchange (`PeerSet`, one node, CUDA IPC): the ranks map each other's small exchange
+    buffers once; afterwards the last CTA of K1 — or of the fused training-step kernel — writes its
+    partial sums straight into the peers' memory over NVLink, waits for theirs and runs K1b in the
+    same launch.  A D-sharded step is then launched exactly like a single-GPU step.
 """
 from __future__ import annotations
+
+import ctypes as C
+import os
+import weakref
 
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 
 
 def world(group=None) -> int:
@@ -22,12 +33,127 @@ def allreduce_dist(sc: "ops.SvgdScratch", group=None) -> None:
         dist.all_reduce(sc.dist, op=dist.ReduceOp.SUM, group=group)
 
 
+# --------------------------------------------------------------------------------------
+# in-kernel exchange over peer memory
+# --------------------------------------------------------------------------------------
+class PeerSet:
+    """The exchange buffers of all ranks of `group`, mapped into this process (include/bde_b200.h,
+    "D-sharded jobs").  Collective: every rank of the group must construct it at the same point."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = world(group)
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self._own = None
+        self._mapped = []
+        self._attached = []
+        lib = _lib.get()
+        own, handle = C.c_void_p(), C.create_string_buffer(64)
+        _lib.check(lib.bde_peer_alloc(C.byref(own), handle), "bde_peer_alloc")
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        bufs, ok = [0] * self.world, 1
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                bufs[r] = self._own
+                continue
+            mapped = C.c_void_p()
+            if lib.bde_peer_open(h, C.byref(mapped)) != 0 or not mapped.value:
+                ok = 0
+                break
+            self._mapped.append(mapped.value)
+            bufs[r] = mapped.value
+        # all ranks must agree before anyone starts waiting on a peer inside a kernel
+        flag = torch.tensor([ok], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            self.close(barrier=False)
+            raise _lib.BdeError("CUDA IPC mapping of a peer's exchange buffer failed on at least one rank")
+        self._bufs = (C.c_uint64 * self.world)(*bufs)
+
+    def attach(self, sc: "ops.SvgdScratch") -> None:
+        """From now on the grid reductions that use sc.ws produce sums over all ranks of the group."""
+        _lib.check(_lib.get().bde_peer_attach(sc.ws.data_ptr(), sc.ws_bytes, self.world, self.rank, self._bufs,
+                                              _lib.stream_ptr(sc.ws.device)), "bde_peer_attach")
+        sc.peers = self
+        self._attached.append(weakref.ref(sc))
+
+    def status(self):
+        """(exchanges completed, exchanges abandoned on a timeout) of this rank — synchronises."""
+        e, t = C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.get().bde_peer_status(self._own, C.byref(e), C.byref(t)), "bde_peer_status")
+        return e.value, t.value
+
+    def close(self, barrier: bool = True) -> None:
+        """Detach the workspaces, unmap the peers and free this rank's buffer.  Collective when barrier=True:
+        no rank may free its buffer while a peer's kernel can still write into it."""
+        if self._own is None:
+            return
+        lib = _lib.get()
+        for ref in self._attached:
+            sc = ref()
+            if sc is not None and getattr(sc, "peers", None) is self:
+                lib.bde_peer_detach(sc.ws.data_ptr(), sc.ws_bytes, _lib.stream_ptr(sc.ws.device))
+                sc.peers = None
+        self._attached = []
+        torch.cuda.synchronize()
+        if barrier and self.world > 1:
+            dist.barrier(group=self.group)
+        for m in self._mapped:
+            lib.bde_peer_close(m)
+        self._mapped = []
+        lib.bde_peer_free(self._own)
+        self._own = None
+
+
+_PEER_SETS: dict = {}
+
+
+def enable_peer_exchange(sc: "ops.SvgdScratch", group=None) -> bool:
+    """Attach `sc` to the group's peer set (created on first use).  Collective over the group.  Returns
+    False — leaving the NCCL all-reduce form in place — for a single rank, CPU tensors, when
+    BDE_PEER_EXCHANGE=0, or when the ranks cannot map each other's memory (not one node / no P2P)."""
+    if world(group) <= 1 or not sc.ws.is_cuda or os.environ.get("BDE_PEER_EXCHANGE", "1") == "0":
+        return False
+    if getattr(sc, "peers", None) is not None:
+        return True
+    key = id(group) if group is not None else None
+    ps = _PEER_SETS.get(key)
+    if ps is None:
+        try:
+            ps = PeerSet(group)
+        except _lib.BdeError:
+            ps = False
+        _PEER_SETS[key] = ps
+    if ps is False:
+        return False
+    ps.attach(sc)
+    return True
+
+
+def shutdown_peer_exchange() -> None:
+    """Collective teardown of every peer set of this process (call before destroy_process_group)."""
+    for key, ps in list(_PEER_SETS.items()):
+        if ps:
+            ps.close()
+        del _PEER_SETS[key]
+
+
+def exchanges_in_kernel(sc: "ops.SvgdScratch", group=None) -> bool:
+    """True when a launch on `sc` already yields cross-rank sums (single rank, or peer set attached)."""
+    return world(group) == 1 or getattr(sc, "peers", None) is not None
+
+
+# --------------------------------------------------------------------------------------
+# the sharded step
+# --------------------------------------------------------------------------------------
 def svgd_kernel_sharded(X: torch.Tensor, sc: "ops.SvgdScratch", l2_reg: float, kernel_grad_scale: float,
                         dataset_size: float, h_override: float = 0.0, group=None, have_partial: bool = False) -> None:
-    """K1 (local partial distances) -> all-reduce of n*n fp64 -> K1b (identical on every rank): leaves
-    K and A in `sc`.  With a single rank K1b runs in K1's tail (one launch).  have_partial: sc.dist
+    """K1 (local partial distances) -> sum over ranks -> K1b (identical on every rank): leaves K and A in `sc`.
+    With a single rank, or with a peer set attached to `sc`, all of it is ONE launch.  have_partial: sc.dist
     already holds this rank's partial sums for the current X (left by the previous training-step launch)."""
-    if world(group) == 1:
+    if exchanges_in_kernel(sc, group):
         if have_partial:
             ops.svgd_bandwidth(sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
         else:
@@ -43,12 +169,8 @@ def svgd_step_sharded(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: "
                       kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0, group=None) -> torch.Tensor:
     """One SVGD posterior update on this rank's [n, D/R] slices.
 
-    K1 (local partial distances) -> all-reduce of n*n fp64 -> K1b (identical on every rank)
-    -> K2 (local).  With a single rank this is the fused two-launch path.
+    K1 (local partial distances) -> sum over ranks -> K1b (identical on every rank) -> K2 (local).
+    Single rank or peer set attached: the fused two-launch path; otherwise K1, all-reduce, K1b, K2.
     """
-    if world(group) == 1:
-        return ops.svgd_step(X, G, out, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
-    ops.svgd_pairdist(X, sc)
-    allreduce_dist(sc, group)
-    ops.svgd_bandwidth(sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+    svgd_kernel_sharded(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override, group)
     return ops.svgd_apply(X, G, out, sc)

@@ -12,7 +12,6 @@ import torch
 
 from . import _lib
 
-_VALUE_WS_BYTES = 16 + 8 * 148 * 8 * 2  # grid_reduce workspace of the value kernels (elementwise.cuh)
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
@@ -58,6 +57,7 @@ class SvgdScratch:
     info: torch.Tensor   # [4] fp64: h, median, d_lo, d_hi
     sel: torch.Tensor    # [2] int32
     ws: torch.Tensor     # reduction workspace (zero-filled once)
+    peers: object = None  # dist.PeerSet once attached: launches on this scratch then sum over all ranks in-kernel
 
     @staticmethod
     def allocate(n: int, device) -> "SvgdScratch":
@@ -285,7 +285,9 @@ def gauss_sample_bwd(grad_w, rho, grad_rho, *, eps=None, seed: int = 0, stream_i
 
 
 def value_workspace(device) -> torch.Tensor:
-    return zeros_bytes(_VALUE_WS_BYTES, device)
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.get().bde_value_workspace_bytes(C.byref(nbytes)), "bde_value_workspace_bytes")
+    return zeros_bytes(nbytes.value, device)
 
 
 def kl_gauss(mu, rho, prior_mu: float, prior_sigma: float, *, value=None, grad_mu=None, grad_rho=None,
@@ -459,6 +461,10 @@ def svgd_step_host(X_host, G_host, out_host, st: HostStaging, sc: SvgdScratch, l
                    dataset_size: float, h_override: float = 0.0, group=None) -> None:
     """End-to-end SVGD posterior update on HOST buffers (this rank's column slice when D-sharded)."""
     from . import dist as bdist
+    if sc.peers is not None:
+        # the chunked host path launches K1 once per chunk on the library's own streams; ranks whose slices differ
+        # by a column could disagree on the chunk count, so it keeps the all-reduce form
+        raise ValueError("svgd_step_host needs a scratch that is not attached to a peer set")
     svgd_host_pairdist(X_host, st, sc)
     bdist.allreduce_dist(sc, group)
     if bdist.world(group) > 1:

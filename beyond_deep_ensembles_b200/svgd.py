@@ -81,6 +81,8 @@ class SVGDOptimizer(BayesianOptimizer):
         self._fused_plan = None
         self._scratch = ops.SvgdScratch.allocate(n, device)
         self._group = process_group
+        # D-sharded on one node: exchange the n*n partial distances inside the kernels (collective over the group)
+        bdist.enable_peer_exchange(self._scratch, process_group)
         # what self._scratch holds for the CURRENT particles: None, "partial" (this rank's pair-distance sums,
         # not yet all-reduced) or "kernel" (K, A, info, sel ready)
         self._cached = None
@@ -130,10 +132,11 @@ class SVGDOptimizer(BayesianOptimizer):
             if bound is not None:
                 # f1: K2 + the n shared-state base-optimizer steps of svgd.py:92-103 in one pass; X in place.
                 # Training-step form (n <= 10): the pass also leaves the next step's pair distances in the
-                # scratch; a single rank finishes K1b in the same launch, D-sharded ranks all-reduce next step.
+                # scratch; a single rank (or a peer set over NVLink) finishes K1b in the same launch, otherwise the
+                # D-sharded ranks all-reduce at the next step.
                 nk = None
                 if self.reuse_pair_distances and 2 <= n <= ops.NEXT_KERNEL_MAX_PARTICLES:
-                    nk = ops.NextKernel(bdist.world(self._group) == 1, *hyper)
+                    nk = ops.NextKernel(bdist.exchanges_in_kernel(self._scratch, self._group), *hyper)
                 if plan.launch(self._X, self._G, self._scratch, self._out_last[0], *bound, next_kernel=nk):
                     self._cached = "kernel" if nk.fuse_bandwidth else "partial"
                     self._cached_hyper = hyper

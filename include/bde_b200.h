@@ -58,6 +58,8 @@ int bde_device_sm_count(int* sm_count);
 
 /* Workspace for bde_svgd_pairdist / bde_kl_* reductions (bytes). */
 int bde_svgd_workspace_bytes(int n, size_t* bytes);
+/* Workspace of the scalar value reductions (bde_kl_*, bde_l2_*, bde_prior_terms_*). */
+int bde_value_workspace_bytes(size_t* bytes);
 
 /*
  * K1: partial squared pairwise distances of the n particle rows over the local D
@@ -301,6 +303,42 @@ int bde_prior_terms_value_and_grad(int count, const int32_t* kinds_host, const u
                                    double prior_p2, double* value, double grad_scale,
                                    const float* grad_scale_dev, int accumulate_grad, void* workspace,
                                    size_t workspace_bytes, bde_stream_t stream);
+
+/* ---- D-sharded jobs: in-kernel exchange over NVLink --------- */
+
+/*
+ * Every GPU holds a column slice [n, D/R] of the particles; the only cross-rank quantity of an
+ * SVGD step is the sum of the n*n partial pair distances (svgd.py:15 over all D columns).  With a
+ * peer set attached to the reduction workspace, the last CTA of bde_svgd_pairdist /
+ * bde_svgd_pairdist_bandwidth / bde_svgd_step / bde_svgd_train_step_* finishes that sum ACROSS
+ * RANKS inside the same launch: P2P stores of its partial sums into every peer's exchange buffer,
+ * a release/acquire epoch flag per rank, and a rank-ordered fp64 sum — the result is bit-identical
+ * on every rank, and a D-sharded step needs no separate all-reduce launch (the NCCL all-reduce of
+ * `dist` remains the portable form).  Every rank must issue the same sequence of launches on the
+ * attached workspaces of one peer set, from one stream.  A peer that never arrives poisons the
+ * sums with NaN after 20 s instead of hanging the GPU (bde_peer_status reports it).
+ *
+ * Protocol (the library keeps no state; the caller owns everything):
+ *   1. each rank: bde_peer_alloc -> device buffer + a BDE_PEER_HANDLE_BYTES CUDA-IPC handle;
+ *   2. exchange the handles between the ranks (any host transport, e.g. torch.distributed);
+ *   3. each rank: bde_peer_open on every OTHER rank's handle -> mapped device pointers;
+ *   4. bde_peer_attach(workspace, ..., world, rank, bufs_host) with bufs_host[r] = rank r's buffer
+ *      as seen from this process (own buffer for r == rank);
+ *   5. teardown after a barrier: bde_peer_detach, bde_peer_close (mapped), bde_peer_free (own).
+ * bde_peer_alloc / open / close / free / status are setup calls: they allocate and synchronise.
+ */
+#define BDE_PEER_HANDLE_BYTES 64
+#define BDE_PEER_MAX_RANKS 16
+int bde_peer_buffer_bytes(size_t* bytes);
+int bde_peer_alloc(void** buf, unsigned char* ipc_handle_host);
+int bde_peer_open(const unsigned char* ipc_handle_host, void** mapped);
+int bde_peer_close(void* mapped);
+int bde_peer_free(void* buf);
+int bde_peer_attach(void* workspace, size_t workspace_bytes, int world, int rank, const uint64_t* bufs_host,
+                    bde_stream_t stream);
+int bde_peer_detach(void* workspace, size_t workspace_bytes, bde_stream_t stream);
+/* exchanges completed / abandoned on this rank's buffer (synchronous device read) */
+int bde_peer_status(const void* buf, uint64_t* epoch_host, uint64_t* timeouts_host);
 
 /* ---- utilities ------------------------------------------------------------ */
 

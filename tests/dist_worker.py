@@ -19,7 +19,7 @@ class _Patch:
         setattr(obj, name, value)
 
 
-def run(rank: int, world: int, port: int, n: int, D: int, out_path: str, backend: str = "gloo"):
+def run(rank: int, world: int, port: int, n: int, D: int, out_path: str, backend: str = "gloo", peer: bool = False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if backend == "nccl":
         torch.cuda.set_device(rank)
@@ -43,8 +43,35 @@ def run(rank: int, world: int, port: int, n: int, D: int, out_path: str, backend
     Xl, Gl = X[:, lo:hi].contiguous().to(dev), G[:, lo:hi].contiguous().to(dev)
     out = torch.empty_like(Xl)
     sc = ops.SvgdScratch.allocate(n, dev)
-    bdist.svgd_step_sharded(Xl, Gl, out, sc, 0.01, 1.0, 50000.0)
+    extra = {}
+    if peer:
+        # in-kernel exchange over peer memory: the sharded step must be the single-GPU launch sequence
+        assert bdist.enable_peer_exchange(sc), "CUDA IPC peer mapping failed"
+        from beyond_deep_ensembles_b200 import _lib
+        for _ in range(3):   # epochs advance; parity double-buffering is exercised
+            l0 = _lib.launch_count
+            bdist.svgd_step_sharded(Xl, Gl, out, sc, 0.01, 1.0, 50000.0)
+            extra["abi_calls_per_step"] = _lib.launch_count - l0
+        # a second scratch on the same peer set (MultiX members share the exchange buffers)
+        sc2 = ops.SvgdScratch.allocate(n, dev)
+        assert bdist.enable_peer_exchange(sc2)
+        ops.svgd_pairdist(Xl, sc2)
+        extra["dist2"] = sc2.dist.cpu()
+        # training-step kernels: K2 + SGD + next pair distances + cross-rank sum + K1b in ONE launch per step
+        Xt, buf = Xl.clone(), torch.zeros(hi - lo, device=dev)
+        nk = ops.NextKernel(True, 0.01, 1.0, 50000.0)
+        kw = dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)
+        if 2 <= n <= ops.NEXT_KERNEL_MAX_PARTICLES:
+            ops.svgd_pairdist_bandwidth(Xt, sc2, 0.01, 1.0, 50000.0)
+            for s in range(3):
+                ops.svgd_apply_sgd(Xt, Gl, sc2, buf, buf_initialized=(s > 0), next_kernel=nk, **kw)
+            extra["train_X"], extra["train_dist"], extra["train_K"] = Xt.cpu(), sc2.dist.cpu(), sc2.K.cpu()
+        torch.cuda.synchronize()
+        extra["peer_status"] = sc.peers.status()
+    else:
+        bdist.svgd_step_sharded(Xl, Gl, out, sc, 0.01, 1.0, 50000.0)
     torch.save({"lo": lo, "hi": hi, "out": out.cpu(), "dist": sc.dist.cpu(), "sel": sc.sel.cpu(), "K": sc.K.cpu(),
-                "calls": list(fake.calls) if fake else None}, f"{out_path}.{rank}")
+                "calls": list(fake.calls) if fake else None, **extra}, f"{out_path}.{rank}")
     dist.barrier()
+    bdist.shutdown_peer_exchange()
     dist.destroy_process_group()

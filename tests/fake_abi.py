@@ -60,6 +60,21 @@ class FakeLib:
         out._obj.value = 64
         return 0
 
+    def bde_value_workspace_bytes(self, out):
+        out._obj.value = 64
+        return 0
+
+    # the NVLink peer exchange needs real devices: the double refuses, callers must use the all-reduce form
+    def bde_peer_buffer_bytes(self, out):
+        out._obj.value = 0
+        return 0
+
+    def _no_peer(self, *a):
+        return -1
+
+    bde_peer_alloc = bde_peer_open = bde_peer_close = bde_peer_free = _no_peer
+    bde_peer_attach = bde_peer_detach = bde_peer_status = _no_peer
+
     def bde_svgd_pairdist(self, X, n, D, ld, dist, accumulate, ws, wsb, stream):
         self.calls.append("pairdist")
         d = O.svgd_pairdist(_mat(X, n, D, ld))

@@ -19,10 +19,10 @@ def free_port():
         return s.getsockname()[1]
 
 
-def check(tmp_path, world, n, D, backend):
+def check(tmp_path, world, n, D, backend, peer=False):
     import dist_worker
     out_path = str(tmp_path / "shard")
-    mp.spawn(dist_worker.run, args=(world, free_port(), n, D, out_path, backend), nprocs=world, join=True)
+    mp.spawn(dist_worker.run, args=(world, free_port(), n, D, out_path, backend, peer), nprocs=world, join=True)
 
     g = torch.Generator().manual_seed(1234)
     X = torch.randn(n, D, generator=g) * (0.05 * (1 + 0.1 * torch.arange(n).float())).unsqueeze(1)
@@ -39,6 +39,7 @@ def check(tmp_path, world, n, D, backend):
         assert torch.equal(p["K"], parts[0]["K"])  # K1b is redundant and identical on every rank
         if backend == "gloo":
             assert p["calls"] == ["pairdist", "bandwidth", "apply"]  # the unfused 3-kernel form when sharded
+    return parts, X, G
 
 
 @pytest.mark.parametrize("world,n,D", [(2, 10, 5000), (3, 5, 1237)])
@@ -53,3 +54,31 @@ def test_sharded_step_nccl(tmp_path, world, n, D):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     check(tmp_path, world, n, D, "nccl")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,n,D", [(2, 10, 1_000_003), (2, 20, 273_610), (2, 5, 2_000_000)])
+def test_sharded_step_peer_exchange(tmp_path, world, n, D):
+    """D-sharded step with the n*n sum done INSIDE K1's tail over peer memory (CUDA IPC + NVLink): same launch
+    sequence as one GPU, bit-identical distances / K on every rank, and the one-launch training step on top."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    parts, X, G = check(tmp_path, world, n, D, "nccl", peer=True)
+    for p in parts:
+        assert p["abi_calls_per_step"] == 2                      # K1+exchange+K1b, K2
+        assert torch.equal(p["dist"], parts[0]["dist"])          # rank-ordered sum: same bits everywhere
+        # a second scratch on the same peer set; ragged slices run the generic K1 whose per-CTA fp64 atomics are
+        # not order-deterministic, hence a tolerance here (the cross-rank sum itself is exact: previous line)
+        np.testing.assert_allclose(p["dist2"].numpy(), parts[0]["dist"].numpy(), rtol=1e-12)
+        assert p["peer_status"][1] == 0                          # no timed-out exchange
+    if "train_X" in parts[0]:
+        # three training steps (K2 + shared-state SGD per particle, svgd.py:83-103) on the unsharded problem
+        Xr, state = X.clone(), {}
+        hyper = dict(lr=0.05, momentum=0.9, nesterov=True, weight_decay=3e-4)
+        for s in range(3):
+            new_grad, _ = O.svgd_step_fused(Xr, G, 0.01, 1.0, 50000.0)
+            Xr, state = O.svgd_base_optimizer_steps(Xr, new_grad.float(), "sgd", hyper, state)
+        full = torch.cat([p["train_X"] for p in parts], dim=1)
+        np.testing.assert_allclose(full.numpy(), Xr.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(parts[0]["train_dist"].numpy(), O.svgd_pairdist(full).numpy(), rtol=2e-6)
+        assert torch.equal(parts[0]["train_K"], parts[1]["train_K"])
