@@ -422,14 +422,16 @@ def main():
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
 
     launches0 = _lib.launch_count
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the sampler thread (NVML init) starts BEFORE the barrier: anything rank-variable between the barrier and
+    # t_begin shows up as start skew, which the in-kernel exchange of step 1 would charge to the fastest rank
     with ClockSampler(local_rank) as clocks:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         t_begin.record()
         for s in range(steps):
             step(evs[s])

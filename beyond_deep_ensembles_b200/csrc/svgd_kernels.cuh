@@ -759,27 +759,37 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
 // order, shared state in registers), re-reading x_i from the stage, and writes X in place — `out`
 // never touches HBM.
 // ---------------------------------------------------------------------------------
+// Tile sets (TS): for n > 12 a thread's quad costs 4 n^2 FFMA2, so the 64 consumer threads of a 256-column tile
+// cannot keep the FMA pipes of four SM sub-partitions busy.  The consumers are therefore split into TS sets of
+// TC/4 threads and set c works on the tiles it = c (mod TS) of the ring: 2 TS consumer warps, every tile still read
+// from shared memory exactly once, every thread still owns all n rows of its quad (the shared-state optimizer
+// steps of the fused form stay thread-local).
 __host__ __device__ constexpr int apply_tile_cols(int n) { return n <= 12 ? 512 : 256; }
+__host__ __device__ constexpr int apply_default_tile_sets(int n) { return n <= 12 ? 1 : 4; }
 __host__ __device__ constexpr int apply_stage_bytes(int n, int opt = 0) {
     return (2 * n + opt_state_rows(opt)) * apply_tile_cols(n) * 4;
 }
+__host__ __device__ constexpr int apply_smem_budget(int n) { return (n <= 12 ? 200 : 212) * 1024; }
 __host__ __device__ constexpr int apply_stages(int n, int opt = 0) {
-    return (200 * 1024) / apply_stage_bytes(n, opt) > 8 ? 8 : (200 * 1024) / apply_stage_bytes(n, opt);
+    return apply_smem_budget(n) / apply_stage_bytes(n, opt) > 8 ? 8 : apply_smem_budget(n) / apply_stage_bytes(n, opt);
 }
 
-template <int N, int OPT, bool NEXT = false>
-__global__ void __launch_bounds__(apply_tile_cols(N) / 4 + 32, 1)
+template <int N, int OPT, bool NEXT = false, int TS = apply_default_tile_sets(N)>
+__global__ void __launch_bounds__(TS * apply_tile_cols(N) / 4 + 32, 1)
 svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
                       const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
                       const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
     static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
+    static_assert(!NEXT || TS == 1, "the training-step form flushes its pair sums CTA-uniformly");
     constexpr int PN = NEXT ? pair_count(N) : 1;
     constexpr int NP = (N + 3) & ~3;
     constexpr int TC = apply_tile_cols(N);
     constexpr int STAGES = apply_stages(N, OPT);
     constexpr int ROWS = 2 * N + opt_state_rows(OPT);
-    constexpr int CONSUMERS = TC / 4;  // threads; one column quad each
+    constexpr int QT = TC / 4;              // threads of one tile set; one column quad each
+    constexpr int CONSUMERS = TS * QT;
     constexpr int CWARPS = CONSUMERS / 32;
+    static_assert(STAGES > TS || TS == 1, "every set holds a stage while it computes: the ring must be deeper than TS");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][ROWS][TC]: X rows, G rows, state rows
     __shared__ __align__(16) float sKT[N][NP];
@@ -801,7 +811,7 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], CWARPS);
+            mbar_init(&empty_bar[s], QT / 32);   // released by the warps of the one set that consumed it
         }
         mbar_fence_init();
     }
@@ -839,18 +849,25 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
         }
     } else {
         const int lane = tid & 31;
+        const int set = tid / QT, q = tid - set * QT;   // tile set and quad within the tile
         f32x2 pacc[PN];
 #pragma unroll
         for (int k = 0; k < PN; ++k) pacc[k] = 0ull;
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        int it = set;
+        for (int64_t t = blockIdx.x + static_cast<int64_t>(set) * gridDim.x; t < ntiles;
+             t += static_cast<int64_t>(TS) * gridDim.x, it += TS) {
             const int s = it % STAGES;
             const uint32_t use = static_cast<uint32_t>(it / STAGES);
             const int64_t col0 = t * TC;
             const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
-            const bool active = 4 * tid < w;
+            const bool active = 4 * q < w;
+            if constexpr (TS > 1) {
+                // another set consumed this stage's previous use: once that release is visible the full barrier can
+                // only be in phase `use`, so the parity wait below cannot alias an older phase
+                if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
+            }
             mbar_wait(&full_bar[s], use & 1u);
-            const float* sx = tiles + static_cast<size_t>(s) * ROWS * TC + 4 * tid;
+            const float* sx = tiles + static_cast<size_t>(s) * ROWS * TC + 4 * q;
             const float* sg = sx + N * TC;
             f32x2 acc[N][2];
 #pragma unroll
@@ -876,7 +893,7 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 if (active) {
-                    float* op = out + col0 + 4 * tid;
+                    float* op = out + col0 + 4 * q;
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         V4 v;
@@ -894,14 +911,14 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                     for (int i = 0; i < N; ++i) xn[i].lo = xn[i].hi = 0ull;
                 }
                 if (active) {
-                    float* xw = const_cast<float*>(X) + col0 + 4 * tid;
+                    float* xw = const_cast<float*>(X) + col0 + 4 * q;
                     if (has_s0) s0 = lds_v4(sg + N * TC);
                     if (OPT == kOptAdam) s1 = lds_v4(sg + (N + 1) * TC);
                     if (o.out_last) {
                         V4 v;
                         v.lo = acc[N - 1][0];
                         v.hi = acc[N - 1][1];
-                        stg_stream_v4(o.out_last + col0 + 4 * tid, v);
+                        stg_stream_v4(o.out_last + col0 + 4 * q, v);
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
@@ -914,8 +931,8 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 if (active) {
-                    if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + col0 + 4 * tid, s0);
-                    if (OPT == kOptAdam) stg_stream_v4(o.state1 + col0 + 4 * tid, s1);
+                    if (OPT == kOptAdam || o.momentum != 0.0f) stg_stream_v4(o.state0 + col0 + 4 * q, s0);
+                    if (OPT == kOptAdam) stg_stream_v4(o.state1 + col0 + 4 * q, s1);
                 }
                 if constexpr (NEXT) {
                     // the K1 of the next step, on the updated particles while they are still in registers
@@ -995,6 +1012,26 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     return BDE_OK;
 }
 
+template <int N, int OPT, bool NEXT, int TS>
+int launch_apply_tma(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
+                     int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st, const NextDistParams& nd) {
+    constexpr int TC = apply_tile_cols(N);
+    constexpr int smem = apply_stages(N, OPT) * apply_stage_bytes(N, OPT);
+    static_assert(apply_stages(N, OPT) >= 2, "ring too shallow");
+    const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
+    static bool configured = false;
+    if (!configured) {
+        BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int64_t grid = sm_count_cached();
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) grid = 1;
+    svgd_apply_tma_kernel<N, OPT, NEXT, TS><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
+
 template <int N, int OPT, bool NEXT = false>
 int launch_apply_opt(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
                      int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st,
@@ -1003,23 +1040,13 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
     constexpr int TC = apply_tile_cols(N);
     const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
     int variant = tuning().apply_variant;
-    // auto: the staged kernel wins once every SM has a few tiles; for N > 12 (two consumer warps per
-    // CTA at the 256-column tile) the direct kernel is still faster — measured, see DESIGN.md
-    if (variant == 0) variant = (N <= 12 && ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+    // auto: the staged kernel wins once every SM has a few tiles per tile set
+    if (variant == 0) variant = (ntiles >= 2 * apply_default_tile_sets(N) * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
     if (variant == 2) {
-        constexpr int smem = apply_stages(N, OPT) * apply_stage_bytes(N, OPT);
-        static_assert(apply_stages(N, OPT) >= 2, "ring too shallow");
-        static bool configured = false;
-        if (!configured) {
-            BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            configured = true;
+        if constexpr (N > 12 && !NEXT) {
+            if (tuning().apply_tile_sets == 3) return launch_apply_tma<N, OPT, NEXT, 3>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
         }
-        int64_t grid = sm_count_cached();
-        if (grid > ntiles) grid = ntiles;
-        if (grid < 1) grid = 1;
-        svgd_apply_tma_kernel<N, OPT, NEXT><<<static_cast<unsigned>(grid), TC / 4 + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
-        BDE_CHECK_LAUNCH();
-        return BDE_OK;
+        return launch_apply_tma<N, OPT, NEXT, apply_default_tile_sets(N)>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
     }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {

@@ -47,8 +47,8 @@ const char* bde_error_string(int code);
 /*
  * Launch-geometry override for tuning sweeps: key is "pairdist_ctas_per_sm",
  * "apply_ctas_per_sm", "ew_ctas_per_sm", or "pairdist_variant" / "apply_variant" /
- * "ew_variant" (1 = direct-LDG kernels, 2 = TMA-staged kernels); value 0 restores the
- * automatic choice.
+ * "ew_variant" (1 = direct-LDG kernels, 2 = TMA-staged kernels), or "apply_tile_sets" (3 or 4
+ * consumer tile sets of the staged K2 at n > 12); value 0 restores the automatic choice.
  */
 int bde_tune(const char* key, int value);
 /* number of SMs of the current device (grid sizing is done inside the library) */

@@ -277,6 +277,52 @@ def check_update(x_new, x_old, ref_new, what):
     assert (np.abs(upd - upd_ref) <= bound).all(), what
 
 
+@pytest.mark.parametrize("tile_sets", [3, 4])
+@pytest.mark.parametrize("opt", [None, "sgd-cifar", "adam"])
+@pytest.mark.parametrize("n,D", [(20, 600_001), (16, 700_003), (13, 450_000)])
+def test_staged_apply_tile_sets(ops, cuda_lib, tile_sets, opt, n, D):
+    """Staged K2 / K2f at n > 12: the consumer warps are split into tile sets that take turns on the ring
+    (svgd_kernels.cuh, "Tile sets").  D is large enough that every set wraps the ring several times (the stage
+    re-use / barrier-parity logic), with a ragged last tile and D % 4 != 0; both set counts; plain, SGD and Adam
+    forms against the oracle, and bit-for-bit against the direct-LDG kernel (same per-column arithmetic)."""
+    X, G = particles(n, D, seed=7 * n + D)
+    X *= 4.0
+    G *= 50.0
+    ld = (D + 3) // 4 * 4
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    ops.svgd_pairdist_bandwidth(dev_matrix(X, ld), sc, 0.01, 1.0, 768.0)
+    results = {}
+    for variant in (1, 2):
+        dX, dG = dev_matrix(X, ld), dev_matrix(G, ld)
+        dOut = dev_matrix(torch.full_like(X, float("nan")), ld)
+        s0, s1, out_last = (torch.zeros(D, device="cuda") for _ in range(3))
+        cuda_lib.bde_tune(b"apply_variant", variant)
+        cuda_lib.bde_tune(b"apply_tile_sets", tile_sets)
+        try:
+            if opt is None:
+                ops.svgd_apply(dX, dG, dOut, sc)
+                ops.svgd_apply(dX, dG, dOut, sc)   # ring state must be clean across launches
+                results[variant] = (dOut.cpu(),)
+            else:
+                kind, hyper = OPT_KINDS[opt]
+                fused_apply(ops, kind, hyper, dX, dG, sc, s0, s1, False, 0, out_last)
+                fused_apply(ops, kind, hyper, dX, dG, sc, s0, s1, True, n, out_last)   # carried state, same K / A
+                results[variant] = (dX.cpu(), s0.cpu(), s1.cpu(), out_last.cpu())
+        finally:
+            cuda_lib.bde_tune(b"apply_variant", 0)
+            cuda_lib.bde_tune(b"apply_tile_sets", 0)
+    for a, b in zip(results[1], results[2]):
+        assert torch.equal(a, b)
+    K, A = sc.K.cpu(), sc.A.cpu()
+    if opt is None:
+        np.testing.assert_allclose(results[2][0].numpy(), O.svgd_apply(X, G, K, A).numpy(), rtol=RTOL, atol=ATOL)
+    else:
+        kind, hyper = OPT_KINDS[opt]
+        x1, state = O.svgd_base_optimizer_steps(X, O.svgd_apply(X, G, K, A).float(), kind, hyper, None)
+        x2, state = O.svgd_base_optimizer_steps(x1, O.svgd_apply(x1, G, K, A).float(), kind, hyper, state)
+        np.testing.assert_allclose(results[2][0].numpy(), x2.numpy(), rtol=RTOL, atol=5 * ATOL)
+
+
 @pytest.mark.parametrize("variant", [1, 2], ids=["direct", "tma"])
 @pytest.mark.parametrize("opt", list(OPT_KINDS))
 @pytest.mark.parametrize("n,D,ld,mis", [(10, 4099, 4100, 0), (10, 501, 512, 0), (5, 37, 40, 0), (20, 1000, 1000, 0),

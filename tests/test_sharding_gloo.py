@@ -57,7 +57,8 @@ def test_sharded_step_nccl(tmp_path, world, n, D):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,n,D", [(2, 10, 1_000_003), (2, 20, 273_610), (2, 5, 2_000_000)])
+@pytest.mark.parametrize("world,n,D", [(2, 10, 1_000_003), (2, 20, 273_610), (2, 5, 2_000_000), (4, 10, 1_000_003),
+                                       (4, 20, 273_610), (8, 10, 4_000_001)])
 def test_sharded_step_peer_exchange(tmp_path, world, n, D):
     """D-sharded step with the n*n sum done INSIDE K1's tail over peer memory (CUDA IPC + NVLink): same launch
     sequence as one GPU, bit-identical distances / K on every rank, and the one-launch training step on top."""
@@ -81,4 +82,5 @@ def test_sharded_step_peer_exchange(tmp_path, world, n, D):
         full = torch.cat([p["train_X"] for p in parts], dim=1)
         np.testing.assert_allclose(full.numpy(), Xr.numpy(), rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(parts[0]["train_dist"].numpy(), O.svgd_pairdist(full).numpy(), rtol=2e-6)
-        assert torch.equal(parts[0]["train_K"], parts[1]["train_K"])
+        for p in parts[1:]:
+            assert torch.equal(parts[0]["train_K"], p["train_K"])
