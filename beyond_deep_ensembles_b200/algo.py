@@ -14,6 +14,10 @@ import torch
 from torch.optim import Optimizer
 
 
+def _scaler_active(grad_scaler) -> bool:
+    return grad_scaler is not None and grad_scaler.is_enabled()
+
+
 class BayesianOptimizer(Optimizer):
     """An optimizer over a distribution of parameters (reference: algo.py:5-81).
 
@@ -24,49 +28,52 @@ class BayesianOptimizer(Optimizer):
 
     def __init__(self, params, defaults):
         super().__init__(params, defaults)
+        # tells torch's GradScaler that step() deals with the loss scale itself (algo.py:17)
         self._step_supports_amp_scaling = True
 
+    # ---- what subclasses implement (algo.py:19-56) ----
     def step(self, forward_closure, backward_closure):
         raise NotImplementedError()
-
-    def complete_epoch(self):
-        pass
 
     def sample_parameters(self):
         raise NotImplementedError()
 
-    def init_grad_scaler(self, grad_scaler):
-        # GradScalers initialise lazily on the first step/unscale; the optimizers poke at the
-        # per-optimizer state before that (algo.py:44-49).
-        if grad_scaler is not None and grad_scaler.is_enabled() and grad_scaler._scale is None:
-            grad_scaler._lazy_init_scale_growth_tracker(self._params_device())
+    def complete_epoch(self):
+        """End-of-epoch bookkeeping; nothing by default."""
 
     def get_base_optimizer(self):
-        pass
+        """The optimizer that makes the actual parameter updates (the one LR schedulers attach to)."""
 
-    def _params_device(self):
-        return self.param_groups[0]["params"][0].device
-
-    def _params(self):
-        for group in self.param_groups:
-            for param in group["params"]:
-                yield param
+    # ---- GradScaler plumbing (algo.py:44-49, 65-81) ----
+    def init_grad_scaler(self, grad_scaler):
+        # GradScalers initialise lazily on the first step/unscale; the optimizers poke at the
+        # per-optimizer state before that, so force the initialisation here.
+        if _scaler_active(grad_scaler) and grad_scaler._scale is None:
+            grad_scaler._lazy_init_scale_growth_tracker(self._params_device())
 
     def _prepare_and_check_grads(self, grad_scaler, optimizer=None):
-        if grad_scaler is None or not grad_scaler.is_enabled():
+        """Unscale the gradients held by `optimizer` (default: self); True when they may be used."""
+        if not _scaler_active(grad_scaler):
             return True
-        opt = self if optimizer is None else optimizer
-        grad_scaler.unscale_(opt)
+        grad_scaler.unscale_(optimizer if optimizer is not None else self)
         # Kept literally from algo.py:73: this reads the OPTIMIZER's state dict (a defaultdict,
         # so the key springs into existence as {}), not the scaler's found-inf record, hence it
         # is always True — the reference's behaviour, which callers have been trained against.
-        return sum(v.item() for v in self.state["found_inf_per_device"].values()) == 0
+        found = self.state["found_inf_per_device"]
+        return sum(flag.item() for flag in found.values()) == 0
 
     def _set_grad_scaler_state(self, grad_scaler, stage, optimizer=None):
-        if grad_scaler is None or not grad_scaler.is_enabled():
-            return
-        opt = self if optimizer is None else optimizer
-        grad_scaler._per_optimizer_states[id(opt)]["stage"] = stage
+        if _scaler_active(grad_scaler):
+            key = id(optimizer if optimizer is not None else self)
+            grad_scaler._per_optimizer_states[key]["stage"] = stage
+
+    # ---- parameter access (algo.py:57-63) ----
+    def _params(self):
+        for group in self.param_groups:
+            yield from group["params"]
+
+    def _params_device(self):
+        return next(self._params()).device
 
 
 class LastLayerBayesianOptimizer(BayesianOptimizer):
@@ -74,8 +81,10 @@ class LastLayerBayesianOptimizer(BayesianOptimizer):
 
     The deterministic gradients are zeroed once and ACCUMULATE over all forward/backward
     passes the Bayesian optimizer makes inside its step before the deterministic optimizer
-    steps — exactly the reference's order (algo.py:100-103).
+    steps — exactly the reference's order (algo.py:100-103).  GradScalers are refused, as there.
     """
+
+    _PARTS = ("ll_bayesian_optimizer", "deterministic_optimizer")
 
     def __init__(self, ll_bayesian_optimizer: BayesianOptimizer, deterministic_optimizer: Optimizer):
         # deliberately no super().__init__(): the reference does not call it either
@@ -83,18 +92,13 @@ class LastLayerBayesianOptimizer(BayesianOptimizer):
         self.deterministic_optimizer = deterministic_optimizer
 
     def step(self, forward_closure, backward_closure, grad_scaler=None):
-        if grad_scaler is not None and grad_scaler.is_enabled():
+        if _scaler_active(grad_scaler):
             raise ValueError("Doesn't support grad scaler")
-        self.deterministic_optimizer.zero_grad()
-        loss = self.ll_bayesian_optimizer.step(forward_closure, backward_closure)
-        self.deterministic_optimizer.step()
+        body, head = self.deterministic_optimizer, self.ll_bayesian_optimizer
+        body.zero_grad()
+        loss = head.step(forward_closure, backward_closure)   # >= 1 backward pass: fills the body's gradients too
+        body.step()
         return loss
-
-    def complete_epoch(self):
-        self.ll_bayesian_optimizer.complete_epoch()
-
-    def sample_parameters(self):
-        self.ll_bayesian_optimizer.sample_parameters()
 
     def init_grad_scaler(self, grad_scaler):
         if grad_scaler.is_enabled():
@@ -104,16 +108,20 @@ class LastLayerBayesianOptimizer(BayesianOptimizer):
         raise RuntimeError("There is no defined base optimizer on the ll optimizer. Call get_base_optimizer directly "
                            "on the passed ll bayesian optimizer")
 
+    def complete_epoch(self):
+        self.ll_bayesian_optimizer.complete_epoch()
+
+    def sample_parameters(self):
+        self.ll_bayesian_optimizer.sample_parameters()
+
     def state_dict(self) -> Dict[str, Any]:
-        return {
-            "ll_bayesian_optimizer": self.ll_bayesian_optimizer.state_dict(),
-            "deterministic_optimizer": self.deterministic_optimizer.state_dict(),
-        }
+        return {part: getattr(self, part).state_dict() for part in self._PARTS}
 
     def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
-        self.ll_bayesian_optimizer.load_state_dict(state_dict["ll_bayesian_optimizer"])
-        self.deterministic_optimizer.load_state_dict(state_dict["deterministic_optimizer"])
+        for part in self._PARTS:
+            getattr(self, part).load_state_dict(state_dict[part])
 
     def __repr__(self) -> str:
-        return ("LL Bayesian Optimizer: \n\n" + repr(self.ll_bayesian_optimizer) +
-                "\n==================================\nDeterministic Optimizer:\n\n" + repr(self.deterministic_optimizer))
+        bar = "=" * 34
+        return (f"LL Bayesian Optimizer: \n\n{self.ll_bayesian_optimizer!r}\n{bar}\n"
+                f"Deterministic Optimizer:\n\n{self.deterministic_optimizer!r}")

@@ -18,44 +18,49 @@ class GaussianPrior:
     _bde_kind = "gauss"
 
     def __init__(self, mu, sigma):
-        self.mu = mu
-        self.sigma = sigma
+        self.mu, self.sigma = mu, sigma
         self.dist = torch.distributions.Normal(mu, sigma)
 
     def log_prob(self, x):
         return self.dist.log_prob(x)
 
     def kl_divergence(self, mu2, sigma2):
-        # API compatibility for callers that hold (mean, std) tensors (the activation-space
-        # layers of bbb_layers.py, outside the optimizer path).  BBBOptimizer itself goes through
-        # GaussianParameter.kl_divergence -> K9.
-        kl = 0.5 * (2 * torch.log(self.sigma / sigma2) - 1 + (sigma2 / self.sigma).pow(2)
-                    + ((self.mu - mu2) / self.sigma).pow(2))
-        return kl.sum()
+        """KL(N(mu2, sigma2^2) || prior) summed over all entries, from (mean, std) TENSORS.
+        API compatibility for the activation-space layers of bbb_layers.py (outside the optimizer
+        path); BBBOptimizer itself goes through GaussianParameter.kl_divergence -> K9."""
+        ratio = sigma2 / self.sigma
+        shift = (self.mu - mu2) / self.sigma
+        per_entry = 0.5 * (2 * torch.log(self.sigma / sigma2) - 1 + ratio.pow(2) + shift.pow(2))
+        return per_entry.sum()
 
 
 class MixturePrior:
-    """Scale mixture of two zero-mean Gaussians (reference: bbb.py:23-37)."""
+    """Scale mixture of two zero-mean Gaussians (reference: bbb.py:23-37); each component's
+    log-density is clamped to [-23, 0] before the mixture is formed, as there."""
     _bde_kind = "mixture"
 
     def __init__(self, pi, sigma1, sigma2, validate_args=None):
         self.pi = torch.tensor(pi)
-        self.sigma1 = sigma1
-        self.sigma2 = sigma2
+        self.sigma1, self.sigma2 = sigma1, sigma2
         self.dist1 = torch.distributions.Normal(0, sigma1, validate_args)
         self.dist2 = torch.distributions.Normal(0, sigma2, validate_args)
 
     def log_prob(self, value):
-        prob1 = torch.log(self.pi) + torch.clamp(self.dist1.log_prob(value), -23, 0)
-        prob2 = torch.log(1 - self.pi) + torch.clamp(self.dist2.log_prob(value), -23, 0)
-        return torch.logaddexp(prob1, prob2)
+        weights = (torch.log(self.pi), torch.log(1 - self.pi))
+        parts = [w + torch.clamp(d.log_prob(value), -23, 0) for w, d in zip(weights, (self.dist1, self.dist2))]
+        return torch.logaddexp(parts[0], parts[1])
 
     def kl_divergence(self, mu2, sigma2):
+        # a point estimate: minus the log-density of the means; sigma2 is ignored (bbb.py:36-37)
         return -self.log_prob(mu2).sum()
 
 
 def collect_kl(model) -> torch.Tensor:
-    return sum(getattr(layer, "kl", 0) + collect_kl(layer) for layer in model.children())
+    """Sum of the `kl` attributes over the module tree below `model` (bbb.py:39-40)."""
+    total = 0
+    for layer in model.children():
+        total = total + getattr(layer, "kl", 0) + collect_kl(layer)
+    return total
 
 
 class BBBOptimizer(BayesianOptimizer):

@@ -1,46 +1,58 @@
-"""MultiX container — drop-in for the reference's DeepEnsemble (src/algos/ensemble.py:8-48)."""
+"""MultiX container — drop-in for the reference's DeepEnsemble (src/algos/ensemble.py:8-48).
+
+Members are independent posterior problems: each model keeps its own optimizer (any class of this
+package), the container only fans state dicts and predictions out over them.
+"""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
 
-class DeepEnsemble(nn.Module):
-    """Models together with their optimizers; members are independent posterior problems."""
+def split_samples(samples: int, members: int):
+    """How many predictions each member contributes (ensemble.py:37-39): `samples // members`
+    each, the FIRST member also takes the remainder."""
+    share = samples // members
+    return [samples - share * (members - 1)] + [share] * (members - 1)
 
+
+class DeepEnsemble(nn.Module):
     def __init__(self, models_and_optimizers):
         super().__init__()
-        pairs = list(models_and_optimizers)
-        self.models = nn.ModuleList([m for m, _ in pairs])
-        self.optimizers = [o for _, o in pairs]
-
-    def state_dict(self, prefix='', keep_vars=False):
-        return {
-            "models": self.models.state_dict(prefix=prefix, keep_vars=keep_vars),
-            "optimizers": [o.state_dict() for o in self.optimizers],
-        }
-
-    def load_state_dict(self, state_dict, strict=True):
-        self.models.load_state_dict(state_dict["models"], strict=strict)
-        for optimizer, optimizer_state in zip(self.optimizers, state_dict["optimizers"]):
-            optimizer.load_state_dict(optimizer_state)
-
-    def predict(self, predict_closure, samples, multisample=False):
-        """`samples` predictions: samples // members per member, the first member takes the
-        remainder; every prediction is preceded by optimizer.sample_parameters() (ensemble.py:28-44)."""
-        if len(self.models) == 1 and getattr(self.models[0], "supports_multisample", False) and multisample:
-            return predict_closure(self.models[0], n_samples=samples)
-
-        members = len(self.models)
-        per_model = samples // members
-        output = []
-        for i, (model, optimizer) in enumerate(self.models_and_optimizers):
-            count = per_model if i > 0 else samples - (members - 1) * per_model
-            for _ in range(count):
-                optimizer.sample_parameters()
-                output.append(predict_closure(model))
-        return torch.stack(output)
+        models, optimizers = [], []
+        for model, optimizer in models_and_optimizers:
+            models.append(model)
+            optimizers.append(optimizer)
+        self.models = nn.ModuleList(models)
+        self.optimizers = optimizers
 
     @property
     def models_and_optimizers(self):
         return list(zip(self.models, self.optimizers))
+
+    # -- checkpoints: {"models": <ModuleList state>, "optimizers": [<optimizer state>, ...]} (ensemble.py:17-26)
+    def state_dict(self, prefix='', keep_vars=False):
+        out = {"models": self.models.state_dict(prefix=prefix, keep_vars=keep_vars)}
+        out["optimizers"] = [optimizer.state_dict() for optimizer in self.optimizers]
+        return out
+
+    def load_state_dict(self, state_dict, strict=True):
+        self.models.load_state_dict(state_dict["models"], strict=strict)
+        saved = state_dict["optimizers"]
+        for k in range(min(len(saved), len(self.optimizers))):   # zip semantics of the reference
+            self.optimizers[k].load_state_dict(saved[k])
+
+    def predict(self, predict_closure, samples, multisample=False):
+        """`samples` predictions stacked along dim 0.  Every single prediction is preceded by that
+        member's `optimizer.sample_parameters()`; a lone member that `supports_multisample` gets the
+        whole request in one call when `multisample` is set (ensemble.py:28-44)."""
+        lone = self.models[0] if len(self.models) == 1 else None
+        if lone is not None and multisample and getattr(lone, "supports_multisample", False):
+            return predict_closure(lone, n_samples=samples)
+
+        drawn = []
+        for (model, optimizer), count in zip(self.models_and_optimizers, split_samples(samples, len(self.models))):
+            for _ in range(count):
+                optimizer.sample_parameters()
+                drawn.append(predict_closure(model))
+        return torch.stack(drawn)
