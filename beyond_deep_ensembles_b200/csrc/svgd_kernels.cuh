@@ -447,8 +447,11 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
             }
         }
     } else {
-        const int g = tid / QT, qi = tid - g * QT;
-        pairdist_tma_dispatch<N, 0>(g, X, D, ld, tiles, full_bar, empty_bar, wacc[tid >> 5], qi);
+        // pair group = warp % NG: warps w and w + 4 sit on the same SM sub-partition, and with NG = 2 or 4 they then
+        // run the SAME unrolled pair loop (one copy in that scheduler's instruction cache instead of two)
+        const int wid = tid >> 5;
+        const int g = wid % NG, qi = (wid / NG) * 32 + (tid & 31);
+        pairdist_tma_dispatch<N, 0>(g, X, D, ld, tiles, full_bar, empty_bar, wacc[wid], qi);
     }
     __syncthreads();
 
@@ -456,7 +459,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
     for (int p = tid; p < P; p += nthreads) {
         const int grp = p / PG, k = p - grp * PG;
         double sacc = 0.0;
-        for (int wv = grp * (QT / 32); wv < (grp + 1) * (QT / 32); ++wv) sacc += wacc[wv][k];
+        for (int wv = grp; wv < CWARPS; wv += NG) sacc += wacc[wv][k];
         cta_vals[p] = sacc;
     }
     __syncthreads();
@@ -477,7 +480,48 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
 // ---------------------------------------------------------------------------------
 // K2 (+ optional fused base-optimizer step, f1)
 // ---------------------------------------------------------------------------------
-__host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : 8; }
+// n > 16: the j-loop of K2 stays rolled (see apply_row)
+__host__ __device__ constexpr bool apply_rolled(int n) { return n > 16; }
+__host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : (n <= 16 ? 8 : 4); }
+
+// out_i += K_ij g_j + A_ij x_j for one source row j of a column quad.  n <= 12: fully unrolled over j by the
+// callers (coefficients become immediates-offset LDS).  n > 12: the callers keep j as a ROLLED loop — the fully
+// unrolled 4 n^2 FFMA2 body (26 KB of code at n = 20) thrashed the instruction cache ("no instruction" was the
+// top warp stall in ncu) — and read the coefficient rows as 128-bit words.
+#ifndef BDE_APPLY_J_UNROLL
+#define BDE_APPLY_J_UNROLL 5   // source rows per iteration of the rolled j-loop (n = 20: 4 iterations of 400 FFMA2)
+#endif
+template <int N>
+__device__ __forceinline__ void apply_row(f32x2 (&acc)[N][2], const V4& g, const V4& x, const float* __restrict__ kt,
+                                          const float* __restrict__ at) {
+    if constexpr (N % 4 == 0 && apply_rolled(N)) {
+#pragma unroll
+        for (int c = 0; c < N / 4; ++c) {
+            const float4 k4 = *reinterpret_cast<const float4*>(kt + 4 * c);
+            const float4 a4 = *reinterpret_cast<const float4*>(at + 4 * c);
+            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = 4 * c + u;
+                acc[i][0] = fma2s(kk[u], g.lo, acc[i][0]);
+                acc[i][1] = fma2s(kk[u], g.hi, acc[i][1]);
+                acc[i][0] = fma2s(aa[u], x.lo, acc[i][0]);
+                acc[i][1] = fma2s(aa[u], x.hi, acc[i][1]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const float kij = kt[i];
+            const float aij = at[i];
+            acc[i][0] = fma2s(kij, g.lo, acc[i][0]);
+            acc[i][1] = fma2s(kij, g.hi, acc[i][1]);
+            acc[i][0] = fma2s(aij, x.lo, acc[i][0]);
+            acc[i][1] = fma2s(aij, x.hi, acc[i][1]);
+        }
+    }
+}
 
 __device__ __forceinline__ f32x2 mul2s(float s, f32x2 b) {
     f32x2 r;
@@ -638,6 +682,7 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
                   const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
     constexpr int NP = (N + 3) & ~3;
     constexpr int JC = apply_row_chunk(N);
+    static_assert(!apply_rolled(N) || N % JC == 0, "the rolled chunk loop has no ragged last chunk");
     constexpr int PN = NEXT ? pair_count(N) : 1;  // pair accumulators of the updated particles
     static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
     // transposed coefficients: sKT[j][i] = K[i][j] so that the i-loop reads contiguous words
@@ -665,8 +710,7 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
         for (int i = 0; i < N; ++i) acc[i][0] = acc[i][1] = 0ull;
         const float* xp = X + 4 * q;
         const float* gp = G + 4 * q;
-#pragma unroll
-        for (int jc = 0; jc < N; jc += JC) {
+        auto row_chunk = [&](int jc) {  // JC source rows: all loads first, then the FFMA2 work
             V4 x[JC], g[JC];
 #pragma unroll
             for (int jj = 0; jj < JC; ++jj) {
@@ -678,20 +722,15 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
                 }
             }
 #pragma unroll
-            for (int jj = 0; jj < JC; ++jj) {
-                if (jc + jj < N) {
-                    const int j = jc + jj;
+            for (int jj = 0; jj < JC; ++jj)
+                if (jc + jj < N) apply_row<N>(acc, g[jj], x[jj], sKT[jc + jj], sAT[jc + jj]);
+        };
+        if constexpr (apply_rolled(N)) {  // rolled over the chunks (N % JC == 0): keeps the loop body inside the instruction cache
+#pragma unroll 1
+            for (int jc = 0; jc < N; jc += JC) row_chunk(jc);
+        } else {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        const float kij = sKT[j][i];
-                        const float aij = sAT[j][i];
-                        acc[i][0] = fma2s(kij, g[jj].lo, acc[i][0]);
-                        acc[i][1] = fma2s(kij, g[jj].hi, acc[i][1]);
-                        acc[i][0] = fma2s(aij, x[jj].lo, acc[i][0]);
-                        acc[i][1] = fma2s(aij, x[jj].hi, acc[i][1]);
-                    }
-                }
-            }
+            for (int jc = 0; jc < N; jc += JC) row_chunk(jc);
         }
         if constexpr (OPT == kOptNone) {
             float* op = out + 4 * q;
@@ -764,27 +803,41 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
 // TC/4 threads and set c works on the tiles it = c (mod TS) of the ring: 2 TS consumer warps, every tile still read
 // from shared memory exactly once, every thread still owns all n rows of its quad (the shared-state optimizer
 // steps of the fused form stay thread-local).
-__host__ __device__ constexpr int apply_tile_cols(int n) { return n <= 12 ? 512 : 256; }
-__host__ __device__ constexpr int apply_default_tile_sets(int n) { return n <= 12 ? 1 : 4; }
-__host__ __device__ constexpr int apply_stage_bytes(int n, int opt = 0) {
-    return (2 * n + opt_state_rows(opt)) * apply_tile_cols(n) * 4;
+// Training-step form (NEXT): the pair distances of the updated particles make the consumer FP32-latency-bound with
+// one warp per scheduler (4 warps on a 512-column tile), so it runs 3 tile sets on 256-column tiles instead
+// (6 consumer warps + producer = 7 warps: still two warps per sub-partition at most, i.e. the 255-register budget
+// that its n(n-1)/2 extra accumulators need).  n > 12: 3 sets for the same reason — with 4 sets (9 warps) one
+// sub-partition holds three warps and the kernel is capped at 168 registers.
+// Measured on B200 (profiles/r01_tilesets_n16_n20.jsonl): n = 16 is fastest fully unrolled on 3 sets, n = 20 rolled
+// (see apply_row) on 4 sets.  n <= 12: 3 x 256 wins for plain K2 at n >= 8 (+3..5 %) and for the training-step form
+// at n >= 9, where a stage is large enough that the 8-stage ring still keeps ~150 KB in flight; the fused K2f forms
+// and small n stay on 1 x 512 (at n = 5 it is 10-25 % faster).
+__host__ __device__ constexpr bool apply_small_tiles(int n, int opt, bool next) {
+    return n > 12 || (next && n >= 9) || (opt == kOptNone && n >= 8);
+}
+__host__ __device__ constexpr int apply_tile_cols(int n, int opt, bool next) { return apply_small_tiles(n, opt, next) ? 256 : 512; }
+__host__ __device__ constexpr int apply_default_tile_sets(int n, int opt, bool next) {
+    return !apply_small_tiles(n, opt, next) ? 1 : (apply_rolled(n) ? 4 : 3);
+}
+__host__ __device__ constexpr int apply_stage_bytes(int n, int opt, int tc) {
+    return (2 * n + opt_state_rows(opt)) * tc * 4;
 }
 __host__ __device__ constexpr int apply_smem_budget(int n) { return (n <= 12 ? 200 : 212) * 1024; }
-__host__ __device__ constexpr int apply_stages(int n, int opt = 0) {
-    return apply_smem_budget(n) / apply_stage_bytes(n, opt) > 8 ? 8 : apply_smem_budget(n) / apply_stage_bytes(n, opt);
+__host__ __device__ constexpr int apply_stages(int n, int opt, int tc) {
+    return apply_smem_budget(n) / apply_stage_bytes(n, opt, tc) > 8 ? 8 : apply_smem_budget(n) / apply_stage_bytes(n, opt, tc);
 }
 
-template <int N, int OPT, bool NEXT = false, int TS = apply_default_tile_sets(N)>
-__global__ void __launch_bounds__(TS * apply_tile_cols(N) / 4 + 32, 1)
+template <int N, int OPT, bool NEXT = false, int TS = apply_default_tile_sets(N, OPT, NEXT), int TC = apply_tile_cols(N, OPT, NEXT)>
+__global__ void __launch_bounds__(TS * TC / 4 + 32, 1)
 svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
                       const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
                       const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
     static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
-    static_assert(!NEXT || TS == 1, "the training-step form flushes its pair sums CTA-uniformly");
     constexpr int PN = NEXT ? pair_count(N) : 1;
     constexpr int NP = (N + 3) & ~3;
-    constexpr int TC = apply_tile_cols(N);
-    constexpr int STAGES = apply_stages(N, OPT);
+    constexpr int STAGES = apply_stages(N, OPT, TC);
+    constexpr bool kApplyRolled = apply_rolled(N);
+    constexpr int kApplyJUnroll = BDE_APPLY_J_UNROLL;
     constexpr int ROWS = 2 * N + opt_state_rows(OPT);
     constexpr int QT = TC / 4;              // threads of one tile set; one column quad each
     constexpr int CONSUMERS = TS * QT;
@@ -873,19 +926,12 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
 #pragma unroll
             for (int i = 0; i < N; ++i) acc[i][0] = acc[i][1] = 0ull;
             if (active) {
+                if constexpr (kApplyRolled) {
+#pragma unroll(kApplyJUnroll)
+                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * TC), lds_v4(sx + j * TC), sKT[j], sAT[j]);
+                } else {
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    const V4 g = lds_v4(sg + j * TC);
-                    const V4 x = lds_v4(sx + j * TC);
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        const float kij = sKT[j][i];
-                        const float aij = sAT[j][i];
-                        acc[i][0] = fma2s(kij, g.lo, acc[i][0]);
-                        acc[i][1] = fma2s(kij, g.hi, acc[i][1]);
-                        acc[i][0] = fma2s(aij, x.lo, acc[i][0]);
-                        acc[i][1] = fma2s(aij, x.hi, acc[i][1]);
-                    }
+                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * TC), lds_v4(sx + j * TC), sKT[j], sAT[j]);
                 }
             }
             if constexpr (OPT == kOptNone) {
@@ -937,7 +983,8 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                 if constexpr (NEXT) {
                     // the K1 of the next step, on the updated particles while they are still in registers
                     pair_accumulate<N, 0>(xn, pacc);
-                    if ((it % kFlushTiles) == kFlushTiles - 1) flush_pairs<PN>(pacc, wacc[tid >> 5], lane);  // `it` is CTA-uniform
+                    // `it` is uniform over the tile set (all of its warps walk the same tiles): warp-level flush
+                    if (((it / TS) % kFlushTiles) == kFlushTiles - 1) flush_pairs<PN>(pacc, wacc[tid >> 5], lane);
                 }
             }
         }
@@ -1012,22 +1059,21 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     return BDE_OK;
 }
 
-template <int N, int OPT, bool NEXT, int TS>
+template <int N, int OPT, bool NEXT, int TS, int TC>
 int launch_apply_tma(const float* X, const float* G, float* out, const float* K, const float* A, int64_t D, int64_t ldx,
                      int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st, const NextDistParams& nd) {
-    constexpr int TC = apply_tile_cols(N);
-    constexpr int smem = apply_stages(N, OPT) * apply_stage_bytes(N, OPT);
-    static_assert(apply_stages(N, OPT) >= 2, "ring too shallow");
+    constexpr int smem = apply_stages(N, OPT, TC) * apply_stage_bytes(N, OPT, TC);
+    static_assert(apply_stages(N, OPT, TC) >= 2, "ring too shallow");
     const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
     static bool configured = false;
     if (!configured) {
-        BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     int64_t grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    svgd_apply_tma_kernel<N, OPT, NEXT, TS><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
+    svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }
@@ -1037,16 +1083,21 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
                      int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st,
                      const NextDistParams& nd = NextDistParams{}) {
     const int64_t nquads = D >> 2;
-    constexpr int TC = apply_tile_cols(N);
-    const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
+    constexpr int TC = apply_tile_cols(N, OPT, NEXT);
+    constexpr int TS0 = apply_default_tile_sets(N, OPT, NEXT);
+    const int64_t d4 = D & ~static_cast<int64_t>(3);
+    const int64_t ntiles = (d4 + TC - 1) / TC;
     int variant = tuning().apply_variant;
     // auto: the staged kernel wins once every SM has a few tiles per tile set
-    if (variant == 0) variant = (ntiles >= 2 * apply_default_tile_sets(N) * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+    if (variant == 0) {
+        variant = (ntiles >= 2 * TS0 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+    }
     if (variant == 2) {
-        if constexpr (N > 12 && !NEXT) {
-            if (tuning().apply_tile_sets == 3) return launch_apply_tma<N, OPT, NEXT, 3>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
-        }
-        return launch_apply_tma<N, OPT, NEXT, apply_default_tile_sets(N)>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
+        // "apply_tile_sets" selects the alternative geometry (A/B runs and the parity tests of both)
+        constexpr int TS_ALT = !apply_small_tiles(N, OPT, NEXT) ? 3 : (N > 12 ? 7 - TS0 : 1);
+        constexpr int TC_ALT = N > 12 ? 256 : 768 - TC;
+        if (tuning().apply_tile_sets == TS_ALT) return launch_apply_tma<N, OPT, NEXT, TS_ALT, TC_ALT>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
+        return launch_apply_tma<N, OPT, NEXT, TS0, TC>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
     }
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {

@@ -432,7 +432,8 @@ def test_train_step_next_distances(ops, cuda_lib, variant, opt, n, D, ld, mis):
             np.testing.assert_allclose(scb.dist.cpu().numpy(), d_ref.numpy(), rtol=2e-6, atol=1e-12)
             np.testing.assert_allclose(scc.dist.cpu().numpy(), scb.dist.cpu().numpy(), rtol=1e-12, atol=1e-15)
             ops.svgd_pairdist_bandwidth(dXb, scr, 0.01, 1.0, 768.0)
-            np.testing.assert_allclose(scb.dist.cpu().numpy(), scr.dist.cpu().numpy(), rtol=1e-9, atol=1e-12)
+            # (two different groupings of the fp32 partial sums: both are ~1e-9 from the fp64 oracle at large D)
+            np.testing.assert_allclose(scb.dist.cpu().numpy(), scr.dist.cpu().numpy(), rtol=5e-8, atol=1e-12)
             # (3) K1b of the next step ran in the tail: same selection, same coefficients
             bw = O.svgd_bandwidth(d_ref, 0.01, 1.0, 768.0)
             assert tuple(scb.sel.cpu().tolist()) == bw["sel"]
@@ -447,6 +448,58 @@ def test_train_step_next_distances(ops, cuda_lib, variant, opt, n, D, ld, mis):
             scc.A.copy_(scb.A)
     finally:
         cuda_lib.bde_tune(b"apply_variant", 0)
+
+
+@pytest.mark.parametrize("opt", ["sgd-cifar", "adam"])
+@pytest.mark.parametrize("n,D", [(10, 2_000_003), (4, 1_500_001), (7, 40_000), (5, 900_001)])
+def test_train_step_tile_geometries(ops, cuda_lib, opt, n, D):
+    """Staged training-step kernel: 1 tile set x 512 columns and 3 sets x 256 columns (one is the default, by n) walk the ring
+    differently (per-set flush counters, stage hand-over between sets) but must update the particles bit for
+    bit alike and leave the same next-step distances; D wraps the ring many times per set, D % 4 != 0."""
+    kind, hyper = OPT_KINDS[opt]
+    X, G = particles(n, D, seed=n * 13 + D)
+    X *= 4.0
+    G *= 50.0
+    ld = (D + 3) // 4 * 4
+    sc0 = ops.SvgdScratch.allocate(n, "cuda")
+    ops.svgd_pairdist_bandwidth(dev_matrix(X, ld), sc0, 0.01, 1.0, 768.0)
+    runs = []
+    for sets in (1, 3):
+        dX, dG = dev_matrix(X, ld), dev_matrix(G, ld)
+        sc = ops.SvgdScratch.allocate(n, "cuda")
+        sc.K.copy_(sc0.K)
+        sc.A.copy_(sc0.A)
+        s0, s1, out_last = (torch.zeros(D, device="cuda") for _ in range(3))
+        cuda_lib.bde_tune(b"apply_variant", 2)
+        cuda_lib.bde_tune(b"apply_tile_sets", sets)
+        try:
+            for step in range(2):
+                nk = ops.NextKernel(True, 0.01, 1.0, 768.0)
+                if kind == "sgd":
+                    ops.svgd_apply_sgd(dX, dG, sc, s0, buf_initialized=step > 0, out_last=out_last, next_kernel=nk, **hyper)
+                else:
+                    ops.svgd_apply_adam(dX, dG, sc, s0, s1, step0=step * n, lr=hyper["lr"], beta1=hyper["betas"][0],
+                                        beta2=hyper["betas"][1], eps=hyper["eps"], weight_decay=hyper["weight_decay"],
+                                        decoupled_weight_decay=False, out_last=out_last, next_kernel=nk)
+                if step == 0:
+                    first = (dX.cpu(), s0.cpu(), s1.cpu(), out_last.cpu())
+        finally:
+            cuda_lib.bde_tune(b"apply_variant", 0)
+            cuda_lib.bde_tune(b"apply_tile_sets", 0)
+        runs.append((first, dX.cpu(), s0.cpu(), s1.cpu(), out_last.cpu(), sc.dist.cpu(), sc.sel.cpu(), sc.K.cpu(), sc.A.cpu()))
+    # step 1 (same K / A): bit for bit; step 2 runs on each geometry's own K / A, whose fp32 partial sums are
+    # grouped differently (~1e-9 apart), so the particles agree to rounding only
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert torch.equal(a, b)
+    for a, b in zip(runs[0][1:5], runs[1][1:5]):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=RTOL, atol=ATOL)
+    for r in runs:
+        d_ref = O.svgd_pairdist(r[1][:, :D])
+        np.testing.assert_allclose(r[5].numpy(), d_ref.numpy(), rtol=2e-6, atol=1e-12)
+        bw = O.svgd_bandwidth(d_ref, 0.01, 1.0, 768.0)
+        assert tuple(r[6].tolist()) == bw["sel"]
+        np.testing.assert_allclose(r[7].numpy(), bw["K"].numpy(), rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(r[8].numpy(), bw["A"].numpy(), rtol=1e-5, atol=1e-9)
 
 
 def test_train_step_full_size(ops):
