@@ -551,14 +551,14 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "bde::svgd_apply_tma_kernel<10> (K2: out = K G + A X)",
+            "roofline": {"bound": "hbm", "kernel": "bde::svgd_apply_tma_kernel<10, 0, false, 3, 256> (K2: out = K G + A X; 3 tile sets x 256 columns)",
                          "achieved": k2_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": k2_gbs / peak_gbs,
                          "peak_source": peak_src, "frac_of_nominal_8TBps": k2_gbs / 8000.0,
                          "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                         # at n=10, D=1e8 (profiles/r01_ncu_summary.md): 8.001 GB + 3.969 GB per launch
-                         "traffic": 11.970e9 * (D / 1e8) if n == 10 else None,
-                         "traffic_source": "profiles/r01_ncu_summary.md (prof_apply_tma.ncu-rep)"},
+                         # at n=10, D=1e8 (profiles/r01_ncu_summary.md): 8.001 GB + 3.968 GB per launch
+                         "traffic": 11.969e9 * (D / 1e8) if n == 10 else None,
+                         "traffic_source": "profiles/r01_ncu_summary.md (prof_n10_all.ncu-rep, session 29)"},
             "kernels": {
                 "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
                                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,

@@ -566,17 +566,24 @@ __device__ __forceinline__ float adam_update1(const BaseOptParams& o, int i, flo
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(denom));
     return fmaf(-o.step_size[i] * m, r, x);                                 // param.addcdiv_(m, denom, -step_size)
 }
+// two columns at once: the same operations as adam_update1, lane for lane, on the packed pipe (FADD2 / FMUL2 /
+// FFMA2 are IEEE per lane, so the results are bit-identical to the scalar form); only sqrt and rcp stay scalar (SFU)
 __device__ __forceinline__ void adam_update2(const BaseOptParams& o, int i, f32x2 g, f32x2& x, f32x2& m, f32x2& v) {
-    float g0, g1, x0, x1, m0, m1, v0, v1;
-    unpack2(g, g0, g1);
-    unpack2(x, x0, x1);
-    unpack2(m, m0, m1);
+    if (o.weight_decay != 0.0f) {
+        if (o.decoupled_wd)
+            x = mul2s(o.decay_factor, x);
+        else
+            g = fma2s(o.weight_decay, x, g);
+    }
+    m = fma2s(o.one_minus_beta1, sub2(g, m), m);
+    v = fma2(mul2s(o.one_minus_beta2, g), g, mul2s(o.beta2, v));
+    float v0, v1, r0, r1;
     unpack2(v, v0, v1);
-    x0 = adam_update1(o, i, g0, x0, m0, v0);
-    x1 = adam_update1(o, i, g1, x1, m1, v1);
-    x = pack2(x0, x1);
-    m = pack2(m0, m1);
-    v = pack2(v0, v1);
+    const f32x2 denom = fma2s(o.inv_bc2_sqrt[i], pack2(sqrt_approx(v0), sqrt_approx(v1)), pack2(o.eps, o.eps));
+    unpack2(denom, v0, v1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(v0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(v1));
+    x = fma2(mul2s(-o.step_size[i], m), pack2(r0, r1), x);
 }
 
 // one particle's optimizer step on a column quad; s0 / s1 are the shared state quads

@@ -109,6 +109,81 @@ swag_sample_kernel(const float* __restrict__ mean, const float* __restrict__ sq,
     }
 }
 
+// K4 batched: S draws from the SAME posterior in one pass — mean, sq and the K deviation rows
+// are read once and S weight vectors are written, 4(K+2)D + 4 S D bytes instead of S * 4(K+3)D.  Draw s is
+// bit-identical to bde_swag_sample with stream_id + s: the same fmaf chain over k, the same Philox counters.
+constexpr int kSwagBatchMax = 16;   // draws per launch (4 accumulator registers each)
+
+template <bool VEC, int SB>
+__global__ void __launch_bounds__(kEwThreads)
+swag_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
+                         int head, int64_t D, int64_t ld, int S, const float* __restrict__ eps_k,
+                         const float* __restrict__ eps_d, int64_t ld_eps, uint64_t seed, uint64_t stream_id, int64_t quad0,
+                         float inv_norm_den, float* __restrict__ theta, int64_t ld_out) {
+    // zc[k][s] = z_s[k] / sqrt(2(K-1)) for the logical column k of draw s (0 for the unused slots s >= S)
+    __shared__ __align__(16) float zc[kMaxSwagRank][SB];
+    __shared__ int64_t rowoff[kMaxSwagRank];
+    for (int e = threadIdx.x; e < K * SB; e += blockDim.x) {
+        const int k = e / SB, sidx = e - k * SB;
+        float z = 0.0f;
+        if (sidx < S) {
+            if (eps_k) {
+                z = eps_k[static_cast<int64_t>(sidx) * K + k];
+            } else {
+                const float4 z4 = philox_normal4(seed, (stream_id + sidx) ^ 0x5741ull, static_cast<uint64_t>(k >> 2));
+                z = (k & 3) == 0 ? z4.x : (k & 3) == 1 ? z4.y : (k & 3) == 2 ? z4.z : z4.w;
+            }
+            z = __fdiv_rn(z, inv_norm_den);
+        }
+        zc[k][sidx] = z;
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) rowoff[k] = static_cast<int64_t>((head + k) % K) * ld;
+    __syncthreads();
+
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 m = load_quad<VEC, true>(mean, b, D);
+        const float4 sv = load_quad<VEC, true>(sq, b, D);
+        float4 low[SB];
+#pragma unroll
+        for (int sidx = 0; sidx < SB; ++sidx) low[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+        for (int k = 0; k < K; ++k) {
+            const float4 d = load_quad<VEC, true>(dev + rowoff[k], b, D);
+#pragma unroll
+            for (int sidx = 0; sidx < SB; ++sidx) {
+                const float z = zc[k][sidx];
+                low[sidx].x = fmaf(d.x, z, low[sidx].x);
+                low[sidx].y = fmaf(d.y, z, low[sidx].y);
+                low[sidx].z = fmaf(d.z, z, low[sidx].z);
+                low[sidx].w = fmaf(d.w, z, low[sidx].w);
+            }
+        }
+        // diag = 0.5 * (relu(sq - mean**2) + 1e-6), shared by all draws (swag.py:112)
+        auto sdev = [&](float mv, float s2) {
+            float v = __fsub_rn(s2, __fmul_rn(mv, mv));
+            v = fmaxf(v, 0.0f);
+            return __fsqrt_rn(__fmul_rn(0.5f, __fadd_rn(v, 1e-6f)));
+        };
+        const float4 sd = BDE_LANES(sdev(m.x, sv.x), sdev(m.y, sv.y), sdev(m.z, sv.z), sdev(m.w, sv.w));
+#pragma unroll
+        for (int sidx = 0; sidx < SB; ++sidx) {
+            if (sidx < S) {
+                float4 e;
+                if (eps_d) {
+                    e = load_quad<VEC, true>(eps_d + sidx * ld_eps, b, D);
+                } else {
+                    e = philox_normal4(seed, stream_id + sidx, static_cast<uint64_t>(quad0 + q));
+                }
+                auto fin = [&](float mv, float lv, float dv, float ev) { return __fadd_rn(__fadd_rn(mv, lv), __fmul_rn(dv, ev)); };
+                const float4 o = BDE_LANES(fin(m.x, low[sidx].x, sd.x, e.x), fin(m.y, low[sidx].y, sd.y, e.y),
+                                           fin(m.z, low[sidx].z, sd.z, e.z), fin(m.w, low[sidx].w, sd.w, e.w));
+                store_quad<VEC>(theta + sidx * ld_out, b, D, o);
+            }
+        }
+    }
+}
+
 }  // namespace bde
 
 using namespace bde;
@@ -157,4 +232,51 @@ extern "C" int bde_swag_sample(const float* mean, const float* sq, const float* 
         rc_ = launch_ew(swag_sample_kernel<false, 5>, D, st, mean, sq, dev, K, head, D, ld, eps_k, eps_d, seed,
                                                                      stream_id, elem0 >> 2, den, theta);
     return rc_;
+}
+
+template <bool VEC>
+static int launch_swag_batch(int sb, int64_t D, cudaStream_t st, const float* mean, const float* sq, const float* dev, int K,
+                             int head, int64_t ld, int S, const float* eps_k, const float* eps_d, int64_t ld_eps,
+                             uint64_t seed, uint64_t stream_id, int64_t quad0, float den, float* theta, int64_t ld_out) {
+    switch (sb) {
+        case 2:
+            return launch_ew(swag_sample_batch_kernel<VEC, 2>, D, st, mean, sq, dev, K, head, D, ld, S, eps_k, eps_d, ld_eps, seed,
+                             stream_id, quad0, den, theta, ld_out);
+        case 4:
+            return launch_ew(swag_sample_batch_kernel<VEC, 4>, D, st, mean, sq, dev, K, head, D, ld, S, eps_k, eps_d, ld_eps, seed,
+                             stream_id, quad0, den, theta, ld_out);
+        case 8:
+            return launch_ew(swag_sample_batch_kernel<VEC, 8>, D, st, mean, sq, dev, K, head, D, ld, S, eps_k, eps_d, ld_eps, seed,
+                             stream_id, quad0, den, theta, ld_out);
+        default:
+            return launch_ew(swag_sample_batch_kernel<VEC, 16>, D, st, mean, sq, dev, K, head, D, ld, S, eps_k, eps_d, ld_eps, seed,
+                             stream_id, quad0, den, theta, ld_out);
+    }
+}
+
+extern "C" int bde_swag_sample_batch(const float* mean, const float* sq, const float* dev, int K, int head, int64_t D,
+                                     int64_t ld, int S, const float* eps_k, const float* eps_d, int64_t ld_eps,
+                                     uint64_t seed, uint64_t stream_id, int64_t elem0, float* theta, int64_t ld_out,
+                                     bde_stream_t stream) {
+    if (!mean || !sq || !dev || !theta || K < 1 || K > kMaxSwagRank || head < 0 || head >= K || D < 0 || ld < D || S < 0 ||
+        ld_out < D || (eps_d && ld_eps < D) || elem0 < 0 || (elem0 & 3))
+        return BDE_ERR_INVALID_ARG;
+    if (D == 0 || S == 0) return BDE_OK;
+    const bool vec = aligned16(mean) && aligned16(sq) && aligned16(dev) && aligned16(theta) && (ld % 4 == 0) &&
+                     (ld_out % 4 == 0) && (!eps_d || (aligned16(eps_d) && ld_eps % 4 == 0));
+    const float den = static_cast<float>(sqrt(2.0 * (K - 1)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int s0 = 0; s0 < S; s0 += kSwagBatchMax) {   // 16 draws per pass over the moments
+        const int c = S - s0 < kSwagBatchMax ? S - s0 : kSwagBatchMax;
+        const int sb = c <= 2 ? 2 : (c <= 4 ? 4 : (c <= 8 ? 8 : 16));
+        const float* ek = eps_k ? eps_k + static_cast<int64_t>(s0) * K : nullptr;
+        const float* ed = eps_d ? eps_d + s0 * ld_eps : nullptr;
+        float* out = theta + s0 * ld_out;
+        const int rc_ = vec ? launch_swag_batch<true>(sb, D, st, mean, sq, dev, K, head, ld, c, ek, ed, ld_eps, seed,
+                                                      stream_id + s0, elem0 >> 2, den, out, ld_out)
+                            : launch_swag_batch<false>(sb, D, st, mean, sq, dev, K, head, ld, c, ek, ed, ld_eps, seed,
+                                                       stream_id + s0, elem0 >> 2, den, out, ld_out);
+        if (rc_ != BDE_OK) return rc_;
+    }
+    return BDE_OK;
 }

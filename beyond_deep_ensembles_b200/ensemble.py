@@ -52,6 +52,10 @@ class DeepEnsemble(nn.Module):
 
         drawn = []
         for (model, optimizer), count in zip(self.models_and_optimizers, split_samples(samples, len(self.models))):
+            # optimizers that can draw a batch of posterior samples in one pass are told how many will follow
+            announce = getattr(optimizer, "presample", None)
+            if announce is not None:
+                announce(count)
             for _ in range(count):
                 optimizer.sample_parameters()
                 drawn.append(predict_closure(model))

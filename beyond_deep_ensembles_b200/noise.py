@@ -39,6 +39,14 @@ def next_stream_id() -> int:
     return _next_stream
 
 
+def reserve_stream_ids(count: int) -> int:
+    """`count` consecutive stream ids (what `count` calls of next_stream_id() would return); returns the first."""
+    global _next_stream
+    first = _next_stream + 1
+    _next_stream += int(count)
+    return first
+
+
 def draw(kind: str, numel: int, device) -> Optional[torch.Tensor]:
     """Injected noise for this draw, or None to let the kernel use Philox."""
     if _injector is None:

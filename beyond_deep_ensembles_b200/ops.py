@@ -224,6 +224,27 @@ def swag_sample(mean, sq, dev, head: int, theta, *, eps_k=None, eps_d=None, seed
               _lib.ptr(eps_d), int(seed), int(stream_id), int(elem0), theta.data_ptr(), _s(mean))
 
 
+def swag_sample_batch(mean, sq, dev, head: int, theta, *, eps_k=None, eps_d=None, seed: int = 0, stream_id: int = 0,
+                      elem0: int = 0) -> None:
+    """K4 batched: theta [S, ld_out] receives S draws in one pass over the moments; draw s is what swag_sample
+    returns for stream_id + s.  eps_k: [S, K], eps_d: [S, D] (row stride free) or None for Philox."""
+    require_cuda(mean, sq, dev, theta, eps_k, eps_d)
+    _lib.require_f32(mean, sq, dev, theta, eps_k, eps_d)
+    D = _vec(mean).numel()
+    K, Dd, ld = _rows(dev)
+    S, Do, ld_out = _rows(theta)
+    assert Dd == D and Do == D and _vec(sq).numel() == D
+    ld_eps = 0
+    if eps_k is not None:
+        assert eps_k.is_contiguous() and tuple(eps_k.shape) == (S, K)
+    if eps_d is not None:
+        Se, De, ld_eps = _rows(eps_d)
+        assert (Se, De) == (S, D)
+    _lib.call("bde_swag_sample_batch", mean.data_ptr(), sq.data_ptr(), dev.data_ptr(), K, int(head), D, ld, S,
+              _lib.ptr(eps_k), _lib.ptr(eps_d), ld_eps, int(seed), int(stream_id), int(elem0), theta.data_ptr(), ld_out,
+              _s(mean))
+
+
 # --------------------------------------------------------------------------------------
 # iVON
 # --------------------------------------------------------------------------------------

@@ -41,6 +41,12 @@ class SwagOptimizer(BayesianOptimizer):
         self._dev = L.new_arena(deviation_samples, device)
         self._tviews = L.views(self._theta)
         self._sviews = L.views(self._sample)
+        # presample(): rows drawn ahead of time, handed out by the following sample_parameters() calls
+        self._pre_buf = None      # [rows, size]
+        self._pre_views = []      # per-row parameter views
+        self._pre_next = 0        # next row of _pre_buf to hand out
+        self._pre_ready = 0       # rows of _pre_buf that hold undelivered draws
+        self._pre_pending = 0     # draws promised by presample() but not generated yet
 
         with torch.no_grad():
             for param, tview in zip(plist, self._tviews):
@@ -59,6 +65,7 @@ class SwagOptimizer(BayesianOptimizer):
 
     # ------------------------------------------------------------------ step
     def step(self, forward_closure, backward_closure, grad_scaler=None):
+        self._drop_presampled()   # the posterior is about to change
         self._restore_original_params()
         base = self.state["__base_optimizer"]
         base.zero_grad()
@@ -75,9 +82,19 @@ class SwagOptimizer(BayesianOptimizer):
         return loss
 
     def sample_parameters(self):
-        """theta~ = mean + Dev z / sqrt(2(K-1)) + sqrt(diag) eps (swag.py:53-58, 107-114), one launch."""
+        """theta~ = mean + Dev z / sqrt(2(K-1)) + sqrt(diag) eps (swag.py:53-58, 107-114), one launch —
+        or the next row of a presample() batch."""
         self._save_original_params()
         self.state["__params_dirty"] = True
+        if self._pre_ready == 0 and self._pre_pending > 0:
+            self._draw_batch()
+        if self._pre_ready > 0:
+            views = self._pre_views[self._pre_next]
+            self._pre_next += 1
+            self._pre_ready -= 1
+            for param, view in zip(self._params(), views):
+                param.data = view
+            return
         K, dev_ = self.deviation_samples, self._theta.device
         eps_k = noise.draw("swag_k", K, dev_)
         eps_d = noise.draw("swag_d", self._layout.logical_size, dev_)
@@ -87,6 +104,43 @@ class SwagOptimizer(BayesianOptimizer):
                         eps_d=eps_d, seed=noise.seed(), stream_id=noise.next_stream_id())
         for param, sview in zip(self._params(), self._sviews):
             param.data = sview
+
+    # ---- batched sampling ----
+    #: upper bound of the presample buffer in bytes; larger requests are drawn in several batches
+    presample_max_bytes = 4 << 30
+
+    def presample(self, count: int):
+        """Announce that the next `count` sample_parameters() calls draw from the CURRENT posterior (what
+        DeepEnsemble.predict does, ensemble.py:37-43): they are generated by one K4-batched launch per 16 draws,
+        reading the moments and the deviation matrix once instead of once per draw.  Every draw is bit-identical
+        to the one sample_parameters() would have produced on its own (same Philox streams, same injected-noise
+        order); each handed-out sample lives in its own row, so earlier samples stay valid until step()."""
+        self._drop_presampled()
+        self._pre_pending = max(int(count), 0) if count and count > 1 else 0
+
+    def _drop_presampled(self):
+        self._pre_ready = self._pre_pending = self._pre_next = 0
+
+    def _draw_batch(self):
+        L, K, dev_ = self._layout, self.deviation_samples, self._theta.device
+        size = self._theta.numel()
+        rows = int(min(self._pre_pending, max(1, self.presample_max_bytes // (4 * size))))
+        if self._pre_buf is None or self._pre_buf.shape[0] < rows:
+            self._pre_buf = L.new_arena(rows, dev_)
+            self._pre_views = [L.views(self._pre_buf[r]) for r in range(rows)]
+        # injected noise is consumed in the order of `rows` sequential calls: (swag_k, swag_d) per draw
+        eps_k, eps_d = [], []
+        for _ in range(rows):
+            eps_k.append(noise.draw("swag_k", K, dev_))
+            eps_d.append(noise.draw("swag_d", L.logical_size, dev_))
+        ek = torch.stack(eps_k) if all(e is not None for e in eps_k) else None
+        ed = torch.stack([L.from_logical(e) for e in eps_d]) if all(e is not None for e in eps_d) else None
+        if (ek is None and any(e is not None for e in eps_k)) or (ed is None and any(e is not None for e in eps_d)):
+            raise ValueError("a noise injector must supply either every draw of a presampled batch or none")
+        ops.swag_sample_batch(self._mean, self._sq, self._dev, self.state["__updates"] % K, self._pre_buf[:rows],
+                              eps_k=ek, eps_d=ed, seed=noise.seed(), stream_id=noise.reserve_stream_ids(rows))
+        self._pre_next, self._pre_ready = 0, rows
+        self._pre_pending -= rows
 
     def complete_epoch(self):
         self.state["__epoch"] += 1
@@ -148,6 +202,7 @@ class SwagOptimizer(BayesianOptimizer):
 
     def load_state_dict(self, state_dict: dict):
         super().load_state_dict(state_dict)
+        self._drop_presampled()
         L, dev_ = self._layout, self._theta.device
         mean = self.state.pop("__mean").to(dev_).float()
         sq = self.state.pop("__sq_weights").to(dev_).float()

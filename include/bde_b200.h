@@ -216,6 +216,18 @@ int bde_swag_sample(const float* mean, const float* sq, const float* dev, int K,
                     uint64_t seed, uint64_t stream_id, int64_t elem0, float* theta,
                     bde_stream_t stream);
 
+/*
+ * K4 batched: S draws from the same posterior in one pass (what
+ * DeepEnsemble.predict, ensemble.py:37-43, asks for with `samples // members` consecutive
+ * sample_parameters() calls).  theta: [S, ld_out]; draw s equals bde_swag_sample with
+ * stream_id + s bit for bit.  eps_k: [S, K] or NULL; eps_d: [S, ld_eps] or NULL.
+ * Reads mean, sq and the K deviation rows once per 16 draws.
+ */
+int bde_swag_sample_batch(const float* mean, const float* sq, const float* dev, int K, int head,
+                          int64_t D, int64_t ld, int S, const float* eps_k, const float* eps_d,
+                          int64_t ld_eps, uint64_t seed, uint64_t stream_id, int64_t elem0,
+                          float* theta, int64_t ld_out, bde_stream_t stream);
+
 /* ---- iVON (reference: src/algos/ivorn.py) --------------------------------- */
 
 /*

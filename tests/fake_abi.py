@@ -197,6 +197,15 @@ class FakeLib:
         _f32(theta, D).copy_(O.swag_sample(_f32(mean, D), _f32(sq, D), dev_DK, ek, ed))
         return 0
 
+    def bde_swag_sample_batch(self, mean, sq, dev, K, head, D, ld, S, eps_k, eps_d, ld_eps, seed, sid, elem0, theta, ld_out,
+                              stream):
+        self.calls.append("swag_sample_batch")
+        for s in range(S):
+            self.bde_swag_sample(mean, sq, dev, K, head, D, ld, eps_k + 4 * s * K if eps_k else 0,
+                                 eps_d + 4 * s * ld_eps if eps_d else 0, seed, sid + s, elem0, theta + 4 * s * ld_out, stream)
+            self.calls.pop()
+        return 0
+
     def bde_ivon_sample(self, mean, prec, delta_sum, theta, D, n_eff, first, deterministic, eps, seed, sid, elem0, stream):
         self.calls.append("ivon_sample")
         e = _f32(eps, D) if eps else torch.from_numpy(O.philox_normal(D, seed, sid, elem0))

@@ -628,6 +628,38 @@ def test_swag_update_and_sample_vs_oracle(ops, ew_variant, D, K):
         assert (~torch.isfinite(theta_out.cpu()) == ~torch.isfinite(ref)).all()
 
 
+@pytest.mark.parametrize("S", [1, 2, 3, 5, 16, 17, 35])
+@pytest.mark.parametrize("D,K,mis", [(100_003, 10, 0), (4099, 30, 0), (777, 3, 1), (1_000_000, 5, 0)])
+def test_swag_sample_batch_equals_single_draws(ops, S, D, K, mis):
+    """bde_swag_sample_batch: draw s == bde_swag_sample with stream_id + s, bit for bit, with Philox noise
+    and with injected noise; ragged D, unaligned views, more draws than one launch holds (16), ring head != 0."""
+    if S > 5 and D > 200_000:
+        pytest.skip("large case covered at small S")
+    g = torch.Generator().manual_seed(S * 7 + D)
+    size = D + 8
+    def vec():
+        return torch.randn(size, generator=g).cuda()[mis:mis + D]
+    mean = vec()
+    sq = (mean ** 2 + 0.01 * torch.rand(D, generator=g).cuda()).contiguous() if mis == 0 else \
+        (torch.zeros(size, device="cuda")[mis:mis + D].copy_(mean ** 2 + 0.01))
+    ld = (D + 7) // 4 * 4 + (1 if mis else 0)
+    dev = torch.as_strided(torch.randn(K * ld + 8, generator=g).cuda() * 0.1, (K, D), (ld, 1), storage_offset=mis)
+    head = 2 % K
+    ld_out = D + (3 if mis else 0)
+    for injected in (False, True):
+        ek = torch.randn(S, K, generator=g).cuda() if injected else None
+        ed = torch.randn(S, D, generator=g).cuda() if injected else None
+        out = torch.as_strided(torch.full((S * ld_out + 8,), float("nan"), device="cuda"), (S, D), (ld_out, 1), storage_offset=mis)
+        ops.swag_sample_batch(mean, sq, dev, head, out, eps_k=ek, eps_d=ed, seed=99, stream_id=5)
+        one = torch.zeros(size, device="cuda")[mis:mis + D]
+        for s_ in range(S):
+            ops.swag_sample(mean, sq, dev, head, one, eps_k=None if ek is None else ek[s_], eps_d=None if ed is None else ed[s_],
+                            seed=99, stream_id=5 + s_)
+            assert torch.equal(out[s_], one), (s_, injected)
+        if S > 1:
+            assert not torch.equal(out[0], out[1])
+
+
 def test_swag_sample_matches_reference_fixture(ops, golden):
     g = golden("swag_steps.npz")
     D, K = g["deviations"].shape

@@ -397,6 +397,98 @@ def test_swag_sample_from_reference_moments(env, golden):
             np.testing.assert_allclose(flat(model.parameters()), g["samples"][k], rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("count,max_rows", [(2, 99), (5, 99), (5, 2)])
+def test_swag_presample_equals_sequential_draws(env, golden, count, max_rows):
+    """presample(count) hands out exactly the draws that `count` single sample_parameters()
+    calls produce — with injected noise (the reference's draw order) and with Philox streams — also when the
+    buffer cap splits the request into several batches, and the batch is dropped by step()."""
+    g = golden("swag_steps.npz")
+
+    def loaded():
+        model, opt = build_swag(env, g)
+        sd = opt.state_dict()
+        sd["state"]["__mean"] = torch.from_numpy(g["mean"])
+        sd["state"]["__sq_weights"] = torch.from_numpy(g["sq"])
+        sd["state"]["__deviations"] = torch.from_numpy(g["deviations"])
+        sd["state"]["__updates"] = int(g["updates"])
+        opt.load_state_dict(sd)
+        return model, opt
+
+    K, D = g["deviations"].shape[1], g["mean"].shape[0]
+    gen = torch.Generator().manual_seed(3)
+    zs = [torch.randn(K if i % 2 == 0 else D, generator=gen) for i in range(2 * count)]
+
+    def draws(batched, injected):
+        model, opt = loaded()
+        if batched:
+            opt.presample_max_bytes = 4 * opt._theta.numel() * max_rows
+            opt.presample(count)
+        noise.set_seed(1234)
+        it = iter(zs)
+        ctx = noise.inject(lambda kind, numel: next(it)) if injected else noise.inject(lambda kind, numel: None)
+        out = []
+        with ctx:
+            for _ in range(count):
+                opt.sample_parameters()
+                out.append(flat(model.parameters()).copy())
+        noise.set_seed(None)
+        return out, model, opt
+
+    for injected in (True, False):
+        single, _, _ = draws(False, injected)
+        batch, model, opt = draws(True, injected)
+        for a, b in zip(single, batch):
+            np.testing.assert_array_equal(a, b)
+        assert any(not np.array_equal(single[0], s) for s in single[1:])
+        if env.fake:
+            assert env.calls("swag_sample_batch") >= 1
+    # the first two draws of the injected run are the reference's own samples for that noise
+    with noise.inject(tape(g["eps"], g["eps_sizes"])):
+        model, opt = loaded()
+        opt.presample(2)
+        for k in range(2):
+            opt.sample_parameters()
+            np.testing.assert_allclose(flat(model.parameters()), g["samples"][k], rtol=RTOL, atol=ATOL)
+    # a training step drops what is left of the batch and restores the training weights
+    opt.presample(3)
+    opt.sample_parameters()
+    fwd, bwd = gm.mse_closures(model, env.t(g["xs"][0]), env.t(g["ys"][0]))
+    opt.step(fwd, bwd)
+    assert opt._pre_ready == 0 and opt._pre_pending == 0 and not opt.state["__params_dirty"]
+
+
+def test_deep_ensemble_announces_batches_to_swag_members(env, golden):
+    """DeepEnsemble.predict tells members that can presample how many draws follow; predictions equal the
+    one-by-one path."""
+    g = golden("swag_steps.npz")
+    x = env.t(g["xs"][0])
+
+    def ensemble():
+        pairs = []
+        for m in range(2):
+            model, opt = build_swag(env, g)
+            for s in range(4):   # a few updates so that the deviation ring is populated
+                if s == 1:
+                    opt.complete_epoch()
+                fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+                opt.step(fwd, bwd)
+            pairs.append((model, opt))
+        return bde.DeepEnsemble(pairs)
+
+    preds = []
+    for batched in (True, False):
+        ens = ensemble()
+        if not batched:
+            for opt in ens.optimizers:
+                opt.presample = lambda count: None
+        noise.set_seed(77)
+        with torch.no_grad():
+            preds.append(ens.predict(lambda mdl: mdl(x).squeeze(-1), samples=7).cpu().numpy())
+        noise.set_seed(None)
+    np.testing.assert_array_equal(preds[0], preds[1])
+    assert preds[0].shape[0] == 7
+
+
 def test_swag_loads_reference_layout_checkpoint(env, golden):
     g = golden("swag_steps.npz")
     model, opt = build_swag(env, g)
