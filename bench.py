@@ -221,7 +221,15 @@ def other_paths(ops, peak_gbs, dev):
     rec("swag_update", time_kernel(swag_upd, 20, 3), 24 * Dp, f"ResNet-50 D={D}, K={K}")
     rec("swag_sample", time_kernel(lambda: ops.swag_sample(mean, sq, ring, 3, out, seed=1, stream_id=2), 20, 3),
         4 * (K + 3) * Dp, f"ResNet-50 D={D}, K={K}, Philox noise")
-    del theta, mean, sq, ring, out
+    # f3: 16 draws from the same posterior in one pass (DeepEnsemble.predict) vs 16 single launches
+    S = 16
+    outs = torch.empty(S, Dp, device=dev)
+    # (A/B on B200 of the draws per pass, bde_tune("swag_batch"): 16 -> 0.995 ms, 8 -> 1.034 ms, 4 -> 1.234 ms)
+    ms_b = time_kernel(lambda: ops.swag_sample_batch(mean, sq, ring, 3, outs, seed=1, stream_id=2), 10, 3)
+    rec("swag_sample_batch16", ms_b, 4 * (K + 2 + S) * Dp,
+        f"ResNet-50 D={D}, K={K}, {S} draws in one pass (reads the moments once; bound by the {S} x D Philox normals, "
+        f"not by HBM); {S} single launches move {4 * (K + 3) * S} x D bytes and take {S * res['swag_sample']['ms']:.3f} ms")
+    del theta, mean, sq, ring, out, outs
     # C4b iVON, DistilBERT + head
     D = 66_955_010
     Dp = (D + 63) // 64 * 64

@@ -43,7 +43,8 @@ struct Tuning {
     int apply_variant = 0;     // 0 auto, 1 direct-LDG kernel, 2 TMA-staged kernel
     int pairdist_variant = 0;  // same for K1
     int ew_variant = 0;        // same for the elementwise family (ew_tma.cuh)
-    int apply_tile_sets = 0;   // staged K2 at n > 12: consumer tile sets (0 = default, 3 or 4)
+    int apply_tile_sets = 0;   // staged K2: alternative consumer geometry (0 = default; see launch_apply_opt)
+    int swag_batch = 0;        // draws per pass of the batched SWAG sampler (0 = default 16; 2, 4, 8, 16)
 };
 Tuning& tuning();
 

@@ -115,7 +115,7 @@ swag_sample_kernel(const float* __restrict__ mean, const float* __restrict__ sq,
 constexpr int kSwagBatchMax = 16;   // draws per launch (4 accumulator registers each)
 
 template <bool VEC, int SB>
-__global__ void __launch_bounds__(kEwThreads)
+__global__ void __launch_bounds__(kEwThreads, SB >= 16 ? 2 : 3)
 swag_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
                          int head, int64_t D, int64_t ld, int S, const float* __restrict__ eps_k,
                          const float* __restrict__ eps_d, int64_t ld_eps, uint64_t seed, uint64_t stream_id, int64_t quad0,
@@ -147,16 +147,34 @@ swag_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
         float4 low[SB];
 #pragma unroll
         for (int sidx = 0; sidx < SB; ++sidx) low[sidx] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-        for (int k = 0; k < K; ++k) {
-            const float4 d = load_quad<VEC, true>(dev + rowoff[k], b, D);
+        constexpr int KU = 5;   // deviation rows in flight per thread, as in the single-draw kernel
+        for (int k0 = 0; k0 < K; k0 += KU) {
+            float4 d[KU];
 #pragma unroll
-            for (int sidx = 0; sidx < SB; ++sidx) {
-                const float z = zc[k][sidx];
-                low[sidx].x = fmaf(d.x, z, low[sidx].x);
-                low[sidx].y = fmaf(d.y, z, low[sidx].y);
-                low[sidx].z = fmaf(d.z, z, low[sidx].z);
-                low[sidx].w = fmaf(d.w, z, low[sidx].w);
+            for (int u = 0; u < KU; ++u)
+                if (k0 + u < K) d[u] = load_quad<VEC, true>(dev + rowoff[k0 + u], b, D);
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                if (k0 + u < K) {
+#pragma unroll
+                    for (int s4 = 0; s4 < SB; s4 += (SB >= 4 ? 4 : 2)) {
+                        float z[4];
+                        if constexpr (SB >= 4) {
+                            const float4 zz = *reinterpret_cast<const float4*>(&zc[k0 + u][s4]);
+                            z[0] = zz.x, z[1] = zz.y, z[2] = zz.z, z[3] = zz.w;
+                        } else {
+                            const float2 zz = *reinterpret_cast<const float2*>(&zc[k0 + u][s4]);
+                            z[0] = zz.x, z[1] = zz.y, z[2] = z[3] = 0.0f;
+                        }
+#pragma unroll
+                        for (int t = 0; t < (SB >= 4 ? 4 : 2); ++t) {
+                            low[s4 + t].x = fmaf(d[u].x, z[t], low[s4 + t].x);
+                            low[s4 + t].y = fmaf(d[u].y, z[t], low[s4 + t].y);
+                            low[s4 + t].z = fmaf(d[u].z, z[t], low[s4 + t].z);
+                            low[s4 + t].w = fmaf(d[u].w, z[t], low[s4 + t].w);
+                        }
+                    }
+                }
             }
         }
         // diag = 0.5 * (relu(sq - mean**2) + 1e-6), shared by all draws (swag.py:112)
@@ -266,8 +284,10 @@ extern "C" int bde_swag_sample_batch(const float* mean, const float* sq, const f
                      (ld_out % 4 == 0) && (!eps_d || (aligned16(eps_d) && ld_eps % 4 == 0));
     const float den = static_cast<float>(sqrt(2.0 * (K - 1)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    for (int s0 = 0; s0 < S; s0 += kSwagBatchMax) {   // 16 draws per pass over the moments
-        const int c = S - s0 < kSwagBatchMax ? S - s0 : kSwagBatchMax;
+    const int tb = tuning().swag_batch;
+    const int per_pass = (tb == 2 || tb == 4 || tb == 8) ? tb : kSwagBatchMax;
+    for (int s0 = 0; s0 < S; s0 += per_pass) {   // up to 16 draws per pass over the moments
+        const int c = S - s0 < per_pass ? S - s0 : per_pass;
         const int sb = c <= 2 ? 2 : (c <= 4 ? 4 : (c <= 8 ? 8 : 16));
         const float* ek = eps_k ? eps_k + static_cast<int64_t>(s0) * K : nullptr;
         const float* ed = eps_d ? eps_d + s0 * ld_eps : nullptr;

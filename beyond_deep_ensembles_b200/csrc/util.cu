@@ -106,6 +106,7 @@ extern "C" int bde_tune(const char* key, int value) {
     else if (k == "pairdist_variant") tuning().pairdist_variant = value;
     else if (k == "ew_variant") tuning().ew_variant = value;
     else if (k == "apply_tile_sets") tuning().apply_tile_sets = value;
+    else if (k == "swag_batch") tuning().swag_batch = value;
     else return BDE_ERR_INVALID_ARG;
     return BDE_OK;
 }
