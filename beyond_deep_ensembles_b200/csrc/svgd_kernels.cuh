@@ -20,18 +20,52 @@ constexpr int kFlushIters = 128;   // fp32 -> fp64 flush period (columns*4 per t
 constexpr int kMaxCtasPairdist = 148 * 8 * 2;
 
 __host__ __device__ constexpr int pair_count(int n) { return n * (n - 1) / 2; }
-__host__ __device__ constexpr int pair_groups(int n) {
+__host__ __device__ __forceinline__ constexpr int pair_index(int i, int j, int n) {  // i < j
+    return i * (2 * n - i - 1) / 2 + (j - i - 1);
+}
+__host__ __device__ constexpr int pair_row(int p, int n) {  // row i of pair p in the row-major upper triangle
+    int i = 0;
+    while (p >= n - 1 - i) {
+        p -= n - 1 - i;
+        ++i;
+    }
+    return i;
+}
+// How the n(n-1)/2 pairs are shared between the thread groups of a CTA (one group keeps <= ~50 pair accumulators):
+//  * contiguous: group g owns pairs [g*PG, (g+1)*PG) of the row-major upper triangle (n = 11, 12: two groups);
+//  * blocked (n = 20; rows in four blocks A B C D of n/4): group 0 = all pairs inside A+B, group 1 = all pairs inside
+//    C+D, group 2 = AxC then BxD, group 3 = AxD then BxC.  A group then touches n/2 rows at a time instead of all n:
+//    half the row registers (no spills under the 168-register cap of the 9-warp CTA) and 60 instead of 80 LDS.128
+//    per column quad.
+__host__ __device__ constexpr int pair_groups_contig(int n) {
     return pair_count(n) <= kPairTarget ? 1 : (pair_count(n) + kPairTarget - 1) / kPairTarget;
 }
+// measured on B200 (D = 5e7 / 6e7): n = 20 staged K1 1.155 -> 0.957 ms blocked; n = 16 is faster contiguous on 3 groups
+// (7 warps, 255 registers: 0.886 ms vs 0.952 ms blocked on 4 groups / 9 warps), so only four-group shapes are blocked
+__host__ __device__ constexpr bool pair_blocked(int n) { return n % 4 == 0 && pair_groups_contig(n) > 3; }
+__host__ __device__ constexpr int pair_groups(int n) { return pair_blocked(n) ? 4 : pair_groups_contig(n); }
 __host__ __device__ constexpr int pairs_per_group(int n) {
+    if (pair_blocked(n)) return pair_count(n / 2) > 2 * (n / 4) * (n / 4) ? pair_count(n / 2) : 2 * (n / 4) * (n / 4);
     return pair_groups(n) == 0 ? 0 : (pair_count(n) + pair_groups(n) - 1) / pair_groups(n);
+}
+// (group, slot inside the group's accumulator array) of pair (i, j), i < j
+__host__ __device__ constexpr int pair_group_of(int i, int j, int n) {
+    if (!pair_blocked(n)) return pair_index(i, j, n) / pairs_per_group(n);
+    const int bs = n / 4, bi = i / bs, bj = j / bs;
+    if (bj <= 1) return 0;
+    if (bi >= 2) return 1;
+    return (bj - bi == 2) ? 2 : 3;   // AxC, BxD -> 2;  AxD, BxC -> 3
+}
+__host__ __device__ constexpr int pair_slot_of(int i, int j, int n) {
+    if (!pair_blocked(n)) return pair_index(i, j, n) % pairs_per_group(n);
+    const int bs = n / 4, h = n / 2, bi = i / bs, bj = j / bs;
+    if (bj <= 1) return pair_index(i, j, h);
+    if (bi >= 2) return pair_index(i - h, j - h, h);
+    return (bi == 0 ? 0 : bs * bs) + (i - bi * bs) * bs + (j - bj * bs);
 }
 __host__ __device__ constexpr int pairdist_tpb(int n) {
     // threads along columns; total CTA threads = tpb * groups
     return pair_groups(n) <= 2 ? 128 : (pair_groups(n) <= 4 ? 64 : 32);
-}
-__host__ __device__ __forceinline__ constexpr int pair_index(int i, int j, int n) {  // i < j
-    return i * (2 * n - i - 1) / 2 + (j - i - 1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -54,6 +88,64 @@ __device__ __forceinline__ void pair_accumulate(const V4 (&v)[N], f32x2 (&acc)[p
                 acc[p - LO] = fma2(d1, d1, acc[p - LO]);
             }
         }
+    }
+}
+
+// all pairs among R rows held in registers: slot = pair_index(a, b, R) + BASE
+template <int R, int BASE, int PGN>
+__device__ __forceinline__ void pairs_within(const V4 (&v)[R], f32x2 (&acc)[PGN]) {
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+#pragma unroll
+        for (int b = a + 1; b < R; ++b) {
+            const int k = BASE + pair_index(a, b, R);
+            const f32x2 d0 = sub2(v[a].lo, v[b].lo);
+            const f32x2 d1 = sub2(v[a].hi, v[b].hi);
+            acc[k] = fma2(d0, d0, acc[k]);
+            acc[k] = fma2(d1, d1, acc[k]);
+        }
+    }
+}
+// all BS x BS pairs between row block `u` (in registers) and the block starting at row WB, whose rows are pulled one
+// at a time (5 + 1 rows live instead of 10): slot = BASE + a*BS + b.  `loaded()` runs after the very last row load.
+template <int BS, int BASE, int WB, bool LAST, int PGN, typename Row, typename Loaded>
+__device__ __forceinline__ void pairs_cross(const V4 (&u)[BS], Row&& row, Loaded&& loaded, f32x2 (&acc)[PGN]) {
+#pragma unroll
+    for (int b = 0; b < BS; ++b) {
+        const V4 w = row(WB + b);
+        if (LAST && b == BS - 1) loaded();
+#pragma unroll
+        for (int a = 0; a < BS; ++a) {
+            const int k = BASE + a * BS + b;
+            const f32x2 d0 = sub2(u[a].lo, w.lo);
+            const f32x2 d1 = sub2(u[a].hi, w.hi);
+            acc[k] = fma2(d0, d0, acc[k]);
+            acc[k] = fma2(d1, d1, acc[k]);
+        }
+    }
+}
+// Blocked decomposition (pair_blocked(N)): group G pulls only the rows it needs through `row(r)` (shared memory,
+// global memory or a ragged-tail column) — in two phases for the cross groups — and calls `loaded()` once its last row
+// is in registers (the staged kernel releases the ring stage there).
+template <int N, int G, typename Row, typename Loaded>
+__device__ __forceinline__ void pair_accumulate_blocked(Row&& row, Loaded&& loaded, f32x2 (&acc)[pairs_per_group(N)]) {
+    constexpr int BS = N / 4, H = N / 2, PGN = pairs_per_group(N);
+    if constexpr (G <= 1) {
+        V4 v[H];
+#pragma unroll
+        for (int r = 0; r < H; ++r) v[r] = row(G * H + r);
+        loaded();
+        pairs_within<H, 0, PGN>(v, acc);
+    } else {
+        constexpr int P1 = (G == 2) ? 2 : 3;   // partner block of A;  B pairs with the other one of C / D
+        constexpr int P2 = (G == 2) ? 3 : 2;
+        V4 u[BS];
+#pragma unroll
+        for (int r = 0; r < BS; ++r) u[r] = row(r);
+        pairs_cross<BS, 0, P1 * BS, false, PGN>(u, row, loaded, acc);
+#pragma unroll
+        for (int r = 0; r < BS; ++r) u[r] = row(BS + r);
+        pairs_cross<BS, BS * BS, P2 * BS, true, PGN>(u, row, loaded, acc);
     }
 }
 
@@ -115,28 +207,52 @@ __device__ __forceinline__ void pairdist_body(const float* __restrict__ X, int64
     while (more) {
         for (int iter = 0; iter < kFlushIters && q0 < nquads; ++iter, q0 += stride) {
             const int64_t q = q0 + threadIdx.x;
-            V4 v[N];
-            if (q < nquads) {
+            if constexpr (pair_blocked(N)) {
                 const float* p = X + 4 * q;
-#pragma unroll
-                for (int i = 0; i < N; ++i) v[i] = (NG > 1) ? ldg_cached_v4(p + i * ld) : ldg_stream_v4(p + i * ld);
+                const bool in = q < nquads;
+                pair_accumulate_blocked<N, G>(
+                    [&](int r) {
+                        V4 z;
+                        z.lo = z.hi = 0ull;
+                        return in ? ldg_cached_v4(p + r * ld) : z;
+                    },
+                    [] {}, acc);
             } else {
+                V4 v[N];
+                if (q < nquads) {
+                    const float* p = X + 4 * q;
 #pragma unroll
-                for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                    for (int i = 0; i < N; ++i) v[i] = (NG > 1) ? ldg_cached_v4(p + i * ld) : ldg_stream_v4(p + i * ld);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                }
+                pair_accumulate<N, G>(v, acc);
             }
-            pair_accumulate<N, G>(v, acc);
         }
         more = q0 < nquads;
         // ragged tail: columns 4*nquads .. D-1, one per thread of CTA 0
         if (!more && blockIdx.x == 0 && (D & 3)) {
-            V4 v[N];
             const int64_t c = 4 * nquads + threadIdx.x;
+            const bool in = threadIdx.x < (D & 3);
+            if constexpr (pair_blocked(N)) {
+                pair_accumulate_blocked<N, G>(
+                    [&](int r) {
+                        V4 z;
+                        z.lo = in ? pack2(__ldg(X + r * ld + c), 0.0f) : 0ull;
+                        z.hi = 0ull;
+                        return z;
+                    },
+                    [] {}, acc);
+            } else {
+                V4 v[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                v[i].lo = (threadIdx.x < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
-                v[i].hi = 0ull;
+                for (int i = 0; i < N; ++i) {
+                    v[i].lo = in ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+                    v[i].hi = 0ull;
+                }
+                pair_accumulate<N, G>(v, acc);
             }
-            pair_accumulate<N, G>(v, acc);
         }
         flush_pairs<PG>(acc, wacc, lane);
     }
@@ -290,7 +406,8 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
     __syncthreads();
 
     for (int p = tid; p < P; p += TPB * NG) {
-        const int grp = p / PG, k = p - grp * PG;
+        const int i = pair_row(p, N), j = p - pair_index(i, i + 1, N) + i + 1;
+        const int grp = pair_group_of(i, j, N), k = pair_slot_of(i, j, N);
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < WPG; ++w) s += wacc[grp * WPG + w][k];
@@ -355,28 +472,55 @@ __device__ __forceinline__ void pairdist_tma_consumer(const float* __restrict__ 
             const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
             mbar_wait(&full_bar[s], use & 1u);
             const float* sx = tiles + static_cast<size_t>(s) * N * TC + 4 * qi;
-            V4 v[N];
-            if (4 * qi < w) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) v[i] = lds_v4(sx + i * TC);
+            if constexpr (pair_blocked(N)) {
+                const bool in = 4 * qi < w;
+                pair_accumulate_blocked<N, G>(
+                    [&](int r) {
+                        V4 z;
+                        z.lo = z.hi = 0ull;
+                        return in ? lds_v4(sx + r * TC) : z;
+                    },
+                    [&] {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[s]);  // last row is in registers: release the stage
+                    },
+                    acc);
             } else {
+                V4 v[N];
+                if (4 * qi < w) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                    for (int i = 0; i < N; ++i) v[i] = lds_v4(sx + i * TC);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) v[i].lo = v[i].hi = 0ull;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);  // data is in registers: release the stage
+                pair_accumulate<N, G>(v, acc);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);  // data is in registers: release the stage
-            pair_accumulate<N, G>(v, acc);
         }
         more = t < ntiles;
         if (!more && blockIdx.x == 0 && (D & 3)) {  // ragged tail columns (D % 4)
-            V4 v[N];
             const int64_t c = d4 + qi;
+            const bool in = qi < (D & 3);
+            if constexpr (pair_blocked(N)) {
+                pair_accumulate_blocked<N, G>(
+                    [&](int r) {
+                        V4 z;
+                        z.lo = in ? pack2(__ldg(X + r * ld + c), 0.0f) : 0ull;
+                        z.hi = 0ull;
+                        return z;
+                    },
+                    [] {}, acc);
+            } else {
+                V4 v[N];
 #pragma unroll
-            for (int i = 0; i < N; ++i) {
-                v[i].lo = (qi < (D & 3)) ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
-                v[i].hi = 0ull;
+                for (int i = 0; i < N; ++i) {
+                    v[i].lo = in ? pack2(__ldg(X + i * ld + c), 0.0f) : 0ull;
+                    v[i].hi = 0ull;
+                }
+                pair_accumulate<N, G>(v, acc);
             }
-            pair_accumulate<N, G>(v, acc);
         }
         flush_pairs<PG>(acc, wacc, lane);
     }
@@ -457,7 +601,8 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
 
     // pair p of group grp is accumulated by that group's warps only
     for (int p = tid; p < P; p += nthreads) {
-        const int grp = p / PG, k = p - grp * PG;
+        const int i = pair_row(p, N), j = p - pair_index(i, i + 1, N) + i + 1;
+        const int grp = pair_group_of(i, j, N), k = pair_slot_of(i, j, N);
         double sacc = 0.0;
         for (int wv = grp; wv < CWARPS; wv += NG) sacc += wacc[wv][k];
         cta_vals[p] = sacc;
