@@ -10,7 +10,6 @@ from __future__ import annotations
 
 from typing import Any, Dict
 
-import torch
 from torch.optim import Optimizer
 
 
