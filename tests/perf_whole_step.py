@@ -232,7 +232,7 @@ def bench_config(name, build, steps, warmup):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="C1,C2,C3,C4a,C4b")
+    ap.add_argument("--configs", default="C1,C2,C3,C4a,C4b,C5")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--eager-only-cpu", action="store_true", help="debug: run only the eager port, on the CPU")
@@ -364,6 +364,27 @@ def main():
                 opt = EagerIVON(model.parameters(), 1e-5, 10.0, 269038, 2, 1e-3)
             return (lambda: opt.step(fwd, bwd)), passes(model, fwd, bwd, 2), None
         out["C4b_civil_distilbert_ivon"] = dict(D=66955010, **bench_config("C4b", build, args.steps, args.warmup))
+
+    # ---- C5: optimizer-only sweep point (n = 10 x D), this library vs the reference op sequence eager on the same GPU
+    if "C5" in want:
+        from beyond_deep_ensembles_b200 import ops
+        from oracle import bde_oracle as O
+        res5 = {}
+        for D5 in (10_000_000, 100_000_000):
+            g = torch.Generator(device=dev).manual_seed(0)
+            X = torch.randn(10, D5, device=dev, generator=g)
+            X *= (0.05 * (1 + 0.1 * torch.arange(10, device=dev, dtype=torch.float32))).unsqueeze(1)
+            G = torch.randn(10, D5, device=dev, generator=g) * 1e-3
+            outb = torch.empty_like(X)
+            sc = ops.SvgdScratch.allocate(10, dev)
+            ms_b = wall_ms(lambda: ops.svgd_step(X, G, outb, sc, 0.01, 1.0, 50000.0), 10, 3)
+            ms_e = wall_ms(lambda: O.svgd_step_reference_order(X, G, 0.01, 1.0, 50000.0), 3, 1)
+            res5[f"D{D5}"] = {"b200_ms": ms_b, "eager_reference_order_ms": ms_e, "speedup": ms_e / ms_b,
+                              "b200_GBps": 16 * 10 * D5 / ms_b / 1e6, "eager_GBps_algorithmic": 16 * 10 * D5 / ms_e / 1e6}
+            log(f"[whole_step] C5 D={D5}: b200 {ms_b:.3f} ms, eager reference order {ms_e:.3f} ms ({ms_e / ms_b:.1f}x)")
+            del X, G, outb
+            torch.cuda.empty_cache()
+        out["C5_svgd_update_only_n10"] = res5
 
     out["_meta"] = {"gpu": torch.cuda.get_device_name(0) if torch.cuda.is_available() else "cpu", "torch": torch.__version__,
                     "timing": "wall clock per step, best of 3 timed loops, synchronised before and after each loop",
