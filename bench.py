@@ -110,11 +110,11 @@ def synth_host(n, D, seed=0):
     return X, G
 
 
-def cpu_reference_run(steps: int, warmup: int, D: int = CPU_SAMPLE_D):
+def cpu_reference_run(steps: int, warmup: int, D: int = CPU_SAMPLE_D, threads: int | None = None):
     """Times oracle.svgd_step_reference_order (the same ATen op sequence as svgd.py:86-89 + rbf)
-    in fp32 with every host thread torch will use.  Returns (GB/s, ms/step, threads)."""
+    in fp32 with every host thread torch will use (or `threads`).  Returns (GB/s, ms/step, threads)."""
     from oracle import bde_oracle as O
-    threads = os.cpu_count() or 1
+    threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     X, G = synth_host(N_PARTICLES, D)
     for _ in range(max(1, warmup)):
@@ -549,6 +549,8 @@ def main():
                         "sample": f"n={N_PARTICLES} x D={CPU_SAMPLE_D} fp32 on the host ({CPU_SAMPLE_D / D_PER_GPU:.0%} of "
                                   "one GPU's columns), 3 timed steps of oracle.svgd_step_reference_order "
                                   "(reference op order, torch CPU ops, all host threads)"}
+            gbs8, ms8, t8 = cpu_reference_run(2, 1, threads=min(8, os.cpu_count() or 1))   # second run pinned to 8 threads
+            cpu_base["pinned_threads_run"] = {"value": gbs8, "unit": "GB/s", "ms_per_step": ms8, "cores": t8}
 
     if rank == 0:
         k2_bytes = 12.0 * n * D
