@@ -138,13 +138,15 @@ class iVONOptimizer(BayesianOptimizer):
         """acc_grad (+)= grad, gathered straight from the scattered .grad tensors (ivorn.py:120-127)."""
         for group, ar in zip(self.param_groups, self._arenas):
             L, r, v = ar["layout"], ar["rows"], ar["views"]
-            grads = []
-            for param in group["params"]:
-                if param.grad is None:
-                    raise TypeError("iVON needs a gradient for every parameter after backward_closure")
-                grads.append(param.grad if param.grad.is_contiguous() else param.grad.contiguous())
+            grads = [param.grad for param in group["params"]]
+            if any(g is None for g in grads):
+                raise TypeError("iVON needs a gradient for every parameter after backward_closure")
             first = ar.get("n_grads", 0) == 0
-            ops.multi_tensor_copy(r["acc_grad"], grads, L.offsets, mode=0 if first else 1)
+            mode = 0 if first else 1
+            try:
+                ops.multi_tensor_copy(r["acc_grad"], grads, L.offsets, mode=mode, table=L.copy_table)
+            except ValueError:   # e.g. channels_last gradients: gather from contiguous copies
+                ops.multi_tensor_copy(r["acc_grad"], [g.contiguous() for g in grads], L.offsets, mode=mode, table=L.copy_table)
             ar["n_grads"] = ar.get("n_grads", 0) + 1
             if first:
                 for k, param in enumerate(group["params"]):

@@ -33,6 +33,15 @@ class ParamLayout:
         self.size = max(off, align)            # padded row length (multiple of `align`)
         self.logical_size = sum(self.numels)
         self._index = {}
+        self._copy_table = None
+
+    @property
+    def copy_table(self):
+        """The constant argument tables of ops.multi_tensor_copy for this layout (built on first use)."""
+        if self._copy_table is None:
+            from . import ops
+            self._copy_table = ops.CopyTable(self.offsets, self.numels)
+        return self._copy_table
 
     def new_arena(self, rows: int, device, dtype=torch.float32) -> torch.Tensor:
         return torch.zeros((rows, self.size), dtype=dtype, device=device)

@@ -409,23 +409,46 @@ def philox_normal(out: torch.Tensor, seed: int, stream_id: int, elem0: int = 0) 
     return out
 
 
-def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int) -> None:
+class CopyTable:
+    """Host-side half of a multi_tensor_copy call that does not change between calls: the flat offsets and the
+    element counts of the tensors (ctypes arrays built once) and a reusable pointer array.  Built once per
+    parameter layout; per call only the data pointers are refreshed (autograd may hand out new .grad storage)."""
+
+    def __init__(self, offsets, numels):
+        self.count = len(offsets)
+        self.numels = [int(n) for n in numels]
+        self.offs = (C.c_int64 * self.count)(*[int(o) for o in offsets])
+        self.sizes = (C.c_int64 * self.count)(*self.numels)
+        self.offs_p = C.cast(self.offs, C.c_void_p)
+        self.sizes_p = C.cast(self.sizes, C.c_void_p)
+
+
+def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int, table: CopyTable | None = None) -> None:
     """Gather (mode 0), gather-add (1) or scatter (2) between `tensors` and a flat arena row.
 
-    offsets: element offsets of each tensor inside flat_row (ascending)."""
-    require_cuda(flat_row, *tensors)
-    _lib.require_f32(flat_row, *tensors)
+    offsets: element offsets of each tensor inside flat_row (ascending); `table` (a CopyTable for the same
+    offsets and tensor sizes) skips rebuilding the constant part of the argument tables."""
     count = len(tensors)
     if count == 0:
         return
-    for t in tensors:
+    require_cuda(flat_row, *tensors)
+    _lib.require_f32(flat_row)
+    if table is None:
+        table = CopyTable(offsets, [t.numel() for t in tensors])
+    elif table.count != count:
+        raise ValueError("multi_tensor_copy: tensor list does not match the copy table")
+    f32, ptrs = torch.float32, []
+    for t, numel in zip(tensors, table.numels):
+        if t.dtype is not f32:
+            raise TypeError(f"expected float32 tensor, got {t.dtype}")
         if not t.is_contiguous():
             raise ValueError("multi_tensor_copy needs contiguous tensors")
-    ptrs = (C.c_uint64 * count)(*[t.data_ptr() for t in tensors])
-    offs = (C.c_int64 * count)(*[int(o) for o in offsets])
-    sizes = (C.c_int64 * count)(*[t.numel() for t in tensors])
-    _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(offs, C.c_void_p),
-              C.cast(sizes, C.c_void_p), count, int(mode), _s(flat_row))
+        if t.numel() != numel:
+            raise ValueError("multi_tensor_copy: tensor size does not match the copy table")
+        ptrs.append(t.data_ptr())
+    cptrs = (C.c_uint64 * count)(*ptrs)
+    _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(cptrs, C.c_void_p), table.offs_p, table.sizes_p,
+              count, int(mode), _s(flat_row))
 
 
 # --------------------------------------------------------------------------------------

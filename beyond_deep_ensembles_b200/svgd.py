@@ -199,12 +199,14 @@ class SVGDOptimizer(BayesianOptimizer):
 
     def _store_grads(self, particle_idx, plist):
         """Gather this particle's gradients into row `particle_idx` of G (one launch)."""
-        grads = []
-        for p in plist:
-            if p.grad is None:
-                raise AttributeError("SVGD needs a gradient for every parameter after backward_closure")
-            grads.append(p.grad if p.grad.is_contiguous() else p.grad.contiguous())
-        ops.multi_tensor_copy(self._G[particle_idx], grads, self._layout.offsets, mode=0)
+        grads = [p.grad for p in plist]
+        if any(g is None for g in grads):
+            raise AttributeError("SVGD needs a gradient for every parameter after backward_closure")
+        row, L = self._G[particle_idx], self._layout
+        try:
+            ops.multi_tensor_copy(row, grads, L.offsets, mode=0, table=L.copy_table)
+        except ValueError:   # e.g. channels_last gradients: gather from contiguous copies
+            ops.multi_tensor_copy(row, [g.contiguous() for g in grads], L.offsets, mode=0, table=L.copy_table)
 
     def get_base_optimizer(self):
         return self.state["__base_optimizer"]

@@ -166,7 +166,8 @@ class SwagOptimizer(BayesianOptimizer):
         if all(p.data_ptr() == v.data_ptr() for p, v in zip(plist, self._tviews)):
             return
         with torch.no_grad():
-            ops.multi_tensor_copy(self._theta, [p.detach().contiguous() for p in plist], self._layout.offsets, mode=0)
+            ops.multi_tensor_copy(self._theta, [p.detach().contiguous() for p in plist], self._layout.offsets, mode=0,
+                                  table=self._layout.copy_table)
             for param, tview in zip(plist, self._tviews):
                 param.data = tview
 
