@@ -26,7 +26,9 @@ def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ("bde_svgd_pairdist", "bde_svgd_bandwidth", "bde_svgd_apply", "bde_swag_update", "bde_swag_sample",
                  "bde_ivon_sample", "bde_ivon_update", "bde_gauss_sample_fwd", "bde_gauss_sample_bwd",
-                 "bde_kl_gauss_value_and_grad", "bde_l2_value_and_grad", "bde_svgd_step_host"):
+                 "bde_kl_gauss_value_and_grad", "bde_l2_value_and_grad", "bde_svgd_step_host", "bde_swag_sample_batch",
+                 "bde_svgd_apply_sgd", "bde_svgd_apply_adam", "bde_svgd_train_step_sgd", "bde_svgd_train_step_adam",
+                 "bde_prior_terms_value_and_grad", "bde_multi_tensor_copy", "bde_peer_attach"):
         assert must in syms
 
 
