@@ -353,6 +353,41 @@ def gen_ensemble():
     np.savez_compressed(OUT / "ensemble_predict.npz", inits=np.stack(inits), x=xs[0].numpy(), preds=preds.numpy())
 
 
+def gen_ensemble_swag():
+    """DeepEnsemble.predict over two SWAG members (ensemble.py:28-44 -> swag.py:53-58): 7 predictions, 4 + 3 draws,
+    low-rank / diagonal noise injected at LowRankMultivariateNormal's draw point.  Pins the batched sampler
+    (SwagOptimizer.presample, announced by predict) to the reference's one-by-one draws."""
+    K, members = 4, 2
+    pairs, inits = [], []
+    xs, ys = batches(27, 8)
+    for m in range(members):
+        torch.manual_seed(80 + m)
+        model = gm.make_mlp()
+        g = torch.Generator().manual_seed(90 + m)
+        D = sum(p.numel() for p in model.parameters())
+        init = (0.3 * torch.randn(D, generator=g)).numpy()
+        gm.load_flat(model.parameters(), init)
+        base = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+        opt = SwagOptimizer(model.parameters(), base, update_interval=1, start_epoch=0, deviation_samples=K)
+        for s in range(6):   # 6 updates: the K=4 deviation matrix has rolled
+            fwd, bwd = gm.mse_closures(model, xs[s], ys[s])
+            opt.step(fwd, bwd)
+        pairs.append((model, opt))
+        inits.append(init)
+    ens = DeepEnsemble(pairs)
+    tape = NoiseTape(43)
+    import torch.distributions.lowrank_multivariate_normal as lrmn
+    orig = lrmn._standard_normal
+    lrmn._standard_normal = tape.standard_normal
+    try:
+        with torch.no_grad():
+            preds = ens.predict(lambda mdl: mdl(xs[7]).squeeze(-1), samples=7)
+    finally:
+        lrmn._standard_normal = orig
+    np.savez_compressed(OUT / "ensemble_swag_predict.npz", inits=np.stack(inits), xs=xs.numpy(), ys=ys.numpy(),
+                        preds=preds.numpy(), eps=np.concatenate(tape.log), eps_sizes=np.array([a.size for a in tape.log]))
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     if len(sys.argv) > 1:  # regenerate selected fixtures only:  python oracle/gen_golden.py gen_svgd_sgd
@@ -367,5 +402,6 @@ if __name__ == "__main__":
     gen_bbb()
     gen_vectors()
     gen_ensemble()
+    gen_ensemble_swag()
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)

@@ -489,6 +489,33 @@ def test_deep_ensemble_announces_batches_to_swag_members(env, golden):
     assert preds[0].shape[0] == 7
 
 
+@pytest.mark.parametrize("batched", [True, False], ids=["presample", "one-by-one"])
+def test_deep_ensemble_over_swag_members_matches_reference(env, golden, batched):
+    """The reference's DeepEnsemble.predict over two SWAG members (fixture recorded from the unmodified reference
+    with its noise draws on tape): the batched sampler announced by predict() and the one-by-one path both
+    reproduce the reference's 4 + 3 predictions."""
+    g = golden("ensemble_swag_predict.npz")
+    pairs = []
+    for m in range(g["inits"].shape[0]):
+        model = gm.make_mlp().to(env.dev)
+        gm.load_flat(model.parameters(), g["inits"][m])
+        base = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+        opt = bde.SwagOptimizer(model.parameters(), base, update_interval=1, start_epoch=0, deviation_samples=4)
+        for s in range(6):
+            fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+            opt.step(fwd, bwd)
+        if not batched:
+            opt.presample = lambda count: None
+        pairs.append((model, opt))
+    ens = bde.DeepEnsemble(pairs)
+    x = env.t(g["xs"][7])
+    with noise.inject(tape(g["eps"], g["eps_sizes"])), torch.no_grad():
+        preds = ens.predict(lambda mdl: mdl(x).squeeze(-1), samples=7)
+    np.testing.assert_allclose(preds.cpu().numpy(), g["preds"], rtol=3e-5, atol=3e-6)
+    if env.fake and batched:
+        assert env.calls("swag_sample_batch") == 2 and env.calls("swag_sample") == 0
+
+
 def test_swag_loads_reference_layout_checkpoint(env, golden):
     g = golden("swag_steps.npz")
     model, opt = build_swag(env, g)
