@@ -54,6 +54,7 @@ SIGNATURES = {
     "bde_swag_sample": [_p, _p, _p, _i, _i, _i64, _i64, _p, _p, _u64, _u64, _i64, _p, _p],
     "bde_swag_sample_batch": [_p, _p, _p, _i, _i, _i64, _i64, _i, _p, _p, _i64, _u64, _u64, _i64, _p, _i64, _p],
     "bde_ivon_sample": [_p, _p, _p, _p, _i64, _d, _i, _i, _p, _u64, _u64, _i64, _p],
+    "bde_ivon_sample_batch": [_p, _p, _p, _p, _i64, _i64, _i, _d, _i, _i, _p, _i64, _u64, _u64, _u64, _i64, _p],
     "bde_ivon_accumulate": [_p, _p, _i64, _i, _p],
     "bde_ivon_update": [_p, _p, _p, _p, _p, _i64, _i, _i64, _d, _d, _d, _d, _d, _d, _d, _p],
     "bde_gauss_sample_fwd": [_p, _p, _p, _i64, _p, _u64, _u64, _i64, _p],

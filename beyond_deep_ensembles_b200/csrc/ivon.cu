@@ -49,6 +49,51 @@ ivon_sample_kernel(const float* __restrict__ mean, const float* __restrict__ pre
     }
 }
 
+// K5 batched: S consecutive draws in one pass — mean and precision are read once, delta_sum is
+// read / written once, S weight vectors are written: (8 or 16 + 4 S) D bytes instead of 20 S D.  Draw s equals
+// bde_ivon_sample with stream_id + s * stream_stride bit for bit (same 1/sqrt factor, same running delta_sum order).
+template <bool VEC>
+__global__ void __launch_bounds__(kEwThreads)
+ivon_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict__ prec, float* __restrict__ delta_sum,
+                         float* __restrict__ theta, int64_t ld_out, int64_t D, int S, float n_eff, int first,
+                         int deterministic, const float* __restrict__ eps, int64_t ld_eps, uint64_t seed,
+                         uint64_t stream_id, uint64_t stream_stride, int64_t quad0) {
+    BDE_QUAD_LOOP(q, D) {
+        const int64_t b = q << 2;
+        const float4 m = load_quad<VEC, true>(mean, b, D);
+        const bool inj = eps != nullptr;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);   // 1 / sqrt(N max(prec, 1e-4)), shared by all draws
+        if (!deterministic) {
+            const float4 p = load_quad<VEC, true>(prec, b, D);
+            auto f = [&](float pv) {
+                const float x = __fmul_rn(n_eff, fmaxf(pv, 1e-4f));
+                return inj ? __fdiv_rn(1.0f, __fsqrt_rn(x)) : rsqrt_approx(x);
+            };
+            c = BDE_LANES(f(p.x), f(p.y), f(p.z), f(p.w));
+        }
+        float4 ds = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!first) ds = load_quad<VEC, false>(delta_sum, b, D);
+        for (int sidx = 0; sidx < S; ++sidx) {
+            float4 dl = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!deterministic) {
+                float4 e;
+                if (inj)
+                    e = load_quad<VEC, true>(eps + sidx * ld_eps, b, D);
+                else
+                    e = philox_normal4(seed, stream_id + sidx * stream_stride, static_cast<uint64_t>(quad0 + q));
+                dl = BDE_LANES(__fmul_rn(c.x, e.x), __fmul_rn(c.y, e.y), __fmul_rn(c.z, e.z), __fmul_rn(c.w, e.w));
+            }
+            const float4 th = BDE_LANES(__fadd_rn(m.x, dl.x), __fadd_rn(m.y, dl.y), __fadd_rn(m.z, dl.z), __fadd_rn(m.w, dl.w));
+            store_quad<VEC>(theta + sidx * ld_out, b, D, th);
+            if (first && sidx == 0)
+                ds = dl;
+            else
+                ds = BDE_LANES(__fadd_rn(ds.x, dl.x), __fadd_rn(ds.y, dl.y), __fadd_rn(ds.z, dl.z), __fadd_rn(ds.w, dl.w));
+        }
+        store_quad<VEC>(delta_sum, b, D, ds);
+    }
+}
+
 // K5, TMA-staged (ew_tma.cuh): inputs mean, prec, [delta_sum unless FIRST], [eps if EPS]
 template <bool FIRST, bool EPS>
 struct IvonSampleOp {
@@ -220,6 +265,25 @@ extern "C" int bde_ivon_sample(const float* mean, const float* prec, float* delt
         rc_ = launch_ew(ivon_sample_kernel<false>, D, st, mean, prec, delta_sum, theta, D, nf, first,
                                                                   deterministic, eps, seed, stream_id, elem0 >> 2);
     return rc_;
+}
+
+extern "C" int bde_ivon_sample_batch(const float* mean, const float* prec, float* delta_sum, float* theta,
+                                     int64_t ld_out, int64_t D, int S, double n_eff, int first, int deterministic,
+                                     const float* eps, int64_t ld_eps, uint64_t seed, uint64_t stream_id,
+                                     uint64_t stream_stride, int64_t elem0, bde_stream_t stream) {
+    if (!mean || !prec || !delta_sum || !theta || D < 0 || S < 0 || ld_out < D || (eps && ld_eps < D) || elem0 < 0 ||
+        (elem0 & 3))
+        return BDE_ERR_INVALID_ARG;
+    if (D == 0 || S == 0) return BDE_OK;
+    const bool vec = aligned16(mean) && aligned16(prec) && aligned16(delta_sum) && aligned16(theta) && (ld_out % 4 == 0) &&
+                     (!eps || (aligned16(eps) && ld_eps % 4 == 0));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float nf = static_cast<float>(n_eff);
+    if (vec)
+        return launch_ew(ivon_sample_batch_kernel<true>, D, st, mean, prec, delta_sum, theta, ld_out, D, S, nf, first,
+                         deterministic, eps, ld_eps, seed, stream_id, stream_stride, elem0 >> 2);
+    return launch_ew(ivon_sample_batch_kernel<false>, D, st, mean, prec, delta_sum, theta, ld_out, D, S, nf, first,
+                     deterministic, eps, ld_eps, seed, stream_id, stream_stride, elem0 >> 2);
 }
 
 extern "C" int bde_ivon_accumulate(float* acc, const float* grad, int64_t D, int first, bde_stream_t stream) {

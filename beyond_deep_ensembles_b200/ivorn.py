@@ -62,6 +62,8 @@ class iVONOptimizer(BayesianOptimizer):
 
         assert mc_samples > 0
         self.mc_samples = mc_samples
+        # presample(): draws generated ahead of time, handed out by the following sample_parameters() calls
+        self._pre_next = self._pre_ready = self._pre_pending = 0
 
     # ------------------------------------------------------------------ step
     def step(self, forward_closure, backward_closure, grad_scaler=None):
@@ -103,6 +105,7 @@ class iVONOptimizer(BayesianOptimizer):
         return acc_loss
 
     def _reset_state(self):
+        self._drop_presampled()
         for group, ar in zip(self.param_groups, self._arenas):
             ar["n_samples"] = 0
             ar["n_grads"] = 0
@@ -112,7 +115,19 @@ class iVONOptimizer(BayesianOptimizer):
                 state["acc_grad"] = None
 
     def sample_parameters(self):
-        """theta = mean + eps / sqrt(N max(prec, 1e-4)); delta_sum (+)= delta (ivorn.py:102-115)."""
+        """theta = mean + eps / sqrt(N max(prec, 1e-4)); delta_sum (+)= delta (ivorn.py:102-115) — or the next
+        row of a presample() batch."""
+        if self._pre_ready == 0 and self._pre_pending > 0:
+            self._draw_batch()
+        if self._pre_ready > 0:
+            row = self._pre_next
+            self._pre_next += 1
+            self._pre_ready -= 1
+            for group, ar in zip(self.param_groups, self._arenas):
+                for k, param in enumerate(group["params"]):
+                    param.data = ar["pre_views"][row][k]
+                    self.state[param]["delta"] = ar["views"]["delta"][k]
+            return
         for group, ar in zip(self.param_groups, self._arenas):
             L, r, v = ar["layout"], ar["rows"], ar["views"]
             first = ar["n_samples"] == 0
@@ -130,6 +145,50 @@ class iVONOptimizer(BayesianOptimizer):
                 for k, param in enumerate(plist):
                     param.data = v["theta"][k]
                     self.state[param]["delta"] = v["delta"][k]
+
+    # ---- batched sampling ----
+    #: upper bound of the presample buffers in bytes; larger requests are drawn in several batches
+    presample_max_bytes = 4 << 30
+
+    def presample(self, count: int):
+        """Announce that the next `count` sample_parameters() calls follow each other without a step() in between
+        (what DeepEnsemble.predict does, ensemble.py:37-43): they are generated by ONE K5-batched launch per
+        parameter group, reading mean / precision once.  Every draw — and delta_sum afterwards — is bit-identical
+        to what `count` single calls produce (same Philox streams, same injected-noise order)."""
+        self._drop_presampled()
+        self._pre_pending = int(count) if count and count > 1 else 0
+
+    def _drop_presampled(self):
+        self._pre_next = self._pre_ready = self._pre_pending = 0
+
+    def _draw_batch(self):
+        groups = len(self.param_groups)
+        total = sum(ar["layout"].size for ar in self._arenas)
+        rows = int(min(self._pre_pending, max(1, self.presample_max_bytes // (4 * total))))
+        # injected noise is consumed in the order of `rows` sequential calls: one draw per group per call
+        eps = [[] for _ in range(groups)]
+        for _ in range(rows):
+            for g, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
+                if not group["deterministic"]:
+                    eps[g].append(noise.draw("ivon", ar["layout"].logical_size, ar["rows"]["mean"].device))
+        first_id = noise.reserve_stream_ids(rows * groups)   # call s, group g: first_id + s * groups + g
+        for g, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
+            L, r = ar["layout"], ar["rows"]
+            if ar.get("pre_buf") is None or ar["pre_buf"].shape[0] < rows:
+                ar["pre_buf"] = L.new_arena(rows, r["mean"].device)
+                ar["pre_views"] = [L.views(ar["pre_buf"][k]) for k in range(rows)]
+            e = None
+            if eps[g] and all(z is not None for z in eps[g]):
+                e = torch.stack([L.from_logical(z) for z in eps[g]])
+            elif any(z is not None for z in eps[g]):
+                raise ValueError("a noise injector must supply either every draw of a presampled batch or none")
+            ops.ivon_sample_batch(r["mean"], r["precision"], r["delta"], ar["pre_buf"][:rows],
+                                  n_eff=group["N"] * group["augmentation"], first=ar["n_samples"] == 0,
+                                  deterministic=bool(group["deterministic"]), eps=e, seed=noise.seed(),
+                                  stream_id=first_id + g, stream_stride=groups)
+            ar["n_samples"] += rows
+        self._pre_next, self._pre_ready = 0, rows
+        self._pre_pending -= rows
 
     def get_base_optimizer(self):
         return self
@@ -155,6 +214,7 @@ class iVONOptimizer(BayesianOptimizer):
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
+        self._drop_presampled()
         with torch.no_grad():
             for group, ar in zip(self.param_groups, self._arenas):
                 v = ar["views"]

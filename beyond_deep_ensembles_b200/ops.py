@@ -260,6 +260,24 @@ def ivon_sample(mean, prec, delta_sum, theta, *, n_eff: float, first: bool, dete
               _s(mean))
 
 
+def ivon_sample_batch(mean, prec, delta_sum, theta, *, n_eff: float, first: bool, deterministic: bool = False, eps=None,
+                      seed: int = 0, stream_id: int = 0, stream_stride: int = 1, elem0: int = 0) -> None:
+    """K5 batched: theta [S, ld_out] receives S consecutive draws; draw s is what ivon_sample returns for
+    stream_id + s * stream_stride, delta_sum ends as after S single calls.  eps: [S, D] (row stride free) or None."""
+    require_cuda(mean, prec, delta_sum, theta, eps)
+    _lib.require_f32(mean, prec, delta_sum, theta, eps)
+    D = _vec(mean).numel()
+    S, Do, ld_out = _rows(theta)
+    assert Do == D and _vec(prec).numel() == D and _vec(delta_sum).numel() == D
+    ld_eps = 0
+    if eps is not None:
+        Se, De, ld_eps = _rows(eps)
+        assert (Se, De) == (S, D)
+    _lib.call("bde_ivon_sample_batch", mean.data_ptr(), prec.data_ptr(), delta_sum.data_ptr(), theta.data_ptr(), ld_out, D,
+              S, float(n_eff), int(first), int(deterministic), _lib.ptr(eps), ld_eps, int(seed), int(stream_id),
+              int(stream_stride), int(elem0), _s(mean))
+
+
 def ivon_accumulate(acc, grad, first: bool) -> None:
     """K6 (ivorn.py:120-127)."""
     require_cuda(acc, grad)

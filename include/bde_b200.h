@@ -240,6 +240,17 @@ int bde_ivon_sample(const float* mean, const float* prec, float* delta_sum, floa
                     int64_t D, double n_eff, int first, int deterministic, const float* eps,
                     uint64_t seed, uint64_t stream_id, int64_t elem0, bde_stream_t stream);
 
+/*
+ * K5 batched: S consecutive draws in one pass (DeepEnsemble.predict).  theta: [S, ld_out];
+ * draw s equals bde_ivon_sample with stream_id + s*stream_stride bit for bit (stream_stride = number of
+ * parameter groups, which take their stream ids round-robin); delta_sum ends as after S single calls.
+ * eps: [S, ld_eps] or NULL.
+ */
+int bde_ivon_sample_batch(const float* mean, const float* prec, float* delta_sum, float* theta,
+                          int64_t ld_out, int64_t D, int S, double n_eff, int first, int deterministic,
+                          const float* eps, int64_t ld_eps, uint64_t seed, uint64_t stream_id,
+                          uint64_t stream_stride, int64_t elem0, bde_stream_t stream);
+
 /* K6: acc = first ? grad : acc + grad.   ivorn.py:120-127. */
 int bde_ivon_accumulate(float* acc, const float* grad, int64_t D, int first, bde_stream_t stream);
 

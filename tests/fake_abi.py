@@ -215,6 +215,15 @@ class FakeLib:
         _f32(delta_sum, D).copy_(ds)
         return 0
 
+    def bde_ivon_sample_batch(self, mean, prec, delta_sum, theta, ld_out, D, S, n_eff, first, deterministic, eps, ld_eps,
+                              seed, sid, stride, elem0, stream):
+        self.calls.append("ivon_sample_batch")
+        for s in range(S):
+            self.bde_ivon_sample(mean, prec, delta_sum, theta + 4 * s * ld_out, D, n_eff, first and s == 0, deterministic,
+                                 eps + 4 * s * ld_eps if eps else 0, seed, sid + s * stride, elem0, stream)
+            self.calls.pop()
+        return 0
+
     def bde_ivon_accumulate(self, acc, grad, D, first, stream):
         a = _f32(acc, D)
         a.copy_(_f32(grad, D) if first else a + _f32(grad, D))

@@ -730,6 +730,34 @@ def test_ivon_kernels_vs_oracle(ops, ew_variant, D):
     assert torch.equal(d_theta, d_mean) and d_dsum.eq(0).all()
 
 
+@pytest.mark.parametrize("S,first,det", [(1, True, False), (3, True, False), (4, False, False), (7, False, False), (3, True, True)])
+@pytest.mark.parametrize("D,mis", [(100_003, 0), (4099, 0), (777, 1), (3_000_000, 0)])
+def test_ivon_sample_batch_equals_single_draws(ops, S, first, det, D, mis):
+    """bde_ivon_sample_batch: draw s == bde_ivon_sample with stream_id + s * stride, and delta_sum ends as after S
+    single calls, bit for bit — Philox and injected noise, first / continuing accumulation, deterministic groups,
+    ragged D, unaligned views, D large enough for the TMA-staged single-draw kernel."""
+    g = torch.Generator().manual_seed(S * 13 + D)
+    def vec(scale=1.0, shift=0.0):
+        return (torch.randn(D + 8, generator=g) * scale + shift).cuda()[mis:mis + D]
+    mean, prec = vec(0.1), vec(1e-3, 0.02).abs_()
+    ld_out = D + (3 if mis else 0)
+    for injected in (False, True):
+        eps = torch.randn(S, D, generator=g).cuda() if injected else None
+        ds0 = vec(0.3)
+        ds_b, ds_s = ds0.clone(), ds0.clone()
+        out = torch.as_strided(torch.full((S * ld_out + 8,), float("nan"), device="cuda"), (S, D), (ld_out, 1), storage_offset=mis)
+        ops.ivon_sample_batch(mean, prec, ds_b, out, n_eff=768.0, first=first, deterministic=det, eps=eps, seed=7,
+                              stream_id=11, stream_stride=2)
+        one = torch.zeros(D + 8, device="cuda")[mis:mis + D]
+        for s_ in range(S):
+            ops.ivon_sample(mean, prec, ds_s, one, n_eff=768.0, first=first and s_ == 0, deterministic=det,
+                            eps=None if eps is None else eps[s_], seed=7, stream_id=11 + 2 * s_)
+            assert torch.equal(out[s_], one), (s_, injected)
+        assert torch.equal(ds_b, ds_s)
+        if S > 1 and not det:
+            assert not torch.equal(out[0], out[1])
+
+
 def test_ivon_sample_philox_matches_oracle_stream(ops, ew_variant):
     D = 100_003
     mean = torch.zeros(D, device="cuda")

@@ -564,6 +564,66 @@ def test_ivon_matches_reference(env, golden):
     assert opt.param_groups[0]["step"] == g["losses"].size
 
 
+@pytest.mark.parametrize("count,max_rows,two_groups", [(2, 99, False), (5, 99, True), (5, 2, True)])
+def test_ivon_presample_equals_sequential_draws(env, golden, count, max_rows, two_groups):
+    """presample(count): the batched K5 launch hands out exactly the draws — and leaves exactly the
+    delta_sum — of `count` single sample_parameters() calls, with injected noise (the reference's draw order over
+    calls and parameter groups) and with Philox streams, also when the buffer cap splits the request, with two
+    parameter groups (round-robin stream ids), and a step() afterwards behaves as if nothing had been presampled."""
+    g = golden("ivon_steps.npz")
+
+    def trained():
+        model = gm.make_mlp().to(env.dev)
+        gm.load_flat(model.parameters(), g["init"])
+        plist = list(model.parameters())
+        params = [{"params": plist[:2]}, {"params": plist[2:], "prior_prec": 20.0}] if two_groups else plist
+        opt = bde.iVONOptimizer(params, lr=1e-2, prior_prec=10.0, dataset_size=768, damping=1e-3, mc_samples=2)
+        noise.set_seed(5)
+        fwd, bwd = gm.mse_closures(model, env.t(g["xs"][0]), env.t(g["ys"][0]))
+        opt.step(fwd, bwd)    # non-trivial precision / mean
+        return model, opt
+
+    sizes = None
+    gen = torch.Generator().manual_seed(11)
+
+    def draws(batched, injected):
+        nonlocal sizes
+        model, opt = trained()
+        if sizes is None:
+            sizes = [ar["layout"].logical_size for ar in opt._arenas]
+        zs = [torch.randn(sizes[i % len(sizes)], generator=torch.Generator().manual_seed(100 + i))
+              for i in range(count * len(sizes))]
+        it = iter(zs)
+        if batched:
+            opt.presample_max_bytes = 4 * sum(ar["layout"].size for ar in opt._arenas) * max_rows
+            opt.presample(count)
+        noise.set_seed(1234)
+        out = []
+        with noise.inject((lambda kind, numel: next(it)) if injected else (lambda kind, numel: None)):
+            for _ in range(count):
+                opt.sample_parameters()
+                out.append(flat(model.parameters()).copy())
+        dsum = torch.cat([ar["rows"]["delta"][:1 << 30].reshape(-1) for ar in opt._arenas]).cpu().numpy().copy()
+        # a training step after prediction-time sampling: same result either way
+        noise.set_seed(99)
+        fwd, bwd = gm.mse_closures(model, env.t(g["xs"][1]), env.t(g["ys"][1]))
+        loss = opt.step(fwd, bwd).item()
+        noise.set_seed(None)
+        return out, dsum, loss, flat(model.parameters()).copy()
+
+    for injected in (True, False):
+        one = draws(False, injected)
+        bat = draws(True, injected)
+        for a, b in zip(one[0], bat[0]):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(one[1], bat[1])
+        assert one[2] == bat[2]
+        np.testing.assert_array_equal(one[3], bat[3])
+        assert any(not np.array_equal(one[0][0], x) for x in one[0][1:])
+    if env.fake:
+        assert env.calls("ivon_sample_batch") >= 1
+
+
 def test_ivon_state_dict_roundtrip(env, golden):
     g = golden("ivon_steps.npz")
     model, opt = build_ivon(env, g)
