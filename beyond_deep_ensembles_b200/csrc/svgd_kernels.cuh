@@ -964,6 +964,7 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
 // (see apply_row) on 4 sets.  n <= 12: 3 x 256 wins for plain K2 at n >= 8 (+3..5 %) and for the training-step form
 // at n >= 9, where a stage is large enough that the 8-stage ring still keeps ~150 KB in flight; the fused K2f forms
 // and small n stay on 1 x 512 (at n = 5 it is 10-25 % faster).
+constexpr int64_t kApplySmallTileMaxElems = 1500000000;  // n * row stride above which plain K2 goes back to 1 x 512
 __host__ __device__ constexpr bool apply_small_tiles(int n, int opt, bool next) {
     return n > 12 || (next && n >= 9) || (opt == kOptNone && n >= 8);
 }
@@ -1249,6 +1250,12 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
         constexpr int TS_ALT = !apply_small_tiles(N, OPT, NEXT) ? 3 : (N > 12 ? 7 - TS0 : 1);
         constexpr int TC_ALT = N > 12 ? 256 : 768 - TC;
         if (tuning().apply_tile_sets == TS_ALT) return launch_apply_tma<N, OPT, NEXT, TS_ALT, TC_ALT>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
+        if constexpr (!NEXT && OPT == kOptNone && N <= 12 && apply_small_tiles(N, OPT, NEXT)) {
+            // plain K2, same-box A/B at n = 10 (profiles/r01_geometry_vs_D.jsonl): 3 x 256 wins by 3-8 % up to D = 1e8 but
+            // loses 3-6 % from D = 2e8 on (rows 0.8 GB apart: half as many bytes per touched page as 512-column tiles)
+            if (tuning().apply_tile_sets == 0 && static_cast<int64_t>(N) * ldx > kApplySmallTileMaxElems)
+                return launch_apply_tma<N, OPT, NEXT, TS_ALT, TC_ALT>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
+        }
         return launch_apply_tma<N, OPT, NEXT, TS0, TC>(X, G, out, K, A, D, ldx, ldg, ldo, o, st, nd);
     }
     static int ctas_per_sm = 0;

@@ -196,6 +196,32 @@ def test_pairdist_variants_agree_with_oracle(ops, cuda_lib, variant, n, D):
     np.testing.assert_allclose(sc.A.cpu().numpy(), bw["A"].numpy(), rtol=RTOL, atol=ATOL)
 
 
+@pytest.mark.parametrize("tile_sets", [1, 3])
+@pytest.mark.parametrize("n,D", [(10, 1_200_003), (8, 900_001), (12, 500_000)])
+def test_staged_plain_apply_geometries(ops, cuda_lib, tile_sets, n, D):
+    """Staged plain K2 at n <= 12: both consumer geometries (1 set x 512 columns, 3 sets x 256 columns — the library
+    picks by n and by the row stride) against the oracle and bit for bit against the direct-LDG kernel."""
+    X, G = particles(n, D, seed=5 * n + D)
+    ld = (D + 3) // 4 * 4
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    dX, dG = dev_matrix(X, ld), dev_matrix(G, ld)
+    ops.svgd_pairdist_bandwidth(dX, sc, 0.01, 1.0, 768.0)
+    outs = {}
+    for variant in (1, 2):
+        dOut = dev_matrix(torch.full_like(X, float("nan")), ld)
+        cuda_lib.bde_tune(b"apply_variant", variant)
+        cuda_lib.bde_tune(b"apply_tile_sets", tile_sets)
+        try:
+            ops.svgd_apply(dX, dG, dOut, sc)
+            ops.svgd_apply(dX, dG, dOut, sc)
+        finally:
+            cuda_lib.bde_tune(b"apply_variant", 0)
+            cuda_lib.bde_tune(b"apply_tile_sets", 0)
+        outs[variant] = dOut.cpu()
+    assert torch.equal(outs[1], outs[2])
+    np.testing.assert_allclose(outs[2].numpy(), O.svgd_apply(X, G, sc.K.cpu(), sc.A.cpu()).numpy(), rtol=RTOL, atol=ATOL)
+
+
 def test_apply_rejects_overlap(ops):
     from beyond_deep_ensembles_b200 import _lib
     n, D = 4, 64
