@@ -113,6 +113,12 @@ class LastLayerBayesianOptimizer(BayesianOptimizer):
     def sample_parameters(self):
         self.ll_bayesian_optimizer.sample_parameters()
 
+    def presample(self, count):
+        """Forward DeepEnsemble.predict's batch announcement to the Bayesian part (no-op if it cannot batch)."""
+        announce = getattr(self.ll_bayesian_optimizer, "presample", None)
+        if announce is not None:
+            announce(count)
+
     def state_dict(self) -> Dict[str, Any]:
         return {part: getattr(self, part).state_dict() for part in self._PARTS}
 
