@@ -4,12 +4,15 @@ Mirrors the reference's public surface (src/algos/algo.py:5-133): same class nam
 names, argument meaning and error behaviour, so training loops written against the reference
 (`loss = optimizer.step(forward_closure, backward_closure, grad_scaler=scaler)`,
 `optimizer.complete_epoch()`, `optimizer.sample_parameters()`, `get_base_optimizer()`,
-`init_grad_scaler()`) run unchanged.  Nothing in this file touches parameter data.
+`init_grad_scaler()`) run unchanged.  The only arithmetic reachable from this file is the gradient gather of
+`_unscale_and_gather` (one C-ABI launch).
 """
 from __future__ import annotations
 
 from typing import Any, Dict
 
+import torch
+from torch.amp.grad_scaler import OptState
 from torch.optim import Optimizer
 
 
@@ -65,6 +68,50 @@ class BayesianOptimizer(Optimizer):
         if _scaler_active(grad_scaler):
             key = id(optimizer if optimizer is not None else self)
             grad_scaler._per_optimizer_states[key]["stage"] = stage
+
+    #: with an active GradScaler, fold unscale_ + the non-finite check into the gradient gather
+    fuse_unscale_into_gather = True
+
+    def _unscale_and_gather(self, grad_scaler, optimizer, row, grads, layout, accumulate=False):
+        """Gradients of the pass that just ran -> the flat arena `row` (gather, or gather-add).  Returns what
+        `_prepare_and_check_grads` returns.
+
+        Without a scaler this is one multi-tensor launch.  With an active GradScaler the reference first runs
+        `grad_scaler.unscale_(optimizer)` — a read-modify-write pass over every gradient plus the non-finite check
+        (algo.py:65-73) — and gathers afterwards; here both happen in the gather launch: the values are multiplied
+        by 1/scale on their way into the arena and `found_inf` is raised on the device, and the scaler's
+        per-optimizer record is left exactly as `unscale_` leaves it (stage UNSCALED, found_inf_per_device), so
+        `grad_scaler.step()` / `update()` behave as before.  The `.grad` tensors themselves stay scaled; the
+        optimizers replace them before anything reads them again."""
+        from . import ops
+        opt = self if optimizer is None else optimizer
+        mode = 1 if accumulate else 0
+
+        def gather(**kw):
+            try:
+                ops.multi_tensor_copy(row, grads, layout.offsets, mode=mode, table=layout.copy_table, **kw)
+            except ValueError:   # e.g. channels_last gradients: gather from contiguous copies
+                ops.multi_tensor_copy(row, [g.contiguous() for g in grads], layout.offsets, mode=mode,
+                                      table=layout.copy_table, **kw)
+
+        if _scaler_active(grad_scaler) and self.fuse_unscale_into_gather:
+            record = grad_scaler._per_optimizer_states[id(opt)]
+            if record["stage"] is OptState.UNSCALED:
+                raise RuntimeError("unscale_() has already been called on this optimizer since the last update().")
+            if record["stage"] is OptState.STEPPED:
+                raise RuntimeError("unscale_() is being called after step().")
+            scale = grad_scaler._scale
+            assert scale is not None, "call init_grad_scaler(grad_scaler) before the first step"
+            inv_scale = scale.double().reciprocal().float()
+            found_inf = torch.full((), 0.0, dtype=torch.float32, device=scale.device)
+            gather(inv_scale=inv_scale, found_inf=found_inf)
+            record["found_inf_per_device"] = {found_inf.device: found_inf}
+            record["stage"] = OptState.UNSCALED
+            return sum(flag.item() for flag in self.state["found_inf_per_device"].values()) == 0   # algo.py:73, literally
+        usable = self._prepare_and_check_grads(grad_scaler, optimizer)
+        if usable:
+            gather()
+        return usable
 
     # ---- parameter access (algo.py:57-63) ----
     def _params(self):

@@ -43,8 +43,20 @@ __device__ __forceinline__ int find_tensor(const MtcTable& t, int64_t e) {
     return lo;
 }
 
+// inv_scale / found_inf (both device scalars, may be null): the gather modes multiply by *inv_scale and raise
+// *found_inf to 1 on any non-finite SOURCE value — torch's _amp_foreach_non_finite_check_and_unscale_ (what
+// GradScaler.unscale_ runs, algo.py:65-73) folded into the gather, so unscaling costs no extra pass.
+__device__ __forceinline__ float4 mtc_unscale(float4 v, const float* inv_scale, float* found_inf) {
+    if (inv_scale == nullptr) return v;
+    if (!(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w))) *found_inf = 1.0f;
+    const float s = *inv_scale;
+    if (s == 1.0f) return v;
+    return make_float4(__fmul_rn(v.x, s), __fmul_rn(v.y, s), __fmul_rn(v.z, s), __fmul_rn(v.w, s));
+}
+
 __global__ void __launch_bounds__(kEwThreads)
-multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTable tab, int mode) {
+multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTable tab, int mode,
+                         const float* __restrict__ inv_scale, float* __restrict__ found_inf) {
     const int64_t base = tab.begin & ~static_cast<int64_t>(3);
     BDE_QUAD_LOOP(q, tab.end - base) {
         const int64_t e0 = base + (q << 2);
@@ -57,7 +69,7 @@ multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTa
             if (mode == 2) {
                 stg_stream_f4(tp + local, ld_f4(flat + e0));
             } else {
-                float4 v = ld_f4(tp + local);
+                float4 v = mtc_unscale(ld_f4(tp + local), inv_scale, found_inf);
                 if (mode == 1) {
                     const float4 a = ld_f4(flat + e0);
                     v = make_float4(__fadd_rn(a.x, v.x), __fadd_rn(a.y, v.y), __fadd_rn(a.z, v.z), __fadd_rn(a.w, v.w));
@@ -72,12 +84,17 @@ multi_tensor_copy_kernel(float* __restrict__ flat, const __grid_constant__ MtcTa
                 const int64_t l2 = e - tab.off[tt];
                 if (l2 < 0 || l2 >= tab.size[tt]) continue;  // padding between tensors
                 float* p2 = reinterpret_cast<float*>(tab.ptr[tt]);
-                if (mode == 2)
+                if (mode == 2) {
                     p2[l2] = flat[e];
-                else if (mode == 1)
-                    flat[e] = __fadd_rn(flat[e], p2[l2]);
-                else
-                    flat[e] = p2[l2];
+                } else {
+                    float v = p2[l2];
+                    if (inv_scale != nullptr) {
+                        if (!isfinite(v)) *found_inf = 1.0f;
+                        const float s = *inv_scale;
+                        if (s != 1.0f) v = __fmul_rn(v, s);
+                    }
+                    flat[e] = (mode == 1) ? __fadd_rn(flat[e], v) : v;
+                }
             }
         }
     }
@@ -145,8 +162,8 @@ extern "C" int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint6
                      elem0 >> 2, aligned16(out) ? 1 : 0);
 }
 
-extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
-                                     const int64_t* sizes_host, int count, int mode, bde_stream_t stream) {
+static int mtc_launch(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host, const int64_t* sizes_host,
+                      int count, int mode, const float* inv_scale, float* found_inf, bde_stream_t stream) {
     if (!flat || !ptrs_host || !offsets_host || !sizes_host || count < 1 || mode < 0 || mode > 2)
         return BDE_ERR_INVALID_ARG;
     for (int i = 0; i < count; ++i) {
@@ -165,8 +182,20 @@ extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, con
         tab.end = tab.off[tab.count - 1] + tab.size[tab.count - 1];
         if (tab.end <= tab.begin) continue;
         const int rc = launch_ew(multi_tensor_copy_kernel, tab.end - (tab.begin & ~static_cast<int64_t>(3)),
-                                 static_cast<cudaStream_t>(stream), flat, tab, mode);
+                                 static_cast<cudaStream_t>(stream), flat, tab, mode, inv_scale, found_inf);
         if (rc != BDE_OK) return rc;
     }
     return BDE_OK;
+}
+
+extern "C" int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
+                                     const int64_t* sizes_host, int count, int mode, bde_stream_t stream) {
+    return mtc_launch(flat, ptrs_host, offsets_host, sizes_host, count, mode, nullptr, nullptr, stream);
+}
+
+extern "C" int bde_multi_tensor_unscale_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
+                                             const int64_t* sizes_host, int count, int mode, const float* inv_scale,
+                                             float* found_inf, bde_stream_t stream) {
+    if (!inv_scale || !found_inf || mode > 1) return BDE_ERR_INVALID_ARG;
+    return mtc_launch(flat, ptrs_host, offsets_host, sizes_host, count, mode, inv_scale, found_inf, stream);
 }

@@ -85,10 +85,8 @@ class iVONOptimizer(BayesianOptimizer):
             else:
                 acc_loss += loss
 
-            if not self._prepare_and_check_grads(grad_scaler):
+            if not self._store_gradients(grad_scaler):   # unscale (if AMP) + gather-accumulate, one launch per group
                 return None
-
-            self._store_gradients()
         acc_loss /= self.mc_samples
 
         with torch.no_grad():
@@ -193,23 +191,43 @@ class iVONOptimizer(BayesianOptimizer):
     def get_base_optimizer(self):
         return self
 
-    def _store_gradients(self):
-        """acc_grad (+)= grad, gathered straight from the scattered .grad tensors (ivorn.py:120-127)."""
-        for group, ar in zip(self.param_groups, self._arenas):
+    def _store_gradients(self, grad_scaler=None):
+        """acc_grad (+)= grad, gathered straight from the scattered .grad tensors (ivorn.py:120-127); under AMP the
+        same launch unscales and checks for non-finite values (ivorn.py:60, algo.py:65-73).  False = skip the step."""
+        usable = True
+        for gi, (group, ar) in enumerate(zip(self.param_groups, self._arenas)):
             L, r, v = ar["layout"], ar["rows"], ar["views"]
             grads = [param.grad for param in group["params"]]
             if any(g is None for g in grads):
                 raise TypeError("iVON needs a gradient for every parameter after backward_closure")
             first = ar.get("n_grads", 0) == 0
-            mode = 0 if first else 1
-            try:
-                ops.multi_tensor_copy(r["acc_grad"], grads, L.offsets, mode=mode, table=L.copy_table)
-            except ValueError:   # e.g. channels_last gradients: gather from contiguous copies
-                ops.multi_tensor_copy(r["acc_grad"], [g.contiguous() for g in grads], L.offsets, mode=mode, table=L.copy_table)
+            if gi == 0:
+                usable = self._unscale_and_gather(grad_scaler, None, r["acc_grad"], grads, L, accumulate=not first)
+                if not usable:
+                    return False
+            else:
+                # further groups share the scaler record the first group just wrote: gather with the same factor
+                self._gather_more(grad_scaler, r["acc_grad"], grads, L, accumulate=not first)
             ar["n_grads"] = ar.get("n_grads", 0) + 1
             if first:
                 for k, param in enumerate(group["params"]):
                     self.state[param]["acc_grad"] = v["acc_grad"][k]
+        return usable
+
+    def _gather_more(self, grad_scaler, row, grads, layout, accumulate):
+        kw = {}
+        if grad_scaler is not None and grad_scaler.is_enabled():
+            if self.fuse_unscale_into_gather:
+                record = grad_scaler._per_optimizer_states[id(self)]
+                kw = dict(inv_scale=grad_scaler._scale.double().reciprocal().float(),
+                          found_inf=record["found_inf_per_device"][row.device])
+            # else: unscale_ of the first group's call already unscaled every .grad of this optimizer in place
+        mode = 1 if accumulate else 0
+        try:
+            ops.multi_tensor_copy(row, grads, layout.offsets, mode=mode, table=layout.copy_table, **kw)
+        except ValueError:
+            ops.multi_tensor_copy(row, [g.contiguous() for g in grads], layout.offsets, mode=mode,
+                                  table=layout.copy_table, **kw)
 
     # ------------------------------------------------------------------ checkpoints
     def load_state_dict(self, state_dict):

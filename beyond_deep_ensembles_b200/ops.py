@@ -441,11 +441,14 @@ class CopyTable:
         self.sizes_p = C.cast(self.sizes, C.c_void_p)
 
 
-def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int, table: CopyTable | None = None) -> None:
+def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int, table: CopyTable | None = None,
+                      inv_scale: torch.Tensor | None = None, found_inf: torch.Tensor | None = None) -> None:
     """Gather (mode 0), gather-add (1) or scatter (2) between `tensors` and a flat arena row.
 
     offsets: element offsets of each tensor inside flat_row (ascending); `table` (a CopyTable for the same
-    offsets and tensor sizes) skips rebuilding the constant part of the argument tables."""
+    offsets and tensor sizes) skips rebuilding the constant part of the argument tables.  With `inv_scale` /
+    `found_inf` (fp32 device scalars) the gather is fused with GradScaler.unscale_: values are multiplied by
+    inv_scale on the way and found_inf is raised on any non-finite source value."""
     count = len(tensors)
     if count == 0:
         return
@@ -465,8 +468,16 @@ def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int, table
             raise ValueError("multi_tensor_copy: tensor size does not match the copy table")
         ptrs.append(t.data_ptr())
     cptrs = (C.c_uint64 * count)(*ptrs)
-    _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(cptrs, C.c_void_p), table.offs_p, table.sizes_p,
-              count, int(mode), _s(flat_row))
+    if inv_scale is None:
+        _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(cptrs, C.c_void_p), table.offs_p, table.sizes_p,
+                  count, int(mode), _s(flat_row))
+        return
+    require_cuda(inv_scale, found_inf)
+    _lib.require_f32(inv_scale, found_inf)
+    if inv_scale.numel() != 1 or found_inf.numel() != 1 or mode not in (0, 1):
+        raise ValueError("unscaling gather: inv_scale / found_inf must be scalars and the mode a gather")
+    _lib.call("bde_multi_tensor_unscale_copy", flat_row.data_ptr(), C.cast(cptrs, C.c_void_p), table.offs_p,
+              table.sizes_p, count, int(mode), inv_scale.data_ptr(), found_inf.data_ptr(), _s(flat_row))
 
 
 # --------------------------------------------------------------------------------------

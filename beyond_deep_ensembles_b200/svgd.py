@@ -115,9 +115,8 @@ class SVGDOptimizer(BayesianOptimizer):
             loss = forward_closure()
             total_loss += loss.detach()
             backward_closure(loss)
-            if not self._prepare_and_check_grads(grad_scaler, base):
+            if not self._store_grads(particle_idx, plist, grad_scaler, base):   # unscale (if AMP) + gather, one launch
                 return None
-            self._store_grads(particle_idx, plist)
 
         with torch.no_grad():
             hyper = (self.state["__l2_reg"], self.state["__kernel_grad_scale"], self.state["__dataset_size"])
@@ -197,16 +196,13 @@ class SVGDOptimizer(BayesianOptimizer):
         for param, view in zip(self._params(), self._xviews[particle_idx]):
             param.data = view
 
-    def _store_grads(self, particle_idx, plist):
-        """Gather this particle's gradients into row `particle_idx` of G (one launch)."""
+    def _store_grads(self, particle_idx, plist, grad_scaler=None, base=None):
+        """This particle's gradients -> row `particle_idx` of G in one launch; under AMP the launch also does what
+        `grad_scaler.unscale_(base)` does (svgd.py:78-84, algo.py:65-73).  False = do not use the gradients."""
         grads = [p.grad for p in plist]
         if any(g is None for g in grads):
             raise AttributeError("SVGD needs a gradient for every parameter after backward_closure")
-        row, L = self._G[particle_idx], self._layout
-        try:
-            ops.multi_tensor_copy(row, grads, L.offsets, mode=0, table=L.copy_table)
-        except ValueError:   # e.g. channels_last gradients: gather from contiguous copies
-            ops.multi_tensor_copy(row, [g.contiguous() for g in grads], L.offsets, mode=0, table=L.copy_table)
+        return self._unscale_and_gather(grad_scaler, base, self._G[particle_idx], grads, self._layout)
 
     def get_base_optimizer(self):
         return self.state["__base_optimizer"]

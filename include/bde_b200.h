@@ -383,6 +383,16 @@ int bde_philox_normal(float* out, int64_t count, uint64_t seed, uint64_t stream_
 int bde_multi_tensor_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
                           const int64_t* sizes_host, int count, int mode, bde_stream_t stream);
 
+/*
+ * The gather modes (0, 1) of bde_multi_tensor_copy fused with GradScaler.unscale_ (algo.py:65-73, i.e. torch's
+ * _amp_foreach_non_finite_check_and_unscale_): flat (+)= tensor * *inv_scale, and *found_inf is raised to 1.0f if
+ * any source value is not finite.  inv_scale / found_inf are DEVICE scalars (no host sync); the source tensors
+ * are left untouched (still scaled).  SURVEY §8 f2.
+ */
+int bde_multi_tensor_unscale_copy(float* flat, const uint64_t* ptrs_host, const int64_t* offsets_host,
+                                  const int64_t* sizes_host, int count, int mode, const float* inv_scale,
+                                  float* found_inf, bde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

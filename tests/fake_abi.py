@@ -347,6 +347,26 @@ class FakeLib:
                 t.copy_(f)
         return 0
 
+    def bde_multi_tensor_unscale_copy(self, flat, ptrs, offsets, sizes, count, mode, inv_scale, found_inf, stream):
+        self.calls.append("mtc_unscale")
+        P = np.ctypeslib.as_array((C.c_uint64 * count).from_address(_addr(ptrs)))
+        Of = np.ctypeslib.as_array((C.c_int64 * count).from_address(_addr(offsets)))
+        Sz = np.ctypeslib.as_array((C.c_int64 * count).from_address(_addr(sizes)))
+        inv, found = _f32(inv_scale, 1), _f32(found_inf, 1)
+        for p, o, s in zip(P, Of, Sz):
+            if s == 0:
+                continue
+            t = _f32(int(p), int(s))
+            f = _f32(flat + 4 * int(o), int(s))
+            if not torch.isfinite(t).all():
+                found.fill_(1.0)
+            v = t * inv
+            if mode == 0:
+                f.copy_(v)
+            else:
+                f.add_(v)
+        return 0
+
 
 def install(monkeypatch):
     """Route the package's C-ABI calls to the oracle-backed double (CPU tests only)."""

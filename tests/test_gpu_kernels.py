@@ -986,6 +986,40 @@ def test_multi_tensor_copy_modes(ops):
     assert torch.equal(flat, torch.cat([t.reshape(-1) for t in tensors]))
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("scale,bad", [(1024.0, None), (1.0, None), (65536.0, "inf"), (8.0, "nan")])
+def test_multi_tensor_unscale_copy_vs_torch(ops, mode, scale, bad):
+    """bde_multi_tensor_unscale_copy == GradScaler's _amp_foreach_non_finite_check_and_unscale_ followed by the
+    gather / gather-add, bit for bit; found_inf raised exactly when a source value is not finite; sources untouched;
+    ragged sizes, an unaligned tensor, more tensors than one kernel-parameter table holds (112)."""
+    g = torch.Generator().manual_seed(17)
+    sizes = [1, 3, 4, 5, 64, 1000, 4097] + [7] * 120
+    tensors = [torch.randn(sz, generator=g).cuda() for sz in sizes]
+    tensors[5] = torch.randn(1001, generator=g).cuda()[1:]          # 4-byte-aligned only
+    if bad:
+        tensors[3][2] = float(bad)
+    before = [t.clone() for t in tensors]
+    offsets, off = [], 0
+    for sz in sizes:
+        offsets.append(off)
+        off += -(-sz // 64) * 64
+    flat0 = torch.randn(off, generator=g).cuda()
+    inv = torch.tensor(1.0 / scale, device="cuda")
+    found = torch.zeros((), device="cuda")
+    flat = flat0.clone()
+    ops.multi_tensor_copy(flat, tensors, offsets, mode, inv_scale=inv, found_inf=found)
+    # torch's own kernel on copies, then the plain gather
+    ref_t = [t.clone() for t in tensors]
+    ref_found = torch.zeros(1, device="cuda")
+    torch._amp_foreach_non_finite_check_and_unscale_(ref_t, ref_found, inv)
+    ref = flat0.clone()
+    ops.multi_tensor_copy(ref, ref_t, offsets, mode)
+    assert found.item() == ref_found.item() == (1.0 if bad else 0.0)
+    assert torch.equal(torch.nan_to_num(flat, nan=123.0), torch.nan_to_num(ref, nan=123.0))
+    for t, b in zip(tensors, before):
+        assert torch.equal(torch.nan_to_num(t, nan=5.0), torch.nan_to_num(b, nan=5.0))
+
+
 def test_host_buffer_step_matches_device_step(ops):
     """The end-to-end host-buffer path (chunked H2D -> K1 .. K1b -> K2 -> D2H pipeline) equals the
     oracle, for a ragged D, a chunk size that does not divide it, and pageable as well as pinned memory."""

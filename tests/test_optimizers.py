@@ -325,6 +325,58 @@ def test_svgd_grad_scaler_protocol(env, golden):
     assert "found_inf_per_device" in opt.state  # the reference leaves this key behind (algo.py:73)
 
 
+@pytest.mark.parametrize("poison", [False, True], ids=["finite", "inf-grad"])
+@pytest.mark.parametrize("algo", ["svgd", "ivon"])
+def test_fused_unscale_gather_equals_unscale_then_gather(env, golden, algo, poison):
+    """with an active GradScaler the gradient gather also does what GradScaler.unscale_ does.  Two
+    steps + scaler.update() with the fused gather and with the literal unscale_()-then-gather order give identical
+    states, scaler scales and skip decisions — also when a gradient is inf (the step of that pass is skipped by the
+    scaler exactly as in the reference)."""
+    g = golden("svgd_steps.npz" if algo == "svgd" else "ivon_steps.npz")
+
+    def run(fused):
+        if algo == "svgd":
+            model, opt = build_svgd(env, g)
+        else:
+            model, opt = build_ivon(env, g)
+        opt.fuse_unscale_into_gather = fused
+        scaler = torch.amp.GradScaler(env.dev, init_scale=1024.0, growth_interval=1)
+        opt.init_grad_scaler(scaler)
+        noise.set_seed(21)
+        calls = {"n": 0}
+        for s in range(2):
+            x, y = env.t(g["xs"][s]), env.t(g["ys"][s])
+
+            def fwd():
+                return ((model(x).squeeze(-1) - y) ** 2).mean()
+
+            def bwd(loss):
+                scaler.scale(loss).backward()
+                calls["n"] += 1
+                if poison and calls["n"] == 2:
+                    next(iter(model.parameters())).grad.view(-1)[0] = float("inf")
+
+            opt.step(fwd, bwd, grad_scaler=scaler)
+            scaler.update()
+        noise.set_seed(None)
+        if algo == "svgd":
+            state = np.stack([flat(opt._params_for_particle(i)) for i in range(10)])
+        else:
+            st = [opt.state[p] for p in model.parameters()]
+            state = np.concatenate([torch.cat([x_[k].reshape(-1) for x_ in st]).cpu().numpy()
+                                    for k in ("mean", "momentum", "precision")])
+        return state, float(scaler.get_scale())
+
+    a, scale_a = run(True)
+    if env.fake:
+        assert env.calls("mtc_unscale") > 0 and env.calls("mtc") == 0
+    b, scale_b = run(False)
+    if env.fake:
+        assert env.calls("mtc") > 0
+    np.testing.assert_array_equal(a, b)
+    assert scale_a == scale_b
+
+
 def test_rbf_function(env, golden):
     g = golden("rbf.npz")
     X = env.t(g["n10_D501_X"])
