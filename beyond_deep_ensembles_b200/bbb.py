@@ -92,7 +92,7 @@ class BBBOptimizer(BayesianOptimizer):
         # goes into ONE multi-tensor launch per prior (value) + one in backward (all gradients); anything
         # else — a foreign prior object, a parameter whose KL is a user-supplied callable, non-contiguous
         # storage — is evaluated per tensor through its own get_parameter_kl.
-        total_kl_loss = torch.tensor(0.0, device=self._params_device())
+        total_kl_loss = torch.zeros((), device=self._params_device())   # no host-to-device copy
         batches = {}   # id(prior) -> (prior, [(mean, rho)])
         deterministic = []
         for group in self.param_groups:

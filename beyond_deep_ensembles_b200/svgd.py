@@ -106,7 +106,7 @@ class SVGDOptimizer(BayesianOptimizer):
         n = self.state["__particle_count"]
         base = self.state["__base_optimizer"]
         plist = list(self._params())
-        total_loss = torch.tensor(0.0, device=self._params_device())
+        total_loss = torch.zeros((), device=self._params_device())   # no host-to-device copy
         for particle_idx in range(n):
             self._set_grad_scaler_state(grad_scaler, OptState.READY, base)
             self._use_particle(particle_idx)
