@@ -41,10 +41,14 @@ struct Tuning {
     int apply_ctas_per_sm = 0;
     int ew_ctas_per_sm = 0;
     int apply_variant = 0;     // 0 auto, 1 direct-LDG kernel, 2 TMA-staged kernel
-    int pairdist_variant = 0;  // same for K1
+    int pairdist_variant = 0;  // same for K1; 3 = centred-Gram kernel (n = 16 / 20), 4 = Gram + forced redo (tests)
     int ew_variant = 0;        // same for the elementwise family (ew_tma.cuh)
     int apply_tile_sets = 0;   // staged K2: alternative consumer geometry (0 = default; see launch_apply_opt)
     int swag_batch = 0;        // draws per pass of the batched SWAG sampler (0 = default 16; 2, 4, 8, 16)
+    int gram_pairing = 0;      // centred-Gram K1: warp -> pair-group mapping (svgd_gram.cuh:gram_warp_role)
+    int gram_fold = 0;         // Gram K1 register budget: 0 auto, 1 producer warpgroup + setmaxnreg (SHIFT), 2 plain ninth warp
+    int gram_l2_promotion = 0; // tensor-map L2 promotion of the Gram kernel's tile loads: 0 none, 1 64 B, 2 128 B, 3 256 B
+    int gram_guard_x1000 = 0;  // centred-Gram K1: acceptance bound (S_ii + S_jj) / d_ij in 1/1000 (0 = default 32.0; 1 forces the exact redo)
 };
 Tuning& tuning();
 
@@ -201,7 +205,8 @@ struct WsHeader {                   // first kWsHeaderBytes of every reduction w
     unsigned int ticket;            // CTA arrival counter (left at zero by every launch)
     int peer_world;                 // 0 / 1: workspace not attached, plain single-GPU reduction
     int peer_rank;
-    int pad;
+    int redo;                       // set by the centred-Gram K1 (svgd_gram.cuh) when its cancellation guard fails: the
+                                    // direct K1 enqueued behind it (only_if_redo) then recomputes exact distances
     PeerBuf* peer[kPeerMaxRanks];   // peer[r] = rank r's exchange buffer mapped into this process
 };
 constexpr size_t kWsHeaderBytes = 256;

@@ -1,6 +1,7 @@
 // svgd.cu — SVGD posterior update on sm_100a: generic kernels, K1b, dispatch and C-ABI.
 // Kernel templates live in svgd_kernels.cuh; reference arithmetic: src/algos/svgd.py:14-32, :83-97.
 #include "svgd_kernels.cuh"
+#include "svgd_gram.cuh"
 
 namespace bde {
 
@@ -117,13 +118,15 @@ svgd_apply_opt_scalar_kernel(float* X, const float* __restrict__ G, const float*
 
 #define X_(N_)                                                                                                     \
     extern template int launch_pairdist<N_>(const float*, int64_t, int64_t, double*, int, void*, int,              \
-                                            const BandwidthParams&, cudaStream_t);                                 \
+                                            const BandwidthParams&, cudaStream_t, int);                                 \
     extern template int launch_apply<N_>(const float*, const float*, float*, const float*, const float*, int64_t, \
                                          int64_t, int64_t, int64_t, cudaStream_t);                           \
     extern template int launch_apply_fused<N_>(float*, const float*, const float*, const float*, int64_t, int64_t, \
                                                int64_t, const BaseOptParams&, cudaStream_t, const NextDistParams*);
 BDE_FOR_EACH_N(X_)
 #undef X_
+extern template int launch_pairgram<16>(const float*, int64_t, int64_t, double*, void*, int, const BandwidthParams&, cudaStream_t);
+extern template int launch_pairgram<20>(const float*, int64_t, int64_t, double*, void*, int, const BandwidthParams&, cudaStream_t);
 
 static bool has_fast_path(int n) {
     switch (n) {
@@ -171,10 +174,21 @@ int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, in
         }
         return BDE_OK;
     }
+    // n = 16 / 20, large D, K1b fused: centred-Gram kernel, with the direct kernel enqueued behind it as the exact
+    // recomputation that only runs when the Gram kernel's cancellation guard raised `redo` (svgd_gram.cuh)
+    int only_if_redo = 0;
+    if ((n == 16 || n == 20) && fuse && !accumulate && D <= 0x7fffffffLL &&
+        (tuning().pairdist_variant == 3 ||
+         (tuning().pairdist_variant == 0 && D >= 4 * static_cast<int64_t>(kGramTileCols) * sm_count_cached()))) {
+        const int rc = n == 16 ? launch_pairgram<16>(X, D, ld, dist, ws, fuse, bp, st)
+                               : launch_pairgram<20>(X, D, ld, dist, ws, fuse, bp, st);
+        if (rc != BDE_OK) return rc;
+        only_if_redo = 1;
+    }
     switch (n) {
 #define X_(N_) \
     case N_:   \
-        return launch_pairdist<N_>(X, D, ld, dist, accumulate, ws, fuse, bp, st);
+        return launch_pairdist<N_>(X, D, ld, dist, accumulate, ws, fuse, bp, st, only_if_redo);
         BDE_FOR_EACH_N(X_)
 #undef X_
         default:

@@ -384,7 +384,9 @@ __device__ __forceinline__ void bandwidth_device(const double* dist, int n, cons
 template <int N>
 __global__ void __launch_bounds__(pairdist_tpb(N) * pair_groups(N))
 svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double* __restrict__ dist, int accumulate,
-                     void* ws, int fuse_bandwidth, BandwidthParams bp) {
+                     void* ws, int fuse_bandwidth, BandwidthParams bp, int only_if_redo) {
+    // enqueued behind the centred-Gram kernel: nothing to do unless its guard asked for exact distances
+    if (only_if_redo && reinterpret_cast<const WsHeader*>(ws)->redo == 0) return;
     constexpr int P = pair_count(N);
     constexpr int PG = pairs_per_group(N);
     constexpr int NG = pair_groups(N);
@@ -539,7 +541,8 @@ __device__ __forceinline__ void pairdist_tma_dispatch(int g, const float* X, int
 template <int N>
 __global__ void __launch_bounds__(pd_consumers(N) + 32, 1)
 svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double* __restrict__ dist, int accumulate,
-                         void* ws, int fuse_bandwidth, BandwidthParams bp) {
+                         void* ws, int fuse_bandwidth, BandwidthParams bp, int only_if_redo) {
+    if (only_if_redo && reinterpret_cast<const WsHeader*>(ws)->redo == 0) return;
     constexpr int P = pair_count(N);
     constexpr int PG = pairs_per_group(N);
     constexpr int NG = pair_groups(N);
@@ -1166,14 +1169,14 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
 // ---------------------------------------------------------------------------------
 template <int N>
 int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int accumulate, void* ws, int fuse,
-                    const BandwidthParams& bp, cudaStream_t st) {
+                    const BandwidthParams& bp, cudaStream_t st, int only_if_redo) {
     constexpr int TPB = pairdist_tpb(N);
     constexpr int NG = pair_groups(N);
     {
         constexpr int TC = pd_tile_cols(N);
         const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
         int variant = tuning().pairdist_variant;
-        if (variant == 0) variant = (ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+        if (variant == 0 || variant > 2) variant = (ntiles >= 2 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
         if (variant == 2) {
             constexpr int smem = pd_stages(N) * pd_stage_bytes(N);
             static bool configured = false;
@@ -1185,7 +1188,7 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
             if (grid > ntiles) grid = ntiles;
             if (grid < 1) grid = 1;
             svgd_pairdist_tma_kernel<N><<<static_cast<unsigned>(grid), pd_consumers(N) + 32, smem, st>>>(X, D, ld, dist, accumulate,
-                                                                                                 ws, fuse, bp);
+                                                                                                 ws, fuse, bp, only_if_redo);
             BDE_CHECK_LAUNCH();
             return BDE_OK;
         }
@@ -1207,7 +1210,7 @@ int launch_pairdist(const float* X, int64_t D, int64_t ld, double* dist, int acc
     if (want > cap) want = cap;
     if (want < 1) want = 1;
     svgd_pairdist_kernel<N><<<dim3(static_cast<unsigned>(want)), dim3(TPB, NG), 0, st>>>(X, D, ld, dist, accumulate, ws,
-                                                                                      fuse, bp);
+                                                                                      fuse, bp, only_if_redo);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }

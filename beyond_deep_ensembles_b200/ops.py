@@ -77,6 +77,11 @@ class SvgdScratch:
     def ws_bytes(self) -> int:
         return self.ws.numel() * 8
 
+    def exact_redo(self) -> bool:
+        """Did the last centred-Gram K1 launch on this scratch (n = 16 / 20, csrc/svgd_gram.cuh) fail its
+        cancellation guard, i.e. were the distances recomputed by the direct kernel?  (WsHeader.redo; syncs.)"""
+        return ((int(self.ws[1].item()) >> 32) & 0xFFFFFFFF) != 0
+
 
 def svgd_pairdist(X: torch.Tensor, sc: SvgdScratch, accumulate: bool = False) -> torch.Tensor:
     """K1: sc.dist (+)= squared pair distances over X's columns (svgd.py:15)."""

@@ -59,10 +59,15 @@ def test_sass_uses_packed_fp32(built_lib):
     import shutil
     import subprocess
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN3bde20svgd_pairdist_kernelILi10EEEvPKfllPdiPviNS_15BandwidthParamsE",
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN3bde20svgd_pairdist_kernelILi10EEEvPKfllPdiPviNS_15BandwidthParamsEi",
                            str(built_lib)], capture_output=True, text=True).stdout
     assert sass.count("FFMA2") >= 90 and sass.count("FADD2") >= 90, "pairdist<10> lost its packed-fp32 inner loop"
     assert "LDG.E.128" in sass or "LDG.E.ENL2.128" in sass or ".128" in sass
+    # centred-Gram K1 (n = 20): 190 entries x 2 FFMA2 per column quad, fed by one tensor-map TMA load per tile
+    sass = subprocess.run([cuobjdump, "-sass", "-fun",
+                           "_ZN3bde20svgd_pairgram_kernelILi20ELb1EEEv14CUtensorMap_stlPdPviNS_15BandwidthParamsEdi",
+                           str(built_lib)], capture_output=True, text=True).stdout
+    assert sass.count("FFMA2") >= 380 and "UTMALDG.2D" in sass, "pairgram<20> lost its packed inner loop / TMA tensor load"
 
 
 def test_no_fallback_when_library_missing(monkeypatch, tmp_path):

@@ -1036,3 +1036,101 @@ def test_host_buffer_step_matches_device_step(ops):
         assert tuple(sc.sel.cpu().tolist()) == info["sel"]
         np.testing.assert_allclose(sc.info[0].item(), info["h"], rtol=1e-6)
         np.testing.assert_allclose(outh.numpy(), ref.numpy(), rtol=RTOL, atol=ATOL)
+
+
+# ---------------------------------------------------------------- K1 for n = 16 / 20: centred-Gram kernel + exact redo
+def _gram_case(ops, cuda_lib, X, variant=3, guard_x1000=0):
+    n, D = X.shape
+    dX = dev_matrix(X, (D + 3) // 4 * 4)
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    cuda_lib.bde_tune(b"pairdist_variant", variant)
+    cuda_lib.bde_tune(b"gram_guard_x1000", guard_x1000)
+    try:
+        ops.svgd_pairdist_bandwidth(dX, sc, 0.01, 1.0, 50000.0)
+        first = (sc.dist.clone(), sc.K.clone(), sc.A.clone(), sc.sel.clone())
+        ops.svgd_pairdist_bandwidth(dX, sc, 0.01, 1.0, 50000.0)   # ring / ticket / flag clean across launches
+        assert torch.equal(sc.dist, first[0]) and torch.equal(sc.K, first[1]) and torch.equal(sc.A, first[2])
+    finally:
+        cuda_lib.bde_tune(b"pairdist_variant", 0)
+        cuda_lib.bde_tune(b"gram_guard_x1000", 0)
+    return sc
+
+
+def _check_vs_fp64(sc, X):
+    d_ref = O.svgd_pairdist(X)
+    bw = O.svgd_bandwidth(d_ref, 0.01, 1.0, 50000.0)
+    np.testing.assert_allclose(sc.dist.cpu().numpy(), d_ref.numpy(), rtol=2e-6, atol=1e-12)
+    assert tuple(sc.sel.cpu().tolist()) == bw["sel"]
+    np.testing.assert_allclose(sc.K.cpu().numpy(), bw["K"].numpy(), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(sc.A.cpu().numpy(), bw["A"].numpy(), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("n,D", [(20, 2_000_003), (20, 1_048_576), (20, 300_001), (16, 2_000_003), (16, 777_777), (20, 255),
+                                 (16, 4)])
+def test_pairgram_vs_oracle(ops, cuda_lib, n, D):
+    """Centred-Gram K1 (svgd_gram.cuh) against the fp64 oracle: distances to 2e-6, identical median selection, K / A
+    within the north-star tolerance; ragged D (TMA zero fill) and a D smaller than one tile included."""
+    X, _ = particles(n, D, seed=5 * n + D)
+    sc = _gram_case(ops, cuda_lib, X)
+    assert not sc.exact_redo()
+    _check_vs_fp64(sc, X)
+
+
+@pytest.mark.parametrize("n", [16, 20])
+def test_pairgram_common_offset_is_harmless(ops, cuda_lib, n):
+    """Particles that share a large common offset (a trained network's weights) and differ by small perturbations:
+    the uncentred Gram form would lose every digit; centring on particle 0 keeps the result inside 2e-6."""
+    D = 1_500_000
+    g = torch.Generator().manual_seed(n)
+    base = torch.randn(1, D, generator=g)
+    X = base + 1e-3 * (1 + 0.1 * torch.arange(n, dtype=torch.float32)).unsqueeze(1) * torch.randn(n, D, generator=g)
+    sc = _gram_case(ops, cuda_lib, X)
+    assert not sc.exact_redo()
+    _check_vs_fp64(sc, X)
+
+
+@pytest.mark.parametrize("n", [16, 20])
+@pytest.mark.parametrize("case", ["duplicate", "near-duplicate", "outlier-0", "forced"])
+def test_pairgram_guard_falls_back_to_exact_distances(ops, cuda_lib, n, case):
+    """When some pair is much closer to each other than to particle 0 the guard raises `redo` and the direct kernel
+    queued behind recomputes: results are then bit-identical to the direct variant (duplicates give exact zeros)."""
+    D = 1_200_003
+    X, _ = particles(n, D, seed=11 * n)
+    guard = 0
+    if case == "duplicate":
+        X[7] = X[5]
+    elif case == "near-duplicate":
+        X[7] = X[5] + 1e-4 * X[3]
+    elif case == "outlier-0":
+        X[0] = 200.0 * X[0]
+    else:
+        guard = 1
+    sc = _gram_case(ops, cuda_lib, X, guard_x1000=guard)
+    assert sc.exact_redo()
+    direct = _gram_case(ops, cuda_lib, X, variant=2)
+    assert torch.equal(sc.dist, direct.dist) and torch.equal(sc.K, direct.K) and torch.equal(sc.A, direct.A)
+    assert torch.equal(sc.sel, direct.sel)
+    if case == "duplicate":
+        assert float(sc.dist[5, 7]) == 0.0
+    _check_vs_fp64(sc, X)
+
+
+def test_pairgram_is_the_default_at_large_D(ops):
+    """Auto selection: n = 20 at a D with >= 4 tiles per SM runs the Gram kernel (redo flag cleared by it) and agrees
+    with the fp64 evaluation on the device; the n = 20 full-size step stays inside the tolerance."""
+    n, D = 20, 20_000_000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.randn(n, D, device="cuda", generator=g)
+    X *= (0.05 * (1 + 0.1 * torch.arange(n, device="cuda", dtype=torch.float32))).unsqueeze(1)
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    sc.ws[1] = (1 << 32) | int(sc.ws[1].item())   # pre-set redo: the Gram kernel must clear it
+    ops.svgd_pairdist_bandwidth(X, sc, 0.01, 1.0, 50000.0)
+    assert not sc.exact_redo()
+    ref = torch.zeros(n, n, dtype=torch.float64, device="cuda")
+    step = 1 << 21
+    for c0 in range(0, D, step):
+        x = X[:, c0:c0 + step].double()
+        ref += torch.cdist(x, x, p=2, compute_mode="donot_use_mm_for_euclid_dist") ** 2
+    np.testing.assert_allclose(sc.dist.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6)
+    bw = O.svgd_bandwidth(ref.cpu(), 0.01, 1.0, 50000.0)
+    assert tuple(sc.sel.cpu().tolist()) == bw["sel"]
