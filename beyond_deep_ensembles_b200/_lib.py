@@ -11,7 +11,10 @@ from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "lib" / "libbde_b200.so"
+import os
+
+# BDE_B200_LIB points at another BUILD of the same library (same-box A/B runs of two kernel versions); default in-tree
+LIB_PATH = Path(os.environ.get("BDE_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libbde_b200.so")
 
 _p = C.c_void_p
 _i = C.c_int
@@ -32,7 +35,7 @@ SIGNATURES = {
     "bde_peer_open": [C.c_char_p, C.POINTER(_p)],
     "bde_peer_close": [_p],
     "bde_peer_free": [_p],
-    "bde_peer_attach": [_p, _sz, _i, _i, C.POINTER(_u64), _p],
+    "bde_peer_attach": [_p, _sz, _i, _i, C.POINTER(_u64), _d, _p, _p],
     "bde_peer_detach": [_p, _sz, _p],
     "bde_peer_status": [_p, C.POINTER(_u64), C.POINTER(_u64)],
     "bde_svgd_pairdist": [_p, _i, _i64, _i64, _p, _i, _p, _sz, _p],
@@ -106,8 +109,14 @@ def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
 
+_call_device = None  # device of the stream handed out last: call() launches there (see call)
+
+
 def stream_ptr(device: torch.device | None = None) -> int:
+    """Current stream of `device` as a raw handle; also notes the device so that call() can make it current."""
+    global _call_device
     if device is not None and device.type == "cuda":
+        _call_device = device
         return torch.cuda.current_stream(device).cuda_stream
     return 0
 
@@ -120,7 +129,15 @@ def require_f32(*tensors: torch.Tensor) -> None:
 
 def call(name: str, *args) -> None:
     """Invoke one C-ABI entry point and raise on a non-zero return code."""
-    global launch_count
-    rc = getattr(get(), name)(*args)
+    global launch_count, _call_device
+    fn = getattr(get(), name)
+    dev, _call_device = _call_device, None
+    # The library launches on the calling thread's CURRENT device (and queries its SM count / occupancy), while the
+    # stream argument was taken from the tensors' device: make the two agree (model on cuda:1, current device cuda:0).
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     launch_count += 1
     check(rc, name)

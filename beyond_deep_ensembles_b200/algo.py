@@ -33,6 +33,20 @@ class BayesianOptimizer(Optimizer):
         # tells torch's GradScaler that step() deals with the loss scale itself (algo.py:17)
         self._step_supports_amp_scaling = True
 
+    # ---- checkpoints: the reference's layout plus the position of the Philox stream counter ----
+    def state_dict(self):
+        """torch's layout (and the reference's keys); one extra top-level entry, ignored by torch / the reference
+        when they load it: how many Philox noise streams have been used, so a resumed run does not replay them."""
+        from . import noise
+        sd = super().state_dict()
+        sd["bde_noise_stream"] = noise.stream_position()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        from . import noise
+        super().load_state_dict(state_dict)
+        noise.restore_stream_position(state_dict.get("bde_noise_stream"))
+
     # ---- what subclasses implement (algo.py:19-56) ----
     def step(self, forward_closure, backward_closure):
         raise NotImplementedError()

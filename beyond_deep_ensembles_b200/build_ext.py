@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
+    "-Xcompiler", "-fno-gnu-unique",   # template statics stay private to this .so (two builds can share a process)
     "-Xptxas", "-v",
     f"-I{ROOT / 'include'}", f"-I{CSRC}",
 ]

@@ -1,5 +1,6 @@
 // common.cuh — shared device helpers for the sm_100a posterior-update kernels.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstddef>
@@ -48,6 +49,7 @@ struct Tuning {
     int gram_pairing = 0;      // centred-Gram K1: warp -> pair-group mapping (svgd_gram.cuh:gram_warp_role)
     int gram_fold = 0;         // Gram K1 register budget: 0 auto, 1 producer warpgroup + setmaxnreg (SHIFT), 2 plain ninth warp
     int gram_l2_promotion = 0; // tensor-map L2 promotion of the Gram kernel's tile loads: 0 none, 1 64 B, 2 128 B, 3 256 B
+    int ring_kb = 0;           // staged SVGD kernels: cap on the shared-memory ring in use, KB (0 = whole ring)
     int gram_guard_x1000 = 0;  // centred-Gram K1: acceptance bound (S_ii + S_jj) / d_ij in 1/1000 (0 = default 32.0; 1 forces the exact redo)
 };
 Tuning& tuning();
@@ -162,6 +164,38 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred P1;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// TMA tensor-map load (SASS UTMALDG.2D): box [rows x box_cols] of a row-major fp32 matrix starting at column c0, row c1,
+// lands densely ([rows][box_cols]) at smem_dst; columns / rows outside the tensor are zero-filled and still counted
+// in the barrier's transaction bytes.  Measured on B200 (tools/microbench/tma_stream.cu): one elected lane issuing
+// one cp.async.bulk per 1 KB row segment cannot stream more than ~3-4 TB/s (the copy instruction is the limit); one
+// tensor-map load per [20 x 256] box streams 6.8-7.3 TB/s.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_map(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// host: tensor map over the rows of M[rows, cols] (row stride ld elements), box = box_cols x rows (svgd_gram.cu)
+int encode_rows_tensor_map(CUtensorMap* map, const float* M, int rows, int64_t cols, int64_t ld, int box_cols,
+                           int l2_promotion = 0);
+constexpr int kTmaBoxCols = 256;   // widest box dimension the tensor map allows
+
 __device__ __forceinline__ V4 lds_v4(const float* p) {
     V4 v;
     asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.lo), "=l"(v.hi) : "r"(smem_u32(p)));
@@ -208,10 +242,15 @@ struct WsHeader {                   // first kWsHeaderBytes of every reduction w
     int redo;                       // set by the centred-Gram K1 (svgd_gram.cuh) when its cancellation guard fails: the
                                     // direct K1 enqueued behind it (only_if_redo) then recomputes exact distances
     PeerBuf* peer[kPeerMaxRanks];   // peer[r] = rank r's exchange buffer mapped into this process
+    unsigned long long timeout_ns;  // how long the last CTA waits for its peers (0 = kPeerTimeoutNs)
+    unsigned long long* host_status;   // pinned, device-mapped host word (may be null): receives the number of abandoned
+                                       // exchanges, so the host can notice a failure without synchronising
+    int peer_failed;                // sticky: an exchange on this workspace timed out — every later exchange is skipped
+                                    // (sums poisoned, K1b not run) until the workspace is attached again
 };
 constexpr size_t kWsHeaderBytes = 256;
 static_assert(sizeof(WsHeader) <= kWsHeaderBytes, "workspace header");
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000 * 1000 * 1000;
+constexpr unsigned long long kPeerTimeoutNs = 120ull * 1000 * 1000 * 1000;   // default; bde_peer_attach sets the real one
 
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
     asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
@@ -237,12 +276,18 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 // Called by every thread of the last CTA with the local sums in total[0..count): on return total holds
 // the sums over all ranks (same bits on every rank).  No-op for an unattached workspace.
-__device__ __forceinline__ void peer_allreduce_fp64(const WsHeader* h, double* total, int count) {
+__device__ __forceinline__ void peer_allreduce_fp64(WsHeader* h, double* total, int count) {
     const int world = h->peer_world;
     if (world <= 1) return;
     const int rank = h->peer_rank;
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
+    const double poison = __longlong_as_double(0x7ff8000000000000LL);
+    if (h->peer_failed) {   // an earlier exchange was abandoned: the ranks' epochs may no longer pair up
+        for (int k = tid; k < count; k += nthreads) total[k] = poison;
+        __syncthreads();
+        return;
+    }
     PeerBuf* me = h->peer[rank];
     __shared__ unsigned long long s_epoch;
     __shared__ int s_timed_out;
@@ -252,6 +297,7 @@ __device__ __forceinline__ void peer_allreduce_fp64(const WsHeader* h, double* t
     }
     __syncthreads();
     const unsigned long long epoch = s_epoch;
+    const unsigned long long limit = h->timeout_ns ? h->timeout_ns : kPeerTimeoutNs;
     const int b = static_cast<int>(epoch & 1ull);
     for (int idx = tid; idx < world * count; idx += nthreads) {
         const int r = idx / count, k = idx - r * count;
@@ -263,7 +309,7 @@ __device__ __forceinline__ void peer_allreduce_fp64(const WsHeader* h, double* t
         st_release_sys_u64(&h->peer[tid]->flags[b][rank][0], epoch);
         const unsigned long long t0 = globaltimer_ns();
         while (ld_acquire_sys_u64(&me->flags[b][tid][0]) < epoch) {
-            if (globaltimer_ns() - t0 > kPeerTimeoutNs) {  // a peer never arrived: poison instead of hanging the GPU
+            if (globaltimer_ns() - t0 > limit) {  // a peer never arrived: give up instead of hanging the GPU
                 s_timed_out = 1;
                 break;
             }
@@ -274,14 +320,25 @@ __device__ __forceinline__ void peer_allreduce_fp64(const WsHeader* h, double* t
     for (int k = tid; k < count; k += nthreads) {
         double s = 0.0;
         for (int r = 0; r < world; ++r) s += ld_relaxed_sys_f64(&me->slots[b][r][k]);
-        total[k] = bad ? __longlong_as_double(0x7ff8000000000000LL) : s;
+        total[k] = bad ? poison : s;
     }
     if (tid == 0) {
         *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = epoch;
-        if (bad) *reinterpret_cast<volatile unsigned long long*>(&me->timeouts) = me->timeouts + 1ull;
+        if (bad) {
+            const unsigned long long nbad = me->timeouts + 1ull;
+            *reinterpret_cast<volatile unsigned long long*>(&me->timeouts) = nbad;
+            h->peer_failed = 1;
+            if (h->host_status) {
+                *reinterpret_cast<volatile unsigned long long*>(h->host_status) = nbad;
+                __threadfence_system();
+            }
+        }
     }
     __syncthreads();
 }
+// true (in the last CTA, after grid_reduce_fp64) when the cross-rank sum behind `ws` was abandoned: the callers
+// then leave K / A as they are instead of running K1b on poisoned sums
+__device__ __forceinline__ bool peer_exchange_failed(const void* ws) { return reinterpret_cast<const WsHeader*>(ws)->peer_failed != 0; }
 
 // Deterministic grid-wide fp64 sum of `count` values per CTA.
 //   cta_vals: this CTA's values in shared memory (count doubles), valid after __syncthreads.
@@ -338,7 +395,7 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     }
     if (tid == 0) *ticket = 0u;
     __syncthreads();
-    if (count <= kPeerMaxVals) peer_allreduce_fp64(reinterpret_cast<const WsHeader*>(ws), total, count);
+    if (count <= kPeerMaxVals) peer_allreduce_fp64(reinterpret_cast<WsHeader*>(ws), total, count);
     return true;
 }
 

@@ -59,13 +59,15 @@ extern "C" int bde_peer_free(void* buf) {
 }
 
 extern "C" int bde_peer_attach(void* workspace, size_t workspace_bytes, int world, int rank, const uint64_t* bufs_host,
-                               bde_stream_t stream) {
+                               double timeout_seconds, uint64_t* host_status, bde_stream_t stream) {
     if (!workspace || workspace_bytes < kWsHeaderBytes || world < 1 || world > kPeerMaxRanks || rank < 0 || rank >= world ||
         (world > 1 && !bufs_host))
         return BDE_ERR_INVALID_ARG;
     WsHeader h{};
     h.peer_world = world;
     h.peer_rank = rank;
+    h.timeout_ns = timeout_seconds > 0.0 ? static_cast<unsigned long long>(timeout_seconds * 1e9) : 0ull;
+    h.host_status = reinterpret_cast<unsigned long long*>(host_status);   // pinned host memory is device-addressable (UVA)
     for (int r = 0; r < world && world > 1; ++r) {
         if (!bufs_host[r]) return BDE_ERR_INVALID_ARG;
         h.peer[r] = reinterpret_cast<PeerBuf*>(static_cast<uintptr_t>(bufs_host[r]));

@@ -40,7 +40,10 @@ svgd_pairdist_scalar_kernel(const float* __restrict__ X, int n, int64_t D, int64
     }
 }
 
-__global__ void __launch_bounds__(256) svgd_bandwidth_kernel(const double* __restrict__ dist, int n, BandwidthParams bp) {
+// ws (nullable): the reduction workspace that produced `dist` — K1b is skipped after an abandoned peer exchange
+__global__ void __launch_bounds__(256) svgd_bandwidth_kernel(const double* __restrict__ dist, int n, BandwidthParams bp,
+                                                             const void* ws) {
+    if (ws && peer_exchange_failed(ws)) return;
     __shared__ double sd[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
     __shared__ double sk[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
     bandwidth_device<BDE_MAX_PARTICLES * BDE_MAX_PARTICLES>(dist, n, bp, sd, sk);
@@ -153,7 +156,7 @@ int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, in
     if (n == 1) {
         if (!accumulate) BDE_RETURN_IF_CUDA(cudaMemsetAsync(dist, 0, sizeof(double), st));
         if (fuse) {
-            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp);
+            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp, ws);
             BDE_CHECK_LAUNCH();
         }
         return BDE_OK;
@@ -169,7 +172,7 @@ int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, in
                                                                                                   accumulate, ws);
         BDE_CHECK_LAUNCH();
         if (fuse) {
-            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp);
+            svgd_bandwidth_kernel<<<1, 256, 0, st>>>(dist, n, bp, ws);
             BDE_CHECK_LAUNCH();
         }
         return BDE_OK;
@@ -308,7 +311,7 @@ extern "C" int bde_svgd_bandwidth(const double* dist, int n, double l2_reg, doub
                                   int32_t* sel, bde_stream_t stream) {
     if (!dist || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || !(dataset_size > 0.0)) return BDE_ERR_INVALID_ARG;
     BandwidthParams bp{l2_reg, kernel_grad_scale, dataset_size, h_override, K, A, info, sel};
-    svgd_bandwidth_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, n, bp);
+    svgd_bandwidth_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(dist, n, bp, nullptr);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }

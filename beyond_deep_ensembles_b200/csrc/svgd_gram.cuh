@@ -27,8 +27,6 @@
 // per-warp fp64 accumulators every 64 tiles; CTA sums are combined by the deterministic last-CTA reduction (and,
 // for a peer-attached workspace, across ranks), then the last CTA converts S to d, checks the guard and runs K1b.
 #pragma once
-#include <cuda.h>
-
 #include "svgd_kernels.cuh"
 
 namespace bde {
@@ -69,25 +67,6 @@ __host__ __device__ constexpr int gram_slot(int i, int j) {
 __host__ __device__ constexpr int gram_group_entries(int n, int g) {
     const int m = n - 1, h1 = (m + 1) / 2, h2 = m - h1, pa = (h2 + 1) / 2, pb = h2 - pa;
     return g == 0 ? h1 * (h1 + 1) / 2 : (g == 1 ? h2 * (h2 + 1) / 2 : (g == 2 ? h1 * pa : h1 * pb));
-}
-
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n.reg .pred P1;\n"
-        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
 }
 
 __device__ __forceinline__ V4 sub4(const V4& a, const V4& b) {
@@ -156,22 +135,20 @@ __device__ __forceinline__ void gram_warp_role(int wid, int pairing, int& g, int
 
 template <int N, int G>
 __device__ __forceinline__ void gram_consumer(int64_t ntiles, const float* __restrict__ tiles, uint64_t* full_bar,
-                                              uint64_t* empty_bar, double* __restrict__ wacc, int qi) {
+                                              uint64_t* empty_bar, double* __restrict__ wacc, int qi, int nst) {
     using GG = GramGeom<N>;
     constexpr int E = gram_group_entries(N, G);
     constexpr int TC = kGramTileCols;
-    constexpr int STAGES = GG::STAGES;
     f32x2 acc[E];
 #pragma unroll
     for (int k = 0; k < E; ++k) acc[k] = 0ull;
     const int lane = threadIdx.x & 31;
-    int it = 0;
+    int s = 0;            // ring slot and its use count, advanced without div / mod
+    uint32_t use = 0;
     int64_t t = blockIdx.x;
     bool more = true;
     while (more) {  // one flush site: every kGramFlushTiles tiles
-        for (int f = 0; f < kGramFlushTiles && t < ntiles; ++f, t += gridDim.x, ++it) {
-            const int s = it % STAGES;
-            const uint32_t use = static_cast<uint32_t>(it / STAGES);
+        for (int f = 0; f < kGramFlushTiles && t < ntiles; ++f, t += gridDim.x, s = (s + 1 == nst) ? 0 : s + 1, use += (s == 0)) {
             mbar_wait(&full_bar[s], use & 1u);
             const float* sx = tiles + static_cast<size_t>(s) * N * TC + 4 * qi;
             gram_accumulate<N, G>([&](int r) { return lds_v4(sx + r * TC); },
@@ -188,11 +165,11 @@ __device__ __forceinline__ void gram_consumer(int64_t ntiles, const float* __res
 
 template <int N, int G>
 __device__ __forceinline__ void gram_dispatch(int g, int64_t ntiles, const float* tiles, uint64_t* full_bar,
-                                              uint64_t* empty_bar, double* wacc, int qi) {
+                                              uint64_t* empty_bar, double* wacc, int qi, int nst) {
     if (g == G) {
-        gram_consumer<N, G>(ntiles, tiles, full_bar, empty_bar, wacc, qi);
+        gram_consumer<N, G>(ntiles, tiles, full_bar, empty_bar, wacc, qi, nst);
     } else {
-        if constexpr (G + 1 < 4) gram_dispatch<N, G + 1>(g, ntiles, tiles, full_bar, empty_bar, wacc, qi);
+        if constexpr (G + 1 < 4) gram_dispatch<N, G + 1>(g, ntiles, tiles, full_bar, empty_bar, wacc, qi, nst);
     }
 }
 
@@ -251,7 +228,7 @@ template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setma
 template <int N, bool SHIFT>
 __global__ void __launch_bounds__(kGramConsumers + (SHIFT ? 128 : 32), 1)
 svgd_pairgram_kernel(const __grid_constant__ CUtensorMap tmap, int64_t D, double* __restrict__ dist, void* ws,
-                     int fuse_bandwidth, BandwidthParams bp, double guard, int pairing) {
+                     int fuse_bandwidth, BandwidthParams bp, double guard, int pairing, int nst) {
     using GG = GramGeom<N>;
     constexpr int TC = kGramTileCols;
     constexpr int STAGES = GG::STAGES;
@@ -277,7 +254,7 @@ svgd_pairgram_kernel(const __grid_constant__ CUtensorMap tmap, int64_t D, double
             mbar_init(&empty_bar[s], CWARPS);
         }
         mbar_fence_init();
-        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+        tma_prefetch_map(&tmap);
     }
     __syncthreads();
 
@@ -287,15 +264,14 @@ svgd_pairgram_kernel(const __grid_constant__ CUtensorMap tmap, int64_t D, double
         if constexpr (SHIFT) reg_inc<kGramRegsConsumer>();
         int g, half;
         gram_warp_role(wid, pairing, g, half);
-        gram_dispatch<N, 0>(g, ntiles, tiles, full_bar, empty_bar, wacc[wid], half * 32 + (tid & 31));
+        gram_dispatch<N, 0>(g, ntiles, tiles, full_bar, empty_bar, wacc[wid], half * 32 + (tid & 31), nst);
         if constexpr (SHIFT) reg_dec<kGramRegsLaunch>();
     } else {
         if constexpr (SHIFT) reg_dec<kGramRegsProducer>();
         if (tid == kGramConsumers) {   // the elected producer lane drives the TMA
-            int it = 0;
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int s = it % STAGES;
-                const uint32_t use = static_cast<uint32_t>(it / STAGES);
+            int s = 0;
+            uint32_t use = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, s = (s + 1 == nst) ? 0 : s + 1, use += (s == 0)) {
                 mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
                 mbar_arrive_expect_tx(&full_bar[s], GG::STAGE_BYTES);
                 tma_load_2d(tiles + static_cast<size_t>(s) * N * TC, &tmap, static_cast<int>(t * TC), 0, &full_bar[s]);
@@ -322,11 +298,10 @@ svgd_pairgram_kernel(const __grid_constant__ CUtensorMap tmap, int64_t D, double
     if (!grid_reduce_fp64(cta_vals, EN, ws, total)) return;
     const bool redo = gram_to_dist<N>(total, dist, guard, tid, nthreads);
     if (tid == 0) reinterpret_cast<WsHeader*>(ws)->redo = redo ? 1 : 0;
-    if (!redo && fuse_bandwidth) bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
+    if (!redo && fuse_bandwidth && !peer_exchange_failed(ws)) bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
 }
 
 // host side -------------------------------------------------------------------------------------------------------
-int encode_rows_tensor_map(CUtensorMap* map, const float* X, int n, int64_t D, int64_t ld, int box_cols, int l2_promotion);
 
 template <int N>
 int launch_pairgram(const float* X, int64_t D, int64_t ld, double* dist, void* ws, int fuse, const BandwidthParams& bp,
@@ -347,11 +322,16 @@ int launch_pairgram(const float* X, int64_t D, int64_t ld, double* dist, void* w
     int64_t grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
+    int nst = GG::STAGES;
+    if (tuning().ring_kb > 0) {
+        const int want = tuning().ring_kb * 1024 / GG::STAGE_BYTES;
+        if (want < nst) nst = want > 2 ? want : 2;
+    }
     const bool shift = tuning().gram_fold == 0 ? (N > 16) : tuning().gram_fold == 1;   // knob: 1 = SHIFT, 2 = plain
     if (shift)
-        svgd_pairgram_kernel<N, true><<<static_cast<unsigned>(grid), kGramConsumers + 128, smem, st>>>(map, D, dist, ws, fuse, bp, guard, tuning().gram_pairing);
+        svgd_pairgram_kernel<N, true><<<static_cast<unsigned>(grid), kGramConsumers + 128, smem, st>>>(map, D, dist, ws, fuse, bp, guard, tuning().gram_pairing, nst);
     else
-        svgd_pairgram_kernel<N, false><<<static_cast<unsigned>(grid), kGramConsumers + 32, smem, st>>>(map, D, dist, ws, fuse, bp, guard, tuning().gram_pairing);
+        svgd_pairgram_kernel<N, false><<<static_cast<unsigned>(grid), kGramConsumers + 32, smem, st>>>(map, D, dist, ws, fuse, bp, guard, tuning().gram_pairing, nst);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }

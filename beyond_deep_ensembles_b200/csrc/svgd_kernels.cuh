@@ -427,7 +427,7 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
         if (accumulate) v += dist[e];
         dist[e] = v;
     }
-    if (fuse_bandwidth) {
+    if (fuse_bandwidth && !peer_exchange_failed(ws)) {
         __syncthreads();
         bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
     }
@@ -619,7 +619,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
         if (accumulate) v += dist[e];
         dist[e] = v;
     }
-    if (fuse_bandwidth) {
+    if (fuse_bandwidth && !peer_exchange_failed(ws)) {
         __syncthreads();
         bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
     }
@@ -824,7 +824,7 @@ __device__ __forceinline__ void next_dist_epilogue(double (*wacc)[pair_count(N) 
         const int i = e / N, j = e - i * N;
         nd.dist[e] = (i != j) ? total[i < j ? pair_index(i, j, N) : pair_index(j, i, N)] : 0.0;
     }
-    if (nd.fuse_bandwidth) {
+    if (nd.fuse_bandwidth && !peer_exchange_failed(nd.ws)) {
         __syncthreads();
         bandwidth_device<pow2_ceil(N * N)>(nd.dist, N, nd.bp, sd, sk);
     }
@@ -985,9 +985,10 @@ __host__ __device__ constexpr int apply_stages(int n, int opt, int tc) {
 
 template <int N, int OPT, bool NEXT = false, int TS = apply_default_tile_sets(N, OPT, NEXT), int TC = apply_tile_cols(N, OPT, NEXT)>
 __global__ void __launch_bounds__(TS * TC / 4 + 32, 1)
-svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, const float* __restrict__ K,
-                      const float* __restrict__ A, int64_t D, int64_t ldx, int64_t ldg, int64_t ldo,
-                      const __grid_constant__ BaseOptParams o, const __grid_constant__ NextDistParams nd) {
+svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG, const float* X,
+                      const float* __restrict__ G, float* out, const float* __restrict__ K, const float* __restrict__ A,
+                      int64_t D, int64_t ldx, int64_t ldg, int64_t ldo, const __grid_constant__ BaseOptParams o,
+                      const __grid_constant__ NextDistParams nd, int nst /* ring stages in use, TS < nst <= STAGES */) {
     static_assert(!NEXT || (OPT != kOptNone && pair_groups(N) == 1 && N >= 2), "NEXT needs a fused optimizer and n <= 10");
     constexpr int PN = NEXT ? pair_count(N) : 1;
     constexpr int NP = (N + 3) & ~3;
@@ -996,11 +997,14 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
     constexpr int kApplyJUnroll = BDE_APPLY_J_UNROLL;
     constexpr int ROWS = 2 * N + opt_state_rows(OPT);
     constexpr int QT = TC / 4;              // threads of one tile set; one column quad each
+    constexpr int BW = kTmaBoxCols;         // a stage holds X and G as TC / BW boxes of [N][BW] each, then the state rows [.][TC]
+    constexpr int NB = TC / BW;
+    static_assert(TC % BW == 0, "tile width must be a multiple of the TMA box width");
     constexpr int CONSUMERS = TS * QT;
     constexpr int CWARPS = CONSUMERS / 32;
     static_assert(STAGES > TS || TS == 1, "every set holds a stage while it computes: the ring must be deeper than TS");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES][ROWS][TC]: X rows, G rows, state rows
+    float* tiles = reinterpret_cast<float*>(smem_raw);  // [STAGES]{X boxes [NB][N][BW], G boxes [NB][N][BW], state rows [.][TC]}
     __shared__ __align__(16) float sKT[N][NP];
     __shared__ __align__(16) float sAT[N][NP];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -1023,6 +1027,8 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
             mbar_init(&empty_bar[s], QT / 32);   // released by the warps of the one set that consumed it
         }
         mbar_fence_init();
+        tma_prefetch_map(&mapX);
+        tma_prefetch_map(&mapG);
     }
     __syncthreads();
 
@@ -1033,22 +1039,22 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
 
     if (is_producer) {
         if (tid == CONSUMERS) {  // one elected lane drives the copy engine
-            int it = 0;
-            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-                const int s = it % STAGES;
-                const uint32_t use = static_cast<uint32_t>(it / STAGES);
+            int s = 0;            // ring slot and how often it has been used before: advanced without div / mod
+            uint32_t use = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, s = (s + 1 == nst) ? 0 : s + 1, use += (s == 0)) {
                 mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
                 const int64_t col0 = t * TC;
                 const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
                 const uint32_t row_bytes = static_cast<uint32_t>(w) * 4u;
-                const uint32_t nrows = 2u * N + (has_s0 ? 1u : 0u) + (OPT == kOptAdam ? 1u : 0u);
-                mbar_arrive_expect_tx(&full_bar[s], nrows * row_bytes);
+                const uint32_t nstate = (has_s0 ? 1u : 0u) + (OPT == kOptAdam ? 1u : 0u);
+                // the tensor-map boxes always deliver (and count) their full size: columns beyond d4 arrive as zeros
+                mbar_arrive_expect_tx(&full_bar[s], 2u * N * TC * 4u + nstate * row_bytes);
                 float* sx = tiles + static_cast<size_t>(s) * ROWS * TC;
                 float* sg = sx + N * TC;
 #pragma unroll
-                for (int r = 0; r < N; ++r) {
-                    tma_load_1d(sx + r * TC, X + r * ldx + col0, row_bytes, &full_bar[s]);
-                    tma_load_1d(sg + r * TC, G + r * ldg + col0, row_bytes, &full_bar[s]);
+                for (int b = 0; b < NB; ++b) {   // one UTMALDG per box instead of one UBLKCP per row (2 N per tile before)
+                    tma_load_2d(sx + b * N * BW, &mapX, static_cast<int>(col0) + b * BW, 0, &full_bar[s]);
+                    tma_load_2d(sg + b * N * BW, &mapG, static_cast<int>(col0) + b * BW, 0, &full_bar[s]);
                 }
                 if constexpr (OPT != kOptNone) {
                     if (has_s0) tma_load_1d(sg + N * TC, o.state0 + col0, row_bytes, &full_bar[s]);
@@ -1063,10 +1069,10 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
 #pragma unroll
         for (int k = 0; k < PN; ++k) pacc[k] = 0ull;
         int it = set;
+        int s = set;          // ring slot of tile `it` and its use count (nst > TS): advanced without div / mod
+        uint32_t use = 0;
         for (int64_t t = blockIdx.x + static_cast<int64_t>(set) * gridDim.x; t < ntiles;
-             t += static_cast<int64_t>(TS) * gridDim.x, it += TS) {
-            const int s = it % STAGES;
-            const uint32_t use = static_cast<uint32_t>(it / STAGES);
+             t += static_cast<int64_t>(TS) * gridDim.x, it += TS, s += TS, use += (s >= nst), s -= (s >= nst) ? nst : 0) {
             const int64_t col0 = t * TC;
             const int64_t w = (d4 - col0 < TC) ? d4 - col0 : TC;
             const bool active = 4 * q < w;
@@ -1076,18 +1082,20 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1u) & 1u);
             }
             mbar_wait(&full_bar[s], use & 1u);
-            const float* sx = tiles + static_cast<size_t>(s) * ROWS * TC + 4 * q;
+            const float* stage = tiles + static_cast<size_t>(s) * ROWS * TC;
+            const float* sx = stage + (q / (BW / 4)) * (N * BW) + 4 * (q % (BW / 4));   // row j of this quad: sx + j * BW
             const float* sg = sx + N * TC;
+            const float* sst = stage + 2 * N * TC + 4 * q;                              // optimizer-state rows: sst + r * TC
             f32x2 acc[N][2];
 #pragma unroll
             for (int i = 0; i < N; ++i) acc[i][0] = acc[i][1] = 0ull;
             if (active) {
                 if constexpr (kApplyRolled) {
 #pragma unroll(kApplyJUnroll)
-                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * TC), lds_v4(sx + j * TC), sKT[j], sAT[j]);
+                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * BW), lds_v4(sx + j * BW), sKT[j], sAT[j]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * TC), lds_v4(sx + j * TC), sKT[j], sAT[j]);
+                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * BW), lds_v4(sx + j * BW), sKT[j], sAT[j]);
                 }
             }
             if constexpr (OPT == kOptNone) {
@@ -1114,8 +1122,8 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                 }
                 if (active) {
                     float* xw = const_cast<float*>(X) + col0 + 4 * q;
-                    if (has_s0) s0 = lds_v4(sg + N * TC);
-                    if (OPT == kOptAdam) s1 = lds_v4(sg + (N + 1) * TC);
+                    if (has_s0) s0 = lds_v4(sst);
+                    if (OPT == kOptAdam) s1 = lds_v4(sst + TC);
                     if (o.out_last) {
                         V4 v;
                         v.lo = acc[N - 1][0];
@@ -1124,7 +1132,7 @@ svgd_apply_tma_kernel(const float* X, const float* __restrict__ G, float* out, c
                     }
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
-                        V4 x = lds_v4(sx + i * TC);
+                        V4 x = lds_v4(sx + i * BW);
                         opt_update_quad<OPT>(o, i, acc[i][0], acc[i][1], x, s0, s1);
                         stg_stream_v4(xw + i * ldx, x);
                         if constexpr (NEXT) xn[i] = x;
@@ -1220,16 +1228,27 @@ int launch_apply_tma(const float* X, const float* G, float* out, const float* K,
                      int64_t ldg, int64_t ldo, const BaseOptParams& o, cudaStream_t st, const NextDistParams& nd) {
     constexpr int smem = apply_stages(N, OPT, TC) * apply_stage_bytes(N, OPT, TC);
     static_assert(apply_stages(N, OPT, TC) >= 2, "ring too shallow");
-    const int64_t ntiles = ((D & ~static_cast<int64_t>(3)) + TC - 1) / TC;
+    const int64_t d4 = D & ~static_cast<int64_t>(3);
+    const int64_t ntiles = (d4 + TC - 1) / TC;
     static bool configured = false;
     if (!configured) {
         BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
+    // tensor maps over the first d4 columns of X and G: columns of the last tile beyond d4 arrive as zeros
+    CUtensorMap mapX, mapG;
+    int rc = encode_rows_tensor_map(&mapX, X, N, d4, ldx, kTmaBoxCols);
+    if (rc == BDE_OK) rc = encode_rows_tensor_map(&mapG, G, N, d4, ldg, kTmaBoxCols);
+    if (rc != BDE_OK) return rc;
+    int nst = apply_stages(N, OPT, TC);
+    if (tuning().ring_kb > 0) {   // shallower ring (A/B knob): fewer tile loads in flight per SM
+        const int want = tuning().ring_kb * 1024 / apply_stage_bytes(N, OPT, TC);
+        if (want < nst) nst = want > TS + 1 ? want : TS + 1;
+    }
     int64_t grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(X, G, out, K, A, D, ldx, ldg, ldo, o, nd);
+    svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(mapX, mapG, X, G, out, K, A, D, ldx, ldg, ldo, o, nd, nst);
     BDE_CHECK_LAUNCH();
     return BDE_OK;
 }
@@ -1248,6 +1267,7 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
     if (variant == 0) {
         variant = (ntiles >= 2 * TS0 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
     }
+    if (d4 == 0 || d4 > 0x7fffffffLL) variant = 1;   // the tensor maps need >= 1 column quad and int32 coordinates
     if (variant == 2) {
         // "apply_tile_sets" selects the alternative geometry (A/B runs and the parity tests of both)
         constexpr int TS_ALT = !apply_small_tiles(N, OPT, NEXT) ? 3 : (N > 12 ? 7 - TS0 : 1);

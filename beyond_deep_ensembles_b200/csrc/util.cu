@@ -127,6 +127,7 @@ extern "C" int bde_tune(const char* key, int value) {
     else if (k == "gram_pairing") tuning().gram_pairing = value;
     else if (k == "gram_fold") tuning().gram_fold = value;
     else if (k == "gram_l2_promotion") tuning().gram_l2_promotion = value;
+    else if (k == "ring_kb") tuning().ring_kb = value;
     else if (k == "gram_guard_x1000") tuning().gram_guard_x1000 = value;
     else return BDE_ERR_INVALID_ARG;
     return BDE_OK;

@@ -23,7 +23,21 @@ import torch.distributed as dist
 from . import _lib, ops
 
 
+class _Single:
+    """Sentinel group: this rank works alone, whatever torch.distributed's state (plain data-parallel jobs)."""
+
+    def __repr__(self):
+        return "bde.dist.SINGLE"
+
+
+SINGLE = _Single()
+
+
 def world(group=None) -> int:
+    """Ranks that hold column slices of ONE problem.  The functional API below takes torch.distributed's
+    convention (group=None = the default group); SVGDOptimizer passes SINGLE unless a group was given explicitly."""
+    if group is SINGLE:
+        return 1
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
@@ -71,13 +85,31 @@ class PeerSet:
             self.close(barrier=False)
             raise _lib.BdeError("CUDA IPC mapping of a peer's exchange buffer failed on at least one rank")
         self._bufs = (C.c_uint64 * self.world)(*bufs)
+        # pinned (device-addressable) host word: the kernels store the number of abandoned exchanges here, so
+        # check() can see a failure without a synchronising device read
+        self._host_status = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.timeout_s = float(os.environ.get("BDE_PEER_TIMEOUT_S", "120"))
 
     def attach(self, sc: "ops.SvgdScratch") -> None:
         """From now on the grid reductions that use sc.ws produce sums over all ranks of the group."""
         _lib.check(_lib.get().bde_peer_attach(sc.ws.data_ptr(), sc.ws_bytes, self.world, self.rank, self._bufs,
+                                              self.timeout_s, self._host_status.data_ptr(),
                                               _lib.stream_ptr(sc.ws.device)), "bde_peer_attach")
         sc.peers = self
         self._attached.append(weakref.ref(sc))
+
+    def check(self) -> None:
+        """Raise if an in-kernel exchange of this peer set was abandoned (a peer did not arrive within
+        `timeout_s`).  Reads a pinned host word — no synchronisation — so a failure is reported by the first call
+        AFTER the failing launch has finished; from that launch on the kernels leave K / A untouched and skip
+        further exchanges, so no NaN reaches the particles in between."""
+        bad = int(self._host_status[0])
+        if bad:
+            raise _lib.BdeError(
+                f"in-kernel peer exchange abandoned {bad} time(s): a rank of the D-sharded group did not reach its "
+                f"SVGD step within {self.timeout_s:g} s (BDE_PEER_TIMEOUT_S); the sums were discarded and the kernel "
+                "matrix was left unchanged.  Re-synchronise the ranks and rebuild the optimizer (or set "
+                "BDE_PEER_EXCHANGE=0 to use the NCCL all-reduce form).")
 
     def status(self):
         """(exchanges completed, exchanges abandoned on a timeout) of this rank — synchronises."""

@@ -68,6 +68,7 @@ class iVONOptimizer(BayesianOptimizer):
     # ------------------------------------------------------------------ step
     def step(self, forward_closure, backward_closure, grad_scaler=None):
         self._reset_state()
+        self._drop_presampled(release=True)   # training does not keep the prediction-time sample buffers
 
         acc_loss = None
         for _ in range(self.mc_samples):
@@ -146,7 +147,8 @@ class iVONOptimizer(BayesianOptimizer):
 
     # ---- batched sampling ----
     #: upper bound of the presample buffers in bytes; larger requests are drawn in several batches
-    presample_max_bytes = 4 << 30
+    presample_max_bytes = 1 << 30
+    presample_max_rows = 16
 
     def presample(self, count: int):
         """Announce that the next `count` sample_parameters() calls follow each other without a step() in between
@@ -156,13 +158,18 @@ class iVONOptimizer(BayesianOptimizer):
         self._drop_presampled()
         self._pre_pending = int(count) if count and count > 1 else 0
 
-    def _drop_presampled(self):
+    def _drop_presampled(self, release: bool = False):
+        """Forget undelivered draws; release=True (every step()) also frees the presample buffers (see swag.py)."""
         self._pre_next = self._pre_ready = self._pre_pending = 0
+        if release:
+            for ar in self._arenas:
+                ar.pop("pre_buf", None)
+                ar.pop("pre_views", None)
 
     def _draw_batch(self):
         groups = len(self.param_groups)
         total = sum(ar["layout"].size for ar in self._arenas)
-        rows = int(min(self._pre_pending, max(1, self.presample_max_bytes // (4 * total))))
+        rows = int(min(self._pre_pending, self.presample_max_rows, max(1, self.presample_max_bytes // (4 * total))))
         # injected noise is consumed in the order of `rows` sequential calls: one draw per group per call
         eps = [[] for _ in range(groups)]
         for _ in range(rows):

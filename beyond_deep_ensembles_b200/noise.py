@@ -47,6 +47,19 @@ def reserve_stream_ids(count: int) -> int:
     return first
 
 
+def stream_position() -> int:
+    """How many Philox stream ids this process has handed out (checkpointed by the optimizers' state_dict)."""
+    return _next_stream
+
+
+def restore_stream_position(position) -> None:
+    """Resume after a checkpoint: never hand out a stream id again that the saved run had already used (a resumed
+    run with the same seed would otherwise replay the same noise)."""
+    global _next_stream
+    if position is not None:
+        _next_stream = max(_next_stream, int(position))
+
+
 def draw(kind: str, numel: int, device) -> Optional[torch.Tensor]:
     """Injected noise for this draw, or None to let the kernel use Philox."""
     if _injector is None:

@@ -15,10 +15,18 @@ from . import _lib
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
-    """The product path is CUDA-only; anything else is an error, never a fallback."""
+    """The product path is CUDA-only; anything else is an error, never a fallback.  All tensors of one call must
+    live on ONE device (the kernels take raw pointers and run on that device's current stream)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.BdeError("beyond_deep_ensembles_b200 runs on CUDA tensors only (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.BdeError(f"tensors of one kernel call span devices ({dev} and {t.device})")
 
 
 def _rows(t: torch.Tensor):

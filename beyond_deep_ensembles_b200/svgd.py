@@ -39,7 +39,9 @@ class SVGDOptimizer(BayesianOptimizer):
 
     One param_group per tensor (svgd.py:50); `reset_params_closure` is called
     particle_count - 1 times to initialise the particles (svgd.py:58-63);
-    `base_optimizer` must optimise the same parameters.
+    `base_optimizer` must optimise the same parameters.  `process_group` (extension, default None = this rank
+    works alone like the reference): the torch.distributed group whose ranks each hold a COLUMN SLICE of every
+    particle; only then are the n x n partial distances summed across ranks.
 
     `fuse_base_optimizer` (class attribute, default True): when the base optimizer is a stock
     torch.optim.SGD / Adam / AdamW and no GradScaler is active, its n per-particle steps
@@ -49,9 +51,12 @@ class SVGDOptimizer(BayesianOptimizer):
     `reuse_pair_distances` (class attribute, default True): the fused launch also computes the pair
     distances of the particles it has just updated (n <= 10), which are exactly what `rbf` needs at the
     next step() — so a training loop reads the particles once per step.  The cached kernel is only valid
-    while nothing but this optimizer writes the particles; load_state_dict() and every unfused step drop
-    it, and code that edits `state[param]["particle_i"]` in place between steps must call
-    `invalidate_kernel_cache()` (or set the attribute to False).
+    while nothing but this optimizer writes the particles: load_state_dict() and every unfused step drop it, and
+    every step() compares autograd's version counters of the particle arena (shared by all `particle_i` views) and
+    of the model parameters (which alias the last particle between steps) with the values recorded after the
+    launch that produced the cache — any tracked in-place write in between (model.load_state_dict(), weight
+    clipping, EMA copies, re-initialisation) drops the cache and K1 runs again.  Writes that bypass the counters
+    (`param.data.mul_()`, raw-pointer kernels) must call `invalidate_kernel_cache()` (or set the attribute to False).
     """
 
     fuse_base_optimizer = True
@@ -80,13 +85,18 @@ class SVGDOptimizer(BayesianOptimizer):
         self._out_last = self._layout.new_arena(1, device)   # new gradient of the last particle (svgd.py:94)
         self._fused_plan = None
         self._scratch = ops.SvgdScratch.allocate(n, device)
-        self._group = process_group
+        # process_group=None means NOT sharded — the reference is rank-local, and under plain data parallelism (DDP)
+        # every rank holds ALL columns of its own particles: summing the pair distances over such replicas would
+        # scale d, the median and h^2 by the world size.  D-sharding is opt-in: pass the group whose ranks hold the
+        # column slices (torch.distributed.group.WORLD for the default group).
+        self._group = bdist.SINGLE if process_group is None else process_group
         # D-sharded on one node: exchange the n*n partial distances inside the kernels (collective over the group)
-        bdist.enable_peer_exchange(self._scratch, process_group)
+        bdist.enable_peer_exchange(self._scratch, self._group)
         # what self._scratch holds for the CURRENT particles: None, "partial" (this rank's pair-distance sums,
         # not yet all-reduced) or "kernel" (K, A, info, sel ready)
         self._cached = None
         self._cached_hyper = None
+        self._cached_versions = None
         self._xviews = [self._layout.views(self._X[i]) for i in range(n)]
         self._gviews = [self._layout.views(self._G[i]) for i in range(n)]
         self._oviews = None
@@ -118,9 +128,13 @@ class SVGDOptimizer(BayesianOptimizer):
             if not self._store_grads(particle_idx, plist, grad_scaler, base):   # unscale (if AMP) + gather, one launch
                 return None
 
+        if self._scratch.peers is not None:
+            self._scratch.peers.check()   # an abandoned in-kernel exchange (straggler rank) is an error, never silent
         with torch.no_grad():
             hyper = (self.state["__l2_reg"], self.state["__kernel_grad_scale"], self.state["__dataset_size"])
             cached = self._cached if (self.reuse_pair_distances and self._cached_hyper == hyper) else None
+            if cached is not None and self._cached_versions != self._write_versions(plist):
+                cached = None   # something else wrote a particle since the cache was computed
             self._cached = None
             if cached != "kernel":
                 # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b
@@ -139,6 +153,7 @@ class SVGDOptimizer(BayesianOptimizer):
                 if plan.launch(self._X, self._G, self._scratch, self._out_last[0], *bound, next_kernel=nk):
                     self._cached = "kernel" if nk.fuse_bandwidth else "partial"
                     self._cached_hyper = hyper
+                    self._cached_versions = self._write_versions(plist)
                 for param, xview, oview in zip(plist, self._xviews[n - 1], self._oviews_last):
                     param.grad = oview
                     param.data = xview
@@ -174,6 +189,11 @@ class SVGDOptimizer(BayesianOptimizer):
         if plan is None or plan.base is not base or not plan.still_valid():
             plan = self._fused_plan = FusedBasePlan.build(base, plist, self._layout, self._X.device)
         return plan
+
+    def _write_versions(self, plist):
+        """Autograd version counters that every tracked in-place write to a particle bumps: the X arena's (shared
+        by all of its views, i.e. by every state[param]["particle_i"]) and the model parameters' (own counters)."""
+        return (self._X._version, tuple(p._version for p in plist))
 
     def invalidate_kernel_cache(self):
         """Forget the pair distances computed by the last fused launch (see `reuse_pair_distances`)."""

@@ -65,7 +65,7 @@ class SwagOptimizer(BayesianOptimizer):
 
     # ------------------------------------------------------------------ step
     def step(self, forward_closure, backward_closure, grad_scaler=None):
-        self._drop_presampled()   # the posterior is about to change
+        self._drop_presampled(release=True)   # the posterior is about to change; training does not keep the buffer
         self._restore_original_params()
         base = self.state["__base_optimizer"]
         base.zero_grad()
@@ -107,7 +107,9 @@ class SwagOptimizer(BayesianOptimizer):
 
     # ---- batched sampling ----
     #: upper bound of the presample buffer in bytes; larger requests are drawn in several batches
-    presample_max_bytes = 4 << 30
+    presample_max_bytes = 1 << 30
+    #: draws generated per _draw_batch call (the kernel reads the moments once per 16 draws: more rows save nothing)
+    presample_max_rows = 16
 
     def presample(self, count: int):
         """Announce that the next `count` sample_parameters() calls draw from the CURRENT posterior (what
@@ -118,13 +120,19 @@ class SwagOptimizer(BayesianOptimizer):
         self._drop_presampled()
         self._pre_pending = max(int(count), 0) if count and count > 1 else 0
 
-    def _drop_presampled(self):
+    def _drop_presampled(self, release: bool = False):
+        """Forget undelivered draws; release=True (every step()) also returns the buffer to the allocator, so one
+        predict() during validation does not pin up to presample_max_bytes per ensemble member for the rest of
+        training (the parameters were re-homed to the sample arena before this is called)."""
         self._pre_ready = self._pre_pending = self._pre_next = 0
+        if release:
+            self._pre_buf = None
+            self._pre_views = []
 
     def _draw_batch(self):
         L, K, dev_ = self._layout, self.deviation_samples, self._theta.device
         size = self._theta.numel()
-        rows = int(min(self._pre_pending, max(1, self.presample_max_bytes // (4 * size))))
+        rows = int(min(self._pre_pending, self.presample_max_rows, max(1, self.presample_max_bytes // (4 * size))))
         if self._pre_buf is None or self._pre_buf.shape[0] < rows:
             self._pre_buf = L.new_arena(rows, dev_)
             self._pre_views = [L.views(self._pre_buf[r]) for r in range(rows)]

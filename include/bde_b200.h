@@ -341,7 +341,8 @@ int bde_prior_terms_value_and_grad(int count, const int32_t* kinds_host, const u
  * on every rank, and a D-sharded step needs no separate all-reduce launch (the NCCL all-reduce of
  * `dist` remains the portable form).  Every rank must issue the same sequence of launches on the
  * attached workspaces of one peer set, from one stream.  A peer that never arrives poisons the
- * sums with NaN after 20 s instead of hanging the GPU (bde_peer_status reports it).
+ * sums with NaN after the attach-time timeout instead of hanging the GPU (bde_peer_status and the host status word
+ * report it).
  *
  * Protocol (the library keeps no state; the caller owns everything):
  *   1. each rank: bde_peer_alloc -> device buffer + a BDE_PEER_HANDLE_BYTES CUDA-IPC handle;
@@ -359,8 +360,12 @@ int bde_peer_alloc(void** buf, unsigned char* ipc_handle_host);
 int bde_peer_open(const unsigned char* ipc_handle_host, void** mapped);
 int bde_peer_close(void* mapped);
 int bde_peer_free(void* buf);
+/* timeout_seconds: how long the last CTA waits for its peers (<= 0: 120 s).  host_status (nullable): one pinned,
+ * device-addressable host word that receives the count of abandoned exchanges, so the caller can notice a failure
+ * without synchronising.  After a timeout the workspace is marked failed: sums are poisoned with NaN, K1b is not run
+ * (K / A keep their previous values) and every later exchange returns at once, until bde_peer_attach is called again. */
 int bde_peer_attach(void* workspace, size_t workspace_bytes, int world, int rank, const uint64_t* bufs_host,
-                    bde_stream_t stream);
+                    double timeout_seconds, uint64_t* host_status, bde_stream_t stream);
 int bde_peer_detach(void* workspace, size_t workspace_bytes, bde_stream_t stream);
 /* exchanges completed / abandoned on this rank's buffer (synchronous device read) */
 int bde_peer_status(const void* buf, uint64_t* epoch_host, uint64_t* timeouts_host);

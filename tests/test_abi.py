@@ -64,9 +64,10 @@ def test_sass_uses_packed_fp32(built_lib):
     assert sass.count("FFMA2") >= 90 and sass.count("FADD2") >= 90, "pairdist<10> lost its packed-fp32 inner loop"
     assert "LDG.E.128" in sass or "LDG.E.ENL2.128" in sass or ".128" in sass
     # centred-Gram K1 (n = 20): 190 entries x 2 FFMA2 per column quad, fed by one tensor-map TMA load per tile
-    sass = subprocess.run([cuobjdump, "-sass", "-fun",
-                           "_ZN3bde20svgd_pairgram_kernelILi20ELb1EEEv14CUtensorMap_stlPdPviNS_15BandwidthParamsEdi",
-                           str(built_lib)], capture_output=True, text=True).stdout
+    nm = subprocess.run(["nm", "-D", str(built_lib)], capture_output=True, text=True).stdout
+    gram = [ln.split()[-1] for ln in nm.splitlines() if "svgd_pairgram_kernelILi20ELb1" in ln]
+    assert gram, "pairgram<20> is not in the library"
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", gram[0], str(built_lib)], capture_output=True, text=True).stdout
     assert sass.count("FFMA2") >= 380 and "UTMALDG.2D" in sass, "pairgram<20> lost its packed inner loop / TMA tensor load"
 
 
