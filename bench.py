@@ -100,7 +100,8 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------
-# CPU baseline: the reference's op sequence (oracle port) on the host cores
+# CPU baseline / reference arm: the UNMODIFIED reference SVGDOptimizer.step (oracle/_ref, staged by
+# oracle/install_ref.py) on the host cores; the oracle's port of its op sequence only if oracle/_ref is missing
 # --------------------------------------------------------------------------------------
 def synth_host(n, D, seed=0):
     g = torch.Generator().manual_seed(seed)
@@ -110,39 +111,64 @@ def synth_host(n, D, seed=0):
     return X, G
 
 
+REF_INCLUDES = ("whole SVGDOptimizer.step of the reference (src/algos/svgd.py:65-105) with free closures: per-particle "
+                "_use_particle / grad clone, gather into [n, D] (parameters_to_vector + stack), prior term, rbf (cdist, "
+                "quantile, exp, matmul), phi, per-particle scatter (slice + clone) and n plain-SGD base-optimizer steps")
+
+
 def cpu_reference_run(steps: int, warmup: int, D: int = CPU_SAMPLE_D, threads: int | None = None):
-    """Times oracle.svgd_step_reference_order (the same ATen op sequence as svgd.py:86-89 + rbf)
-    in fp32 with every host thread torch will use (or `threads`).  Returns (GB/s, ms/step, threads)."""
-    from oracle import bde_oracle as O
+    """Times the posterior-update path of the reference on the host in fp32 with every host thread torch will use
+    (or `threads`).  Returns (GB/s, ms/step, threads, kind, D): kind "reference" = the unmodified SVGDOptimizer.step
+    from oracle/_ref driven by oracle/ref_driver.py; "port" = oracle.svgd_step_reference_order (same ATen op
+    sequence, no gather / scatter / base optimizer) when the staged reference is absent."""
+    from oracle import install_ref
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    X, G = synth_host(N_PARTICLES, D)
-    for _ in range(max(1, warmup)):
-        O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
-    times = []
-    for _ in range(max(1, steps)):
+    if install_ref.available():
+        from oracle import ref_driver
+        X, G = ref_driver.synth(N_PARTICLES, D, "cpu")
+        job = ref_driver.ReferenceSvgdJob(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
         t0 = time.perf_counter()
-        O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
-        times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
+        job.step()                                   # first warm-up step, also the size probe
+        first = time.perf_counter() - t0
+        if first * (steps + warmup) > 240.0 and D > 2_000_000:   # keep the whole run inside a few minutes
+            return cpu_reference_run(steps, warmup, D // 5, threads)
+        ms = ref_driver.time_reference_steps(job, max(1, steps), max(0, warmup - 1))
+        kind = "reference"
+    else:
+        from oracle import bde_oracle as O
+        X, G = synth_host(N_PARTICLES, D)
+        for _ in range(max(1, warmup)):
+            O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
+            O.svgd_step_reference_order(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        ms = 1e3 * (time.perf_counter() - t0) / max(1, steps)
+        kind = "port"
     gbs = 16.0 * N_PARTICLES * D / (ms * 1e-3) / 1e9
-    return gbs, ms, torch.get_num_threads()
+    return gbs, ms, torch.get_num_threads(), kind, D
+
+
+def cpu_sample_text(kind, D, steps):
+    what = ("the unmodified reference SVGDOptimizer.step (oracle/_ref/src/algos/svgd.py driven by oracle/ref_driver.py: "
+            + REF_INCLUDES + ")") if kind == "reference" else \
+           "oracle.svgd_step_reference_order (port of the reference's ATen op sequence; no gather / scatter / base optimizer)"
+    return (f"n={N_PARTICLES} x D={D} fp32 on the host ({D / D_PER_GPU:.0%} of one GPU's columns; the rate is per byte, so "
+            f"the sample size does not enter the metric), {steps} timed steps of {what}")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = min(args.steps, 10)
-    gbs, ms, threads = cpu_reference_run(steps, min(args.warmup, 2))
-    sample = (f"n={N_PARTICLES} x D={CPU_SAMPLE_D} fp32 on the host ({CPU_SAMPLE_D / D_PER_GPU:.0%} of one GPU's columns), "
-              f"{steps} timed steps of oracle.svgd_step_reference_order (reference op order, torch CPU ops)")
+    steps, warmup = max(1, args.steps), max(1, args.warmup)   # same steps / warm-up as the GPU arm
+    gbs, ms, threads, kind, D = cpu_reference_run(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": kind, "sample": cpu_sample_text(kind, D, steps)},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -158,6 +184,32 @@ def workload_config(n_gpus):
         "parallelism": f"D-shard x{n_gpus}; only the 10x10 fp64 partial distances cross NVLink (summed inside K1's tail "
                        "over peer memory, or by one NCCL all-reduce)",
     }
+
+
+def eager_cuda_reference(dev, D=None, steps=3):
+    """The kernel-for-kernel competitor of SURVEY.md §8(d): the same unmodified reference class, eager PyTorch on THIS
+    GPU (device-resident inputs, wall clock bracketed by synchronize).  None if oracle/_ref is not staged."""
+    from oracle import install_ref
+    if not install_ref.available():
+        return None
+    from oracle import ref_driver
+    D = D or D_PER_GPU
+    try:
+        X, G = ref_driver.synth(N_PARTICLES, D, dev)
+        job = ref_driver.ReferenceSvgdJob(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+        del X
+        ms = ref_driver.time_reference_steps(job, steps, 1, sync=torch.cuda.synchronize)
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 1e9
+        res = {"ms_per_step": ms, "GBps": 16.0 * N_PARTICLES * D / (ms * 1e-3) / 1e9, "steps": steps, "kind": "reference",
+               "what": f"oracle/_ref SVGDOptimizer.step, eager PyTorch on the same GPU, n={N_PARTICLES} x D={D}: " + REF_INCLUDES,
+               "peak_device_memory_GB": peak_gb}
+        log(f"[bench] reference eager on this GPU: {ms:.2f} ms/step")
+        del job, G
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] eager_cuda reference failed: {e}")
+        res = {"error": str(e)}
+    torch.cuda.empty_cache()
+    return res
 
 
 # --------------------------------------------------------------------------------------
@@ -335,6 +387,27 @@ def other_paths(ops, peak_gbs, dev):
         f"({ms_unfused / ms_fused:.2f}x)")
     del Xf, Gf, Of, buf, olast, param, base
     torch.cuda.empty_cache()
+    # n = 20 (the CIFAR particle count) and n = 16 at a bandwidth-bound D: K1 = centred-Gram kernel, K2 on tensor-map tiles
+    for nn_, Dn in ((20, 50_000_000), (16, 60_000_000)):
+        Xn = torch.empty(nn_, Dn, device=dev)
+        Gn = torch.empty(nn_, Dn, device=dev)
+        for i in range(nn_):
+            Xn[i].normal_(0.0, 0.05 * (1 + 0.1 * i), generator=g)
+            Gn[i].normal_(0.0, 1e-3, generator=g)
+        On = torch.empty_like(Xn)
+        scn = ops.SvgdScratch.allocate(nn_, dev)
+        rec(f"svgd_pairdist_n{nn_}", time_kernel(lambda: ops.svgd_pairdist_bandwidth(Xn, scn, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE), 10, 3),
+            4 * nn_ * Dn, f"n={nn_} x D={Dn}: K1 (centred Gram, tensor-map TMA) + fused K1b; exact redo fired: {scn.exact_redo()}")
+        rec(f"svgd_apply_n{nn_}", time_kernel(lambda: ops.svgd_apply(Xn, Gn, On, scn), 10, 3), 12 * nn_ * Dn, f"n={nn_} x D={Dn}: K2")
+        rec(f"svgd_step_n{nn_}", time_kernel(lambda: ops.svgd_step(Xn, Gn, On, scn, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE), 10, 3),
+            16 * nn_ * Dn, f"n={nn_} x D={Dn}: K1 + K1b + K2 (two launches + the conditional exact-redo launch)")
+        bufn = torch.zeros(Dn, device=dev)
+        rec(f"svgd_apply_fused_sgd_n{nn_}",
+            time_kernel(lambda: ops.svgd_apply_sgd(Xn, Gn, scn, bufn, buf_initialized=True, lr=1e-7, momentum=0.9, nesterov=True,
+                                                   weight_decay=3e-4), 10, 3),
+            (12 * nn_ + 8) * Dn, f"n={nn_} x D={Dn}: K2 + {nn_} SGD steps in one pass, X in place")
+        del Xn, Gn, On, scn, bufn
+        torch.cuda.empty_cache()
     # C2 CIFAR ResNet-20 SVGD, n = 20 (small D: latency-bound, reported as time)
     n2, D2 = 20, 273_610
     D2p = (D2 + 63) // 64 * 64
@@ -351,6 +424,93 @@ def other_paths(ops, peak_gbs, dev):
     sc1 = ops.SvgdScratch.allocate(10, dev)
     rec("svgd_step_n10_uci", time_kernel(lambda: ops.svgd_step(X1, G1, O1, sc1, 0.01, 1.0, 768.0), 50, 5),
         16 * 10 * 512, "UCI MLP D=501, n=10 (launch latency)")
+    return res
+
+
+def strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel, steps):
+    """D_total = 1e8 and 1e9 columns x n particles split over the `world` ranks (every rank [n, D_total / world]),
+    timed like the headline step (barrier, CUDA events, max over ranks); rank 0 then runs the SAME total problem alone
+    on its GPU, so the speed-up is measured inside one run.  With the in-kernel exchange the per-rank wait of K1's
+    tail for its slowest peer (rank skew) is reported next to it."""
+    from beyond_deep_ensembles_b200.layout import shard_bounds
+    res = {}
+    for D_total in (100_000_000, 1_000_000_000):
+        lo, hi = shard_bounds(D_total, world, rank)
+        Dl = hi - lo
+        g = torch.Generator(device=dev).manual_seed(77 + rank)
+        Xs = torch.empty(n, Dl, device=dev)
+        Gs = torch.empty(n, Dl, device=dev)
+        for i in range(n):
+            Xs[i].normal_(0.0, 0.05 * (1 + 0.1 * i), generator=g)
+            Gs[i].normal_(0.0, 1e-3, generator=g)
+        Os = torch.empty_like(Xs)
+
+        def one(scr, X_, G_, O_, single):
+            if single or in_kernel:
+                ops.svgd_pairdist_bandwidth(X_, scr, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+            else:
+                ops.svgd_pairdist(X_, scr)
+                bdist.allreduce_dist(scr)
+                ops.svgd_bandwidth(scr, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+            ops.svgd_apply(X_, G_, O_, scr)
+
+        for _ in range(3):
+            one(sc, Xs, Gs, Os, False)
+        torch.cuda.synchronize()
+        if sc.peers is not None:
+            sc.peers.wait_stats(reset=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one(sc, Xs, Gs, Os, False)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        entry = {"D_total": D_total, "D_per_gpu": D_total // world, "ms_per_step": t.item(),
+                 "GBps_aggregate": 16.0 * n * D_total / (t.item() * 1e-3) / 1e9}
+        if sc.peers is not None:
+            cnt, wsum, wmax = sc.peers.wait_stats(reset=True)
+            w = torch.tensor([wsum / max(cnt, 1) / 1e3, wmax / 1e3], dtype=torch.float64, device=dev)
+            allw = [torch.zeros_like(w) for _ in range(world)]
+            dist.all_gather(allw, w)
+            entry["peer_wait_us_per_rank"] = {"mean": [round(float(x[0]), 2) for x in allw],
+                                              "max": [round(float(x[1]), 2) for x in allw],
+                                              "what": "time K1's last CTA waited for its slowest peer per exchange (rank skew)"}
+        del Xs, Gs, Os
+        torch.cuda.empty_cache()
+        if world > 1:
+            t1 = torch.zeros(1, dtype=torch.float64, device=dev)
+            if rank == 0:   # the same TOTAL problem on one GPU, unattached scratch
+                sc1 = ops.SvgdScratch.allocate(n, dev)
+                X1 = torch.empty(n, D_total, device=dev)
+                G1 = torch.empty(n, D_total, device=dev)
+                for i in range(n):
+                    X1[i].normal_(0.0, 0.05 * (1 + 0.1 * i), generator=g)
+                    G1[i].normal_(0.0, 1e-3, generator=g)
+                O1 = torch.empty_like(X1)
+                for _ in range(2):
+                    one(sc1, X1, G1, O1, True)
+                torch.cuda.synchronize()
+                k = max(2, steps // 2)
+                e0.record()
+                for _ in range(k):
+                    one(sc1, X1, G1, O1, True)
+                e1.record()
+                torch.cuda.synchronize()
+                t1[0] = e0.elapsed_time(e1) / k
+                del X1, G1, O1, sc1
+                torch.cuda.empty_cache()
+            dist.all_reduce(t1, op=dist.ReduceOp.MAX)
+            entry["ms_per_step_1gpu_same_total"] = t1.item()
+            entry["speedup"] = t1.item() / t.item()
+            entry["efficiency"] = t1.item() / t.item() / world
+        res[f"D{D_total:.0e}".replace("+0", "").replace("+", "")] = entry
+        log(f"[bench] strong D_total={D_total}: {entry}")
     return res
 
 
@@ -490,9 +650,17 @@ def main():
             sc = sc_peer
             in_kernel[0] = True
 
+    # ---- strong scaling: a FIXED total problem split N ways (north star: near-linear 1 -> 8 at D >= 100 M x 10) ----
+    strong = None
+    if not args.skip_extras:
+        del out
+        strong = strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel[0], max(3, min(steps, 10)))
+        out = torch.empty_like(X)
+        step()   # K / A of the headline problem back in the scratch, `out` refilled (the e2e leg compares against it)
+
     # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
     e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
-    paths, cpu_base = None, None
+    paths, cpu_base, eager = None, None, None
     if not args.skip_extras:
         try:
             import psutil
@@ -544,12 +712,11 @@ def main():
             except Exception as e:  # noqa: BLE001
                 log(f"[bench] other paths failed: {e}")
                 paths = {"error": str(e)}
-            gbs, ms, threads = cpu_reference_run(3, 1)
-            cpu_base = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "cores": threads, "kind": "port",
-                        "sample": f"n={N_PARTICLES} x D={CPU_SAMPLE_D} fp32 on the host ({CPU_SAMPLE_D / D_PER_GPU:.0%} of "
-                                  "one GPU's columns), 3 timed steps of oracle.svgd_step_reference_order "
-                                  "(reference op order, torch CPU ops, all host threads)"}
-            gbs8, ms8, t8 = cpu_reference_run(2, 1, threads=min(8, os.cpu_count() or 1))   # second run pinned to 8 threads
+            eager = eager_cuda_reference(dev)
+            gbs, ms, threads, kind, Dc = cpu_reference_run(3, 1)
+            cpu_base = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "cores": threads, "kind": kind,
+                        "sample": cpu_sample_text(kind, Dc, 3) + ", all host threads"}
+            gbs8, ms8, t8, _, _ = cpu_reference_run(2, 1, threads=min(8, os.cpu_count() or 1))   # second run pinned to 8 threads
             cpu_base["pinned_threads_run"] = {"value": gbs8, "unit": "GB/s", "ms_per_step": ms8, "cores": t8}
 
     if rank == 0:
@@ -579,7 +746,7 @@ def main():
             },
             "step_frac_of_measured_peak": value / world / peak_gbs,
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
-            "cpu_baseline": cpu_base, "paths": paths, "exchange": exchange,
+            "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
         try:

@@ -38,6 +38,7 @@ SIGNATURES = {
     "bde_peer_attach": [_p, _sz, _i, _i, C.POINTER(_u64), _d, _p, _p],
     "bde_peer_detach": [_p, _sz, _p],
     "bde_peer_status": [_p, C.POINTER(_u64), C.POINTER(_u64)],
+    "bde_peer_wait_stats": [_p, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _i],
     "bde_svgd_pairdist": [_p, _i, _i64, _i64, _p, _i, _p, _sz, _p],
     "bde_svgd_bandwidth": [_p, _i, _d, _d, _d, _d, _p, _p, _p, _p, _p],
     "bde_svgd_apply": [_p, _p, _p, _p, _p, _i, _i64, _i64, _p],

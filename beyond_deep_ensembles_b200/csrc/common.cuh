@@ -231,7 +231,10 @@ constexpr int kPeerMaxVals = 512;   // >= pair_count(BDE_MAX_PARTICLES) = 496
 struct PeerBuf {                    // one per rank, cudaMalloc'ed (IPC-shareable), zero-filled
     unsigned long long epoch;       // exchanges completed on this rank (device-side counter)
     unsigned long long timeouts;    // exchanges abandoned after kPeerTimeoutNs (results poisoned with NaN)
-    unsigned long long pad[14];
+    unsigned long long wait_ns_sum; // time the last CTA spent waiting for its slowest peer, summed over exchanges ...
+    unsigned long long wait_ns_max; // ... and the longest single wait (rank skew; bde_peer_wait_stats)
+    unsigned long long waits;       // exchanges counted in the two fields above
+    unsigned long long pad[11];
     unsigned long long flags[2][kPeerMaxRanks][4];   // [parity][writer rank], one 32-byte sector each
     double slots[2][kPeerMaxRanks][kPeerMaxVals];    // [parity][writer rank][value]
 };
@@ -290,10 +293,12 @@ __device__ __forceinline__ void peer_allreduce_fp64(WsHeader* h, double* total, 
     }
     PeerBuf* me = h->peer[rank];
     __shared__ unsigned long long s_epoch;
+    __shared__ unsigned long long s_wait_ns;
     __shared__ int s_timed_out;
     if (tid == 0) {
         s_epoch = *reinterpret_cast<volatile unsigned long long*>(&me->epoch) + 1ull;
         s_timed_out = 0;
+        s_wait_ns = 0ull;
     }
     __syncthreads();
     const unsigned long long epoch = s_epoch;
@@ -314,6 +319,7 @@ __device__ __forceinline__ void peer_allreduce_fp64(WsHeader* h, double* total, 
                 break;
             }
         }
+        atomicMax(&s_wait_ns, globaltimer_ns() - t0);   // the slowest peer sets the wait of this exchange
     }
     __syncthreads();
     const bool bad = s_timed_out != 0;
@@ -324,6 +330,9 @@ __device__ __forceinline__ void peer_allreduce_fp64(WsHeader* h, double* total, 
     }
     if (tid == 0) {
         *reinterpret_cast<volatile unsigned long long*>(&me->epoch) = epoch;
+        me->wait_ns_sum += s_wait_ns;
+        if (s_wait_ns > me->wait_ns_max) me->wait_ns_max = s_wait_ns;
+        me->waits += 1ull;
         if (bad) {
             const unsigned long long nbad = me->timeouts + 1ull;
             *reinterpret_cast<volatile unsigned long long*>(&me->timeouts) = nbad;

@@ -92,3 +92,16 @@ extern "C" int bde_peer_status(const void* buf, uint64_t* epoch_host, uint64_t* 
     if (timeouts_host) *timeouts_host = v[1];
     return BDE_OK;
 }
+
+extern "C" int bde_peer_wait_stats(void* buf, uint64_t* exchanges_host, uint64_t* wait_ns_sum_host, uint64_t* wait_ns_max_host,
+                                   int reset) {
+    if (!buf) return BDE_ERR_INVALID_ARG;
+    PeerBuf* pb = static_cast<PeerBuf*>(buf);
+    unsigned long long v[3] = {0, 0, 0};   // wait_ns_sum, wait_ns_max, waits are consecutive fields
+    BDE_RETURN_IF_CUDA(cudaMemcpy(v, &pb->wait_ns_sum, sizeof(v), cudaMemcpyDeviceToHost));
+    if (wait_ns_sum_host) *wait_ns_sum_host = v[0];
+    if (wait_ns_max_host) *wait_ns_max_host = v[1];
+    if (exchanges_host) *exchanges_host = v[2];
+    if (reset) BDE_RETURN_IF_CUDA(cudaMemset(&pb->wait_ns_sum, 0, sizeof(v)));
+    return BDE_OK;
+}

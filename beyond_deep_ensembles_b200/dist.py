@@ -117,6 +117,14 @@ class PeerSet:
         _lib.check(_lib.get().bde_peer_status(self._own, C.byref(e), C.byref(t)), "bde_peer_status")
         return e.value, t.value
 
+    def wait_stats(self, reset: bool = False):
+        """(exchanges, summed wait ns, longest wait ns) of this rank's in-kernel exchanges since the last reset: the
+        time the last CTA of K1 spent waiting for its slowest peer — rank skew, not link time.  Synchronises."""
+        n, s, m = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _lib.check(_lib.get().bde_peer_wait_stats(self._own, C.byref(n), C.byref(s), C.byref(m), int(reset)),
+                   "bde_peer_wait_stats")
+        return n.value, s.value, m.value
+
     def close(self, barrier: bool = True) -> None:
         """Detach the workspaces, unmap the peers and free this rank's buffer.  Collective when barrier=True:
         no rank may free its buffer while a peer's kernel can still write into it."""

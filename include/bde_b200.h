@@ -369,6 +369,10 @@ int bde_peer_attach(void* workspace, size_t workspace_bytes, int world, int rank
 int bde_peer_detach(void* workspace, size_t workspace_bytes, bde_stream_t stream);
 /* exchanges completed / abandoned on this rank's buffer (synchronous device read) */
 int bde_peer_status(const void* buf, uint64_t* epoch_host, uint64_t* timeouts_host);
+/* How long this rank's exchanges waited for their slowest peer (rank skew): number of exchanges, summed and longest
+ * wait in ns since the last reset.  Synchronises; reset != 0 clears the counters. */
+int bde_peer_wait_stats(void* buf, uint64_t* exchanges_host, uint64_t* wait_ns_sum_host, uint64_t* wait_ns_max_host,
+                        int reset);
 
 /* ---- utilities ------------------------------------------------------------ */
 

@@ -73,7 +73,7 @@ class FakeLib:
         return -1
 
     bde_peer_alloc = bde_peer_open = bde_peer_close = bde_peer_free = _no_peer
-    bde_peer_attach = bde_peer_detach = bde_peer_status = _no_peer
+    bde_peer_attach = bde_peer_detach = bde_peer_status = bde_peer_wait_stats = _no_peer
 
     def bde_svgd_pairdist(self, X, n, D, ld, dist, accumulate, ws, wsb, stream):
         self.calls.append("pairdist")

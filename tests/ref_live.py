@@ -1,0 +1,274 @@
+"""Helper of tests/test_reference_on_gpu.py (run as a subprocess): the reference's OWN experiment factories on a CUDA
+device, first with the unmodified reference classes (oracle/_ref), then after `bde.install()` with this package's
+— same seeds, same data, identical injected noise — and the two trajectories compared.
+
+    python tests/ref_live.py <task> <algo>        # task: uci | cifar ; algo: svgd | swag | ivon | bbb | rank1
+
+Prints REF_LIVE_OK on success.  Nothing here reads /root/reference: the staged copy under oracle/_ref travels with
+the snapshot (oracle/install_ref.py).
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+from oracle import install_ref  # noqa: E402
+
+install_ref.add_to_path()
+
+RTOL, ATOL = 1e-5, 1e-6          # north star, per update
+RTOL_C, ATOL_C = 3e-5, 3e-6      # where two optimizer steps (n base-optimizer steps each) compound
+STEPS = 2
+
+
+def uci_config(algo):
+    base = {"in_dim": 8, "std_init": 1.0, "learn_var": False, "members": 1, "prior_std": 1.0}
+    extra = {
+        "svgd": {"optimizer": {"base": {"lr": 1e-3, "weight_decay": 0},
+                               "svgd": {"particle_count": 10, "l2_reg": 0.01, "dataset_size": 768, "kernel_grad_scale": 1.0}}},
+        "swag": {"optimizer": {"base": {"lr": 1e-3}, "swag": {"start_epoch": 0, "update_interval": 1, "deviation_samples": 5}}},
+        "ivon": {"optimizer": {"ivon": {"lr": 1e-3, "prior_prec": 1.0, "dataset_size": 768, "damping": 1e-3, "mc_samples": 2}}},
+        "rank1": {"optimizer": {"base": {"lr": 1e-3}, "rank1": {"mc_samples": 2, "kl_rescaling": 1.0, "dataset_size": 768,
+                                                                 "components": 1, "l2_scale": 0.1}}},
+        "bbb": {"optimizer": {"base": {"lr": 1e-3}, "bbb": {"mc_samples": 2, "kl_rescaling": 1.0, "dataset_size": 768}}},
+    }[algo]
+    return {**base, **extra}
+
+
+def cifar_config(algo):
+    """experiments/cifar/cifar.yaml's optimizer settings (ResNet-20-FRN, D = 273,610, 96 tensors)."""
+    cfg = {"members": 1, "use_compile": False, "prior_std": 1.0, "components": 2,
+           "base_optimizer": {"lr": 0.05, "momentum": 0.9, "nesterov": True, "weight_decay": 3e-4},
+           "svgd": {"particle_count": 20, "l2_reg": 3e-4, "dataset_size": 50000},
+           "swag": {"update_interval": 1, "start_epoch": 0, "deviation_samples": 4},
+           "ivon": {"lr": 0.05, "prior_prec": 50.0, "dataset_size": 50000, "damping": 1e-3, "augmentation": 10, "mc_samples": 2},
+           "bbb": {"mc_samples": 2, "kl_rescaling": 0.2, "dataset_size": 50000}}
+    if algo == "rank1":
+        cfg["bbb"] = {"mc_samples": 2, "kl_rescaling": 1.0, "dataset_size": 50000, "components": 2, "l2_scale": 3e-4}
+    return cfg
+
+
+def batches(task, dev):
+    g = torch.Generator().manual_seed(5)
+    if task == "uci":
+        w = torch.randn(8, generator=g)
+        xs = [torch.randn(32, 8, generator=g) for _ in range(STEPS)]
+        return [(x.to(dev), (x @ w + 0.1 * torch.randn(32, generator=g)).to(dev)) for x in xs]
+    return [(torch.randn(16, 3, 32, 32, generator=g).to(dev), torch.randint(0, 10, (16,), generator=g).to(dev))
+            for _ in range(STEPS)]
+
+
+def closures(task, model, x, y):
+    if task == "uci":
+        def fwd():
+            out = model(x)                       # [B, 1, 2]: mean and std from the reference's GaussLayer
+            return ((out[..., 0].squeeze(-1) - y) ** 2).mean()
+    else:
+        def fwd():
+            return torch.nn.functional.nll_loss(model(x), y)
+    return fwd, lambda loss: loss.backward()
+
+
+class Recorder:
+    """Reference side: draws noise from a seeded CPU generator at the reference's draw points and logs it."""
+
+    def __init__(self, seed):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.log = []
+
+    def normal_like(self, tensor):
+        z = torch.randn(tensor.shape, generator=self.gen, dtype=torch.float32)
+        self.log.append(z.reshape(-1))
+        return z.to(tensor.device, tensor.dtype)
+
+
+class Replayer:
+    """Second run: ONE tape for every consumer, in call order — the reference's own layer code that stays in place
+    after install() (bbb_layers.py's activation noise, patched `normal_like`) and this package's kernels
+    (`noise.inject`).  This package draws one noise vector where the reference draws several (iVON: one per
+    parameter group instead of one per tensor), so a request of `numel` elements is served by concatenating the
+    next recorded draws."""
+
+    def __init__(self, chunks):
+        self.it = iter(chunks)
+
+    def take(self, numel, what):
+        got, parts = 0, []
+        while got < numel:
+            c = next(self.it)
+            parts.append(c)
+            got += c.numel()
+        assert got == numel, f"noise tape out of step: wanted {numel} elements for {what!r}, recorded draws give {got}"
+        return torch.cat(parts)
+
+    def normal_like(self, tensor):
+        return self.take(tensor.numel(), "normal_like").view(tensor.shape).to(tensor.device, tensor.dtype)
+
+    def inject(self, kind, numel):
+        return self.take(numel, kind)
+
+
+def _base_of(opt):
+    try:
+        base = opt.get_base_optimizer()
+    except Exception:  # noqa: BLE001
+        return None
+    return base if isinstance(base, torch.optim.Optimizer) and base is not opt else None
+
+
+def snapshot(algo, model, opt):
+    """Everything the next step depends on, as flat CPU arrays."""
+    def cat(ts):
+        return torch.cat([t.detach().reshape(-1).float().cpu() for t in ts]).numpy()
+    out = {"params": cat(model.parameters())}
+    params = [p for g in opt.param_groups for p in g["params"]]
+    if algo == "svgd":
+        n = opt.state["__particle_count"]
+        out["particles"] = np.stack([cat(opt.state[p][f"particle_{i}"] for p in params) for i in range(n)])
+    elif algo == "ivon":
+        for key in ("mean", "momentum", "precision"):
+            out[key] = cat(opt.state[p][key] for p in params)
+    base = _base_of(opt)
+    if base is not None:
+        bparams = [p for g in base.param_groups for p in g["params"]]
+        for key in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
+            if bparams and all(key in base.state[p] for p in bparams):
+                out[f"base.{key}"] = cat(base.state[p][key] for p in bparams)
+    return out
+
+
+def force_state(algo, model, opt, snap):
+    """Teacher forcing: overwrite everything the next step depends on with a recorded state, IN PLACE (the in-place
+    copies bump autograd's version counters, which is also what drops this package's cached SVGD kernel)."""
+    def scatter(ts, flat):
+        off = 0
+        for t in ts:
+            k = t.numel()
+            t.copy_(torch.from_numpy(flat[off:off + k]).view(t.shape).to(t.device, t.dtype))
+            off += k
+        assert off == flat.size
+    params = [p for g in opt.param_groups for p in g["params"]]
+    with torch.no_grad():
+        scatter(list(model.parameters()), snap["params"])
+        if algo == "svgd":
+            for i in range(opt.state["__particle_count"]):
+                scatter([opt.state[p][f"particle_{i}"] for p in params], snap["particles"][i])
+        elif algo == "ivon":
+            for key in ("mean", "momentum", "precision"):
+                scatter([opt.state[p][key] for p in params], snap[key])
+        base = _base_of(opt)
+        if base is not None:
+            bparams = [p for g in base.param_groups for p in g["params"]]
+            for key in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
+                if f"base.{key}" in snap:
+                    scatter([base.state[p][key] for p in bparams], snap[f"base.{key}"])
+
+
+def run(task, algo, dev, forced=None):
+    """One member of the reference's factory ensemble, STEPS optimizer steps; returns losses + snapshots.
+    forced: snapshots of another run — before step s >= 1 the state is overwritten with forced[s - 1]."""
+    models = importlib.import_module(f"experiments.{task}.models")
+    torch.manual_seed(1234)
+    if dev.type == "cuda":
+        torch.cuda.manual_seed_all(1234)
+    ens = models.get_model(algo, uci_config(algo) if task == "uci" else cifar_config(algo), dev)
+    model, opt = ens.models_and_optimizers[0]
+    losses, snaps = [], []
+    for s, (x, y) in enumerate(batches(task, dev)):
+        if forced is not None and s >= 1:
+            force_state(algo, model, opt, forced[s - 1])
+        fwd, bwd = closures(task, model, x, y)
+        loss = opt.step(fwd, bwd)
+        opt.complete_epoch()
+        losses.append(float(loss))
+        snaps.append(snapshot(algo, model, opt))
+    return type(opt), losses, snaps
+
+
+def main():
+    task, algo = sys.argv[1], sys.argv[2]
+    import os
+    # the model's forward / backward must be the same function of its inputs in both runs
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    dev = torch.device(os.environ.get("REF_LIVE_DEVICE", "cuda:0"))
+    if dev.type == "cpu":   # host-logic run (CPU suite): the C-ABI is the oracle-backed double of tests/fake_abi.py
+        import fake_abi
+
+        class _P:
+            def setattr(self, o, n, v):
+                setattr(o, n, v)
+        fake_abi.install(_P())
+        torch.set_num_threads(1)
+    else:
+        assert torch.cuda.is_available()
+    # ---- the unmodified reference, eager PyTorch on this GPU, noise recorded at its own draw points ----
+    import src.algos.util as ref_util
+    import src.algos.ivorn as ref_ivorn
+    import src.algos.bbb_layers as ref_layers
+    rec = Recorder(99)
+    for mod in (ref_util, ref_ivorn, ref_layers):
+        mod.normal_like = rec.normal_like
+    ref_cls, ref_losses, ref_snaps = run(task, algo, dev)
+    assert ref_cls.__module__.startswith("src.algos"), ref_cls
+    # A deep network amplifies rounding-level differences from one optimizer step to the next (measured on the
+    # ResNet-20 / SVGD case: the reference against itself with K scaled by 1 + 1e-6 moves 1.6e-7 after step 0 and
+    # 2e-4 after step 1; on a GPU the model's own atomics are enough), so on the CIFAR models every step after the
+    # first starts from the reference's recorded state (teacher forcing): each step is then a one-update comparison.
+    note, forced = "", (ref_snaps if task == "cifar" else None)
+    if task == "cifar" and algo == "svgd":
+        # SURVEY.md §8c caveat 1: at D = 273,610 the reference's fp32 `cdist` reduction is off by ~1e-4 and a deep
+        # network amplifies that over the 20 momentum steps of one SVGD step (the reference in fp32 and the SAME
+        # reference code with rbf evaluated on .double() inputs drift 2e-4 apart within two steps).  Parity above
+        # D ~ 1e4 is therefore asserted against the reference with its own rbf() run in fp64; the distance of the
+        # fp32 reference from it is reported alongside.
+        import src.algos.svgd as ref_svgd
+        rbf32 = ref_svgd.rbf
+
+        def rbf64(x, h_override=None):
+            k, gk = rbf32(x.double(), h_override)
+            return k.to(x.dtype), gk.to(x.dtype)
+        ref_svgd.rbf = rbf64
+        _, ref_losses64, ref_snaps64 = run(task, algo, dev)
+        drift = max(float(np.abs(a["particles"] - b["particles"]).max()) for a, b in zip(ref_snaps, ref_snaps64))
+        note = f"; fp32 reference drifts {drift:.2e} from the fp64-rbf reference over {STEPS} free-running steps"
+        ref_losses, ref_snaps = ref_losses64, ref_snaps64
+        forced = ref_snaps
+    # ---- the same factories after install(): this package's classes on the C-ABI library ----
+    import beyond_deep_ensembles_b200 as bde
+    from beyond_deep_ensembles_b200 import _lib, noise
+    if dev.type == "cuda":
+        _lib.get()
+    patched = bde.install()
+    assert "src.algos.svgd.SVGDOptimizer" in patched, patched
+    importlib.reload(importlib.import_module(f"experiments.{task}.models"))   # re-bind its `from src.algos... import`
+    launches0 = _lib.launch_count
+    rep = Replayer(rec.log)
+    for mod in (ref_util, ref_ivorn, ref_layers):
+        mod.normal_like = rep.normal_like
+    with noise.inject(rep.inject):
+        our_cls, our_losses, our_snaps = run(task, algo, dev, forced=forced)
+    assert next(rep.it, None) is None, "the installed path consumed fewer noise draws than the reference"
+    assert our_cls.__module__.startswith("beyond_deep_ensembles_b200"), our_cls
+    assert dev.type == "cpu" or _lib.launch_count > launches0, "no C-ABI launch happened: the CUDA path did not run"
+    # ---- compare ----
+    for s in range(STEPS):
+        np.testing.assert_allclose(our_losses[s], ref_losses[s], rtol=2e-5, err_msg=f"loss of step {s}")
+        for key, ref in ref_snaps[s].items():
+            rt, at = (RTOL, ATOL) if s == 0 and algo != "svgd" else (RTOL_C, ATOL_C)
+            np.testing.assert_allclose(our_snaps[s][key], ref, rtol=rt, atol=at, err_msg=f"{key} after step {s}")
+    print(f"REF_LIVE_OK {task} {algo}: {our_cls.__name__} == {ref_cls.__module__}.{ref_cls.__name__} over {STEPS} steps "
+          f"({_lib.launch_count - launches0} C-ABI launches){note}")
+
+
+if __name__ == "__main__":
+    main()
