@@ -195,6 +195,7 @@ def eager_cuda_reference(dev, D=None, steps=3):
     from oracle import ref_driver
     D = D or D_PER_GPU
     try:
+        torch.cuda.reset_peak_memory_stats(dev)
         X, G = ref_driver.synth(N_PARTICLES, D, dev)
         job = ref_driver.ReferenceSvgdJob(X, G, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
         del X

@@ -19,6 +19,103 @@ class _Patch:
         setattr(obj, name, value)
 
 
+def run_timeout(rank: int, world: int, port: int, out_path: str):
+    """A rank that never reaches its exchange: the waiting rank's kernel gives up after BDE_PEER_TIMEOUT_S, leaves
+    K / A untouched, marks the workspace failed (later exchanges return at once) and PeerSet.check() raises."""
+    import time
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), BDE_PEER_TIMEOUT_S="2")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from beyond_deep_ensembles_b200 import _lib
+    from beyond_deep_ensembles_b200 import dist as bdist
+    from beyond_deep_ensembles_b200 import ops
+    n, D = 10, 300_000
+    g = torch.Generator().manual_seed(7 + rank)
+    X = (torch.randn(n, D, generator=g) * 0.05).to(dev)
+    sc = ops.SvgdScratch.allocate(n, dev)
+    assert bdist.enable_peer_exchange(sc)
+    ops.svgd_pairdist_bandwidth(X, sc, 0.01, 1.0, 50000.0)      # a good exchange on every rank
+    torch.cuda.synchronize()
+    sc.peers.check()
+    K_good = sc.K.clone()
+    res = {"rank": rank}
+    dist.barrier()
+    if rank == 0:
+        t0 = time.time()
+        ops.svgd_pairdist_bandwidth(X * 1.5, sc, 0.01, 1.0, 50000.0)   # the peer never launches this one
+        torch.cuda.synchronize()
+        res["waited_s"] = time.time() - t0
+        res["K_unchanged"] = bool(torch.equal(sc.K, K_good))
+        res["dist_poisoned"] = bool(torch.isnan(sc.dist).any())
+        try:
+            sc.peers.check()
+            res["raised"] = False
+        except _lib.BdeError as e:
+            res["raised"] = True
+            res["message"] = str(e)
+        t0 = time.time()
+        ops.svgd_pairdist_bandwidth(X, sc, 0.01, 1.0, 50000.0)          # failed workspace: no second wait
+        torch.cuda.synchronize()
+        res["second_wait_s"] = time.time() - t0
+        res["status"] = sc.peers.status()
+    else:
+        time.sleep(5.0)
+    torch.save(res, f"{out_path}.{rank}")
+    dist.barrier()
+    bdist.shutdown_peer_exchange()
+    dist.destroy_process_group()
+
+
+def run_rank_local(rank: int, world: int, port: int, out_path: str, backend: str = "nccl"):
+    """SVGDOptimizer(process_group=None) under an initialised default group: no collective, rank-local bandwidth."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(1)
+        import fake_abi
+        fake_abi.install(_Patch())
+    import beyond_deep_ensembles_b200 as bde
+    import golden_models as gm
+
+    def one_step():
+        torch.manual_seed(100 + rank)           # DDP-style: every rank its own particles / data
+        model = gm.make_mlp().to(dev)
+        base = torch.optim.SGD(model.parameters(), lr=1e-2)
+
+        def reset():
+            for m in model:
+                if hasattr(m, "reset_parameters"):
+                    m.reset_parameters()
+        opt = bde.SVGDOptimizer(model.parameters(), reset, base, particle_count=5, dataset_size=768, l2_reg=0.01)
+        x, y = torch.randn(32, 8, device=dev), torch.randn(32, device=dev)
+        fwd, bwd = gm.mse_closures(model, x, y)
+        opt.step(fwd, bwd)
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+        return opt, float(opt._scratch.info[0])
+
+    calls = []
+    orig = dist.all_reduce
+
+    def spy(*a, **k):
+        calls.append("all_reduce")
+        return orig(*a, **k)
+    dist.all_reduce = spy
+    opt, h_ddp = one_step()
+    dist.all_reduce = orig
+    res = {"h_ddp": h_ddp, "peers": opt._scratch.peers, "abi_collectives": len(calls)}
+    dist.barrier()
+    dist.destroy_process_group()
+    _, res["h_alone"] = one_step()              # the same seeds without torch.distributed
+    torch.save(res, f"{out_path}.{rank}")
+
+
 def run(rank: int, world: int, port: int, n: int, D: int, out_path: str, backend: str = "gloo", peer: bool = False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if backend == "nccl":

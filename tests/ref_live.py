@@ -55,8 +55,32 @@ def cifar_config(algo):
     return cfg
 
 
+def civil_config(algo):
+    """experiments/civilcomments/civil.yaml: BBB / Rank-1 head on DistilBERT with all layers trained, full-model iVON."""
+    return {"members": 1, "train_all_layers": True, "prior_std": 1.0,
+            "base_optimizer": {"lr": 1e-5, "weight_decay": 0.0},
+            "bbb": {"mc_samples": 2, "kl_rescaling": 1.0, "dataset_size": 269038},
+            "rank1": {"mc_samples": 2, "kl_rescaling": 1.0, "dataset_size": 269038, "components": 5, "l2_scale": 0.01},
+            "ivon": {"lr": 1e-5, "prior_prec": 10, "damping": 1e-3, "augmentation": 1, "mc_samples": 2, "dataset_size": 269038}}
+
+
+def patch_pretrained():
+    """No network on the box: DistilBertModel.from_pretrained (src/architectures/bert.py:13) builds the same
+    architecture (distilbert-base: 6 layers, 768 wide, 66.36 M parameters) with seeded random weights instead."""
+    import transformers
+    transformers.DistilBertModel.from_pretrained = classmethod(
+        lambda cls, *a, **k: cls(transformers.DistilBertConfig()))
+
+
 def batches(task, dev):
     g = torch.Generator().manual_seed(5)
+    if task == "civilcomments":
+        out = []
+        for _ in range(STEPS):
+            ids = torch.randint(0, 30522, (4, 64), generator=g)
+            x = torch.stack([ids, torch.ones_like(ids)], dim=-1)       # [B, T, 2]: token ids, attention mask
+            out.append((x.to(dev), torch.randint(0, 2, (4,), generator=g).to(dev)))
+        return out
     if task == "uci":
         w = torch.randn(8, generator=g)
         xs = [torch.randn(32, 8, generator=g) for _ in range(STEPS)]
@@ -178,9 +202,12 @@ def run(task, algo, dev, forced=None):
     torch.manual_seed(1234)
     if dev.type == "cuda":
         torch.cuda.manual_seed_all(1234)
-    ens = models.get_model(algo, uci_config(algo) if task == "uci" else cifar_config(algo), dev)
+    cfg = {"uci": uci_config, "cifar": cifar_config, "civilcomments": civil_config}[task](algo)
+    ens = models.get_model(algo, cfg, dev)
     model, opt = ens.models_and_optimizers[0]
-    losses, snaps = [], []
+    if task == "civilcomments":
+        model.eval()     # dropout off: the optimizer path is under test, not torch's dropout stream
+    losses, snaps = [], [snapshot(algo, model, opt)]   # snaps[0] = state before the first step
     for s, (x, y) in enumerate(batches(task, dev)):
         if forced is not None and s >= 1:
             force_state(algo, model, opt, forced[s - 1])
@@ -215,6 +242,8 @@ def main():
     import src.algos.util as ref_util
     import src.algos.ivorn as ref_ivorn
     import src.algos.bbb_layers as ref_layers
+    if task == "civilcomments":
+        patch_pretrained()
     rec = Recorder(99)
     for mod in (ref_util, ref_ivorn, ref_layers):
         mod.normal_like = rec.normal_like
@@ -224,7 +253,7 @@ def main():
     # ResNet-20 / SVGD case: the reference against itself with K scaled by 1 + 1e-6 moves 1.6e-7 after step 0 and
     # 2e-4 after step 1; on a GPU the model's own atomics are enough), so on the CIFAR models every step after the
     # first starts from the reference's recorded state (teacher forcing): each step is then a one-update comparison.
-    note, forced = "", (ref_snaps if task == "cifar" else None)
+    note, forced = "", (ref_snaps[1:] if task != "uci" else None)
     if task == "cifar" and algo == "svgd":
         # SURVEY.md §8c caveat 1: at D = 273,610 the reference's fp32 `cdist` reduction is off by ~1e-4 and a deep
         # network amplifies that over the 20 momentum steps of one SVGD step (the reference in fp32 and the SAME
@@ -242,7 +271,7 @@ def main():
         drift = max(float(np.abs(a["particles"] - b["particles"]).max()) for a, b in zip(ref_snaps, ref_snaps64))
         note = f"; fp32 reference drifts {drift:.2e} from the fp64-rbf reference over {STEPS} free-running steps"
         ref_losses, ref_snaps = ref_losses64, ref_snaps64
-        forced = ref_snaps
+        forced = ref_snaps[1:]
     # ---- the same factories after install(): this package's classes on the C-ABI library ----
     import beyond_deep_ensembles_b200 as bde
     from beyond_deep_ensembles_b200 import _lib, noise
@@ -260,12 +289,25 @@ def main():
     assert next(rep.it, None) is None, "the installed path consumed fewer noise draws than the reference"
     assert our_cls.__module__.startswith("beyond_deep_ensembles_b200"), our_cls
     assert dev.type == "cpu" or _lib.launch_count > launches0, "no C-ABI launch happened: the CUDA path did not run"
-    # ---- compare ----
+    # ---- compare: snaps[s + 1] is the state after step s ----
     for s in range(STEPS):
         np.testing.assert_allclose(our_losses[s], ref_losses[s], rtol=2e-5, err_msg=f"loss of step {s}")
-        for key, ref in ref_snaps[s].items():
-            rt, at = (RTOL, ATOL) if s == 0 and algo != "svgd" else (RTOL_C, ATOL_C)
-            np.testing.assert_allclose(our_snaps[s][key], ref, rtol=rt, atol=at, err_msg=f"{key} after step {s}")
+        for key, ref in ref_snaps[s + 1].items():
+            ours = our_snaps[s + 1][key]
+            rt, at = (RTOL, ATOL) if (s == 0 or forced is not None) and algo != "svgd" else (RTOL_C, ATOL_C)
+            np.testing.assert_allclose(ours, ref, rtol=rt, atol=at, err_msg=f"{key} after step {s}")
+            # the UPDATE itself (a small correction of the state when the learning rate is small): both runs started
+            # this step from the same state (initial, or teacher-forced), so the two differences are comparable
+            src = ref_snaps[s] if (s == 0 or forced is None) else forced[s - 1]
+            if (forced is not None or s == 0) and key in src:   # base-optimizer state only exists after a step
+                before = src[key]
+                d_ref, d_our = ref - before, ours - before
+                # 0.2 % of the update + 2e-5 of the largest update + one fp32 ulp of the value being updated
+                tol = 2e-3 * np.abs(d_ref) + 2e-5 * float(np.abs(d_ref).max()) + 1.2e-7 * np.abs(before)
+                bad = np.abs(d_our - d_ref) > tol
+                assert not bad.any(), (f"update of {key} in step {s}: {int(bad.sum())} of {bad.size} elements differ, worst "
+                                       f"{float(np.abs(d_our - d_ref)[bad].max()):.3e} against an update of "
+                                       f"{float(np.abs(d_ref)[bad].max()):.3e}")
     print(f"REF_LIVE_OK {task} {algo}: {our_cls.__name__} == {ref_cls.__module__}.{ref_cls.__name__} over {STEPS} steps "
           f"({_lib.launch_count - launches0} C-ABI launches){note}")
 

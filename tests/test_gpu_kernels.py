@@ -1134,3 +1134,140 @@ def test_pairgram_is_the_default_at_large_D(ops):
     np.testing.assert_allclose(sc.dist.cpu().numpy(), ref.cpu().numpy(), rtol=2e-6)
     bw = O.svgd_bandwidth(ref.cpu(), 0.01, 1.0, 50000.0)
     assert tuple(sc.sel.cpu().tolist()) == bw["sel"]
+
+
+# ---------------------------------------------------------------- BASELINE sizes of the elementwise family
+def _sample_cols(D, count=4096, seed=1):
+    cols = torch.randint(0, D, (count,), generator=torch.Generator().manual_seed(seed))
+    return torch.unique(torch.cat([cols, torch.arange(64), torch.arange(D - 64, D)]))
+
+
+def test_swag_full_size_properties(ops):
+    """C3 (iWildCam ResNet-50 + fc182: D = 23,880,950, K = 10): K + 2 updates (the ring wraps) are bit-exact against the
+    fp32 oracle on a column sample (4096 random columns, the first and the last 64), a draw matches the oracle on the
+    same columns, the single and the batched sampler agree bit for bit on the WHOLE vector, and an update with
+    theta = mean leaves mean unchanged and writes an all-zero deviation row (size-independent properties)."""
+    D, K = 23_880_950, 10
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mean = torch.randn(D, device="cuda", generator=g) * 0.3
+    sq = mean * mean + 0.01 * torch.rand(D, device="cuda", generator=g)
+    ring = torch.zeros(K, D, device="cuda")
+    cols = _sample_cols(D)
+    cd = cols.cuda()
+    m_ref, s_ref = mean[cd].cpu(), sq[cd].cpu()
+    ring_ref = torch.zeros(K, cols.numel())
+    updates = 0
+    for _ in range(K + 2):
+        theta = mean + 0.05 * torch.randn(D, device="cuda", generator=g)
+        updates += 1
+        th_c = theta[cd].cpu()
+        ops.swag_update(theta, mean, sq, ring[(updates - 1) % K], updates)
+        m_ref, s_ref, col = O.swag_update(th_c, m_ref, s_ref, updates)
+        ring_ref[(updates - 1) % K] = col
+    assert torch.equal(mean[cd].cpu(), m_ref) and torch.equal(sq[cd].cpu(), s_ref) and torch.equal(ring[:, cd].cpu(), ring_ref)
+    # one draw with injected noise on the sampled columns
+    eps_k = torch.randn(K, generator=torch.Generator().manual_seed(5))
+    eps_d = torch.randn(D, device="cuda", generator=g)
+    out = torch.empty(D, device="cuda")
+    ops.swag_sample(mean, sq, ring, updates % K, out, eps_k=eps_k.cuda(), eps_d=eps_d)
+    ref = O.swag_sample(m_ref, s_ref, O.swag_ring_to_reference(ring_ref, updates), eps_k, eps_d[cd].cpu(), dtype=torch.float64)
+    np.testing.assert_allclose(out[cd].cpu().numpy(), ref.numpy(), rtol=RTOL, atol=ATOL)
+    # Philox draws: batched == single, whole vector, bit for bit
+    outs = torch.empty(3, D, device="cuda")
+    ops.swag_sample_batch(mean, sq, ring, updates % K, outs, seed=11, stream_id=40)
+    for s_ in range(3):
+        ops.swag_sample(mean, sq, ring, updates % K, out, seed=11, stream_id=40 + s_)
+        assert torch.equal(outs[s_], out)
+    # idempotence-like property: theta == mean  ->  mean unchanged, deviation row exactly zero
+    before = mean.clone()
+    updates += 1
+    ops.swag_update(before.clone(), mean, sq, ring[(updates - 1) % K], updates)
+    torch.testing.assert_close(mean, before, rtol=3e-7, atol=0)     # (u m + m) / (u + 1) rounds at most twice
+    assert float(ring[(updates - 1) % K].abs().max()) <= 3e-7 * float(before.abs().max())
+
+
+def test_ivon_full_size_properties(ops):
+    """C4b (CivilComments DistilBERT + head, full-model iVON: D = 66,955,010): two MC samples + gradient accumulation +
+    the update against the oracle on a column sample; the accumulate kernel is exact; batched == single draws on the
+    whole vector; a deterministic draw returns the mean exactly."""
+    D = 66_955_010
+    N, S = 269038.0, 2
+    g = torch.Generator(device="cuda").manual_seed(4)
+    mean = torch.randn(D, device="cuda", generator=g) * 0.05
+    prec = torch.rand(D, device="cuda", generator=g) * 1e-4 + 10.0 / 269038
+    mom = torch.randn(D, device="cuda", generator=g) * 1e-4
+    dsum, theta, acc = (torch.empty(D, device="cuda") for _ in range(3))
+    cols = _sample_cols(D)
+    cd = cols.cuda()
+    mean_c, prec_c, mom_c = mean[cd].cpu(), prec[cd].cpu(), mom[cd].cpu()
+    dsum_ref, acc_ref = None, None
+    for s in range(S):
+        eps = torch.randn(D, device="cuda", generator=g)
+        ops.ivon_sample(mean, prec, dsum, theta, n_eff=N, first=(s == 0), eps=eps)
+        th_ref, dsum_ref = O.ivon_sample(mean_c, prec_c, dsum_ref, eps[cd].cpu(), N)
+        np.testing.assert_allclose(theta[cd].cpu().numpy(), th_ref.numpy(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(dsum[cd].cpu().numpy(), dsum_ref.numpy(), rtol=RTOL, atol=ATOL)
+        dsum_ref = dsum[cd].cpu().clone()
+        grad = torch.randn(D, device="cuda", generator=g) * 1e-3
+        ops.ivon_accumulate(acc, grad, first=(s == 0))
+        acc_ref = grad[cd].cpu() if acc_ref is None else acc_ref + grad[cd].cpu()
+        assert torch.equal(acc[cd].cpu(), acc_ref)
+    kw = dict(mc_samples=S, step=7, lr=1e-5, prior_prec=10.0, n_eff=N, tempering=1.0, damping=1e-3)
+    ops.ivon_update(acc, dsum, mean, mom, prec, beta1=0.9, beta2=0.999, **kw)
+    m_ref, mo_ref, p_ref = O.ivon_update(acc_ref, dsum_ref, mean_c, mom_c, prec_c, betas=(0.9, 0.999), **kw)
+    for got, ref in ((mean, m_ref), (mom, mo_ref), (prec, p_ref)):
+        np.testing.assert_allclose(got[cd].cpu().numpy(), ref.numpy(), rtol=RTOL, atol=ATOL)
+    assert bool(torch.isfinite(prec).all()) and bool(torch.isfinite(mean).all())
+    # batched == single (Philox), whole vector
+    outs = torch.empty(2, D, device="cuda")
+    ds_b, ds_s = dsum.clone(), dsum.clone()
+    ops.ivon_sample_batch(mean, prec, ds_b, outs, n_eff=N, first=False, seed=5, stream_id=21, stream_stride=3)
+    for s_ in range(2):
+        ops.ivon_sample(mean, prec, ds_s, theta, n_eff=N, first=False, seed=5, stream_id=21 + 3 * s_)
+        assert torch.equal(outs[s_], theta)
+    assert torch.equal(ds_b, ds_s)
+    ops.ivon_sample(mean, prec, dsum, theta, n_eff=N, first=True, deterministic=True)
+    assert torch.equal(theta, mean) and bool(dsum.eq(0).all())
+
+
+@pytest.mark.parametrize("kind,n,D", [("adam", 10, 40_003), ("adamw", 5, 300_000), ("adam", 20, 20_000)])
+def test_fused_adam_does_not_drift_over_200_steps(ops, kind, n, D):
+    """the fused Adam uses MUFU sqrt / rcp (~1 ulp each).  200 consecutive SVGD steps (200 n Adam steps on
+    the shared state) next to `torch.optim.Adam` stepped literally as the reference does (svgd.py:92-103), both fed
+    the SAME new gradients every step: the particles stay within the north-star tolerance relative to the size of
+    the accumulated movement, i.e. the approximate instructions do not accumulate a bias."""
+    g = torch.Generator().manual_seed(n + D)
+    X0 = (0.05 * torch.randn(n, D, generator=g)).cuda()
+    hyper = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01 if kind == "adamw" else 0.0)
+    Xf = X0.clone()
+    sc = ops.SvgdScratch.allocate(n, "cuda")
+    m = torch.zeros(D, device="cuda")
+    v = torch.zeros(D, device="cuda")
+    # literal torch side: ONE parameter re-pointed at particle i, one optimizer whose state is shared
+    Xt = X0.clone()
+    param = torch.nn.Parameter(Xt[0])
+    cls = torch.optim.AdamW if kind == "adamw" else torch.optim.Adam
+    base = cls([param], foreach=False, **hyper)
+    out = torch.empty_like(X0)
+    worst = 0.0
+    for step in range(200):
+        G = (1e-2 * torch.randn(n, D, generator=g)).cuda()
+        # the kernel matrix of the FUSED trajectory drives both sides, so the comparison isolates the optimizer arithmetic
+        ops.svgd_pairdist_bandwidth(Xf, sc, 0.01, 1.0, 50000.0)
+        ops.svgd_apply(Xf, G, out, sc)
+        ops.svgd_apply_adam(Xf, G, sc, m, v, step0=step * n, lr=hyper["lr"], beta1=0.9, beta2=0.999, eps=1e-8,
+                            weight_decay=hyper["weight_decay"], decoupled_weight_decay=(kind == "adamw"))
+        for i in range(n):
+            param.data = Xt[i]
+            param.grad = out[i].clone()
+            base.step()
+        if step % 20 == 19 or step == 0:
+            moved = (Xt - X0).abs().max().item()
+            diff = (Xf - Xt).abs().max().item()
+            worst = max(worst, diff / max(moved, 1e-30))
+            # per-step-relative bound: the gap never exceeds 1e-5 of the distance travelled (+ 1e-6 absolute)
+            assert diff <= 1e-5 * moved + 1e-6, (step, diff, moved)
+    np.testing.assert_allclose(Xf.cpu().numpy(), Xt.cpu().numpy(), rtol=RTOL, atol=ATOL)
+    st = base.state[param]
+    np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"].cpu().numpy(), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(v.cpu().numpy(), st["exp_avg_sq"].cpu().numpy(), rtol=1e-4, atol=1e-9)

@@ -21,7 +21,8 @@ from oracle import install_ref
 ROOT = Path(__file__).resolve().parent.parent
 
 CASES = [("uci", a) for a in ("svgd", "swag", "ivon", "bbb", "rank1")] + \
-        [("cifar", a) for a in ("svgd", "swag", "ivon", "bbb", "rank1")]
+        [("cifar", a) for a in ("svgd", "swag", "ivon", "bbb", "rank1")] + \
+        [("civilcomments", a) for a in ("bbb", "rank1", "ivon")]     # DistilBERT (random init) + BBB / Rank-1 head, full iVON
 
 
 def _staged():

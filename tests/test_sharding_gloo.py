@@ -84,3 +84,36 @@ def test_sharded_step_peer_exchange(tmp_path, world, n, D):
         np.testing.assert_allclose(parts[0]["train_dist"].numpy(), O.svgd_pairdist(full).numpy(), rtol=2e-6)
         for p in parts[1:]:
             assert torch.equal(parts[0]["train_K"], p["train_K"])
+
+
+@pytest.mark.gpu
+def test_abandoned_peer_exchange_is_reported_not_silent(tmp_path):
+    """a straggler rank must not make the others write NaN into their particles.  Rank 1 never launches
+    its exchange; rank 0's kernel gives up after the (2 s) timeout, K / A keep their previous values, the partial
+    sums are poisoned, PeerSet.check() raises, and the failed workspace does not wait again."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import dist_worker
+    out_path = str(tmp_path / "timeout")
+    mp.spawn(dist_worker.run_timeout, args=(2, free_port(), out_path), nprocs=2, join=True)
+    r0 = torch.load(f"{out_path}.0")
+    assert 1.5 < r0["waited_s"] < 30.0
+    assert r0["K_unchanged"] and r0["dist_poisoned"] and r0["raised"], r0
+    assert "abandoned" in r0["message"]
+    assert r0["second_wait_s"] < 1.0
+    assert r0["status"][1] == 1
+
+
+@pytest.mark.parametrize("backend", ["gloo", pytest.param("nccl", marks=pytest.mark.gpu)])
+def test_optimizer_without_process_group_is_rank_local(tmp_path, backend):
+    """with torch.distributed initialised (plain data parallelism) and process_group=None the SVGD
+    optimizer must NOT sum pair distances across ranks: every rank reproduces its own single-process result."""
+    if backend == "nccl" and torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import dist_worker
+    out_path = str(tmp_path / "local")
+    mp.spawn(dist_worker.run_rank_local, args=(2, free_port(), out_path, backend), nprocs=2, join=True)
+    for r in range(2):
+        res = torch.load(f"{out_path}.{r}")
+        assert res["peers"] is None and res["abi_collectives"] == 0
+        np.testing.assert_allclose(res["h_ddp"], res["h_alone"], rtol=0, atol=0)
