@@ -86,6 +86,20 @@ class BayesianOptimizer(Optimizer):
     #: with an active GradScaler, fold unscale_ + the non-finite check into the gradient gather
     fuse_unscale_into_gather = True
 
+    #: zero-copy gradient capture: before each backward pass every `param.grad` is bound to its slice of
+    #: the flat gradient arena (zeroed once per step), so autograd accumulates straight into the arena and the
+    #: per-particle / per-sample gather launch disappears.  "auto" = only while the arena row is small enough that the
+    #: launch and its host-side marshalling cost more than the extra HBM traffic of accumulate-into-zeros (12 D bytes
+    #: per pass against 8 D for a gather: measured A/B in profiles/r02_prebind_ab.json); True / False force it.
+    #: Never used with an active GradScaler (the gather then also unscales).
+    prebind_grads = "auto"
+    prebind_auto_max_elements = 8_000_000
+
+    def _prebind_active(self, grad_scaler, row_elements: int) -> bool:
+        if _scaler_active(grad_scaler) or self.prebind_grads is False:
+            return False
+        return self.prebind_grads is True or row_elements <= self.prebind_auto_max_elements
+
     def _unscale_and_gather(self, grad_scaler, optimizer, row, grads, layout, accumulate=False):
         """Gradients of the pass that just ran -> the flat arena `row` (gather, or gather-add).  Returns what
         `_prepare_and_check_grads` returns.

@@ -182,7 +182,7 @@ int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, in
     int only_if_redo = 0;
     if ((n == 16 || n == 20) && fuse && !accumulate && D <= 0x7fffffffLL &&
         (tuning().pairdist_variant == 3 ||
-         (tuning().pairdist_variant == 0 && D >= 4 * static_cast<int64_t>(kGramTileCols) * sm_count_cached()))) {
+         (tuning().pairdist_variant == 0 && D >= kGramMinColumns))) {
         const int rc = n == 16 ? launch_pairgram<16>(X, D, ld, dist, ws, fuse, bp, st)
                                : launch_pairgram<20>(X, D, ld, dist, ws, fuse, bp, st);
         if (rc != BDE_OK) return rc;

@@ -35,6 +35,10 @@ constexpr double kGramGuard = 32.0;      // max (S_ii + S_jj) / d_ij for which t
 constexpr int kGramTileCols = 256;
 constexpr int kGramConsumers = 256;      // 8 warps
 constexpr int kGramFlushTiles = 64;
+// automatic selection: below this many columns the direct kernels win — the Gram form carries ~20 us of fixed cost (tensor-map
+// encode, the conditional exact-redo launch, the register hand-over): measured crossover 4-8 M columns at n = 16 and 20
+// (profiles/r02_k1_small.jsonl, L2 flushed between launches)
+constexpr int64_t kGramMinColumns = 6000000;
 
 template <int N>
 struct GramGeom {

@@ -71,13 +71,24 @@ class iVONOptimizer(BayesianOptimizer):
         self._drop_presampled(release=True)   # training does not keep the prediction-time sample buffers
 
         acc_loss = None
+        prebind = self._prebind_active(grad_scaler, max(ar["layout"].size for ar in self._arenas))
+        if prebind:
+            # zero-copy capture: every MC sample's backward accumulates straight into acc_grad (ivorn.py:120-127 is
+            # "acc = grad; acc += grad ..."): one memset per group and step, no gather / accumulate launches
+            for ar in self._arenas:
+                ar["rows"]["acc_grad"].zero_()
         for _ in range(self.mc_samples):
             # READY so that GradScaler.unscale_ may be called once per MC sample (ivorn.py:47)
             self._set_grad_scaler_state(grad_scaler, OptState.READY)
 
             self.sample_parameters()
             with torch.enable_grad():
-                self.zero_grad()
+                if prebind:
+                    for group, ar in zip(self.param_groups, self._arenas):
+                        for param, gview in zip(group["params"], ar["views"]["acc_grad"]):
+                            param.grad = gview
+                else:
+                    self.zero_grad()
                 loss = forward_closure()
                 backward_closure(loss)
 
@@ -86,6 +97,15 @@ class iVONOptimizer(BayesianOptimizer):
             else:
                 acc_loss += loss
 
+            if prebind and self._grads_still_bound():
+                for group, ar in zip(self.param_groups, self._arenas):
+                    if ar.get("n_grads", 0) == 0:
+                        for k, param in enumerate(group["params"]):
+                            self.state[param]["acc_grad"] = ar["views"]["acc_grad"][k]
+                    ar["n_grads"] = ar.get("n_grads", 0) + 1
+                continue
+            # gather(-accumulate): prebinding off, AMP, or the closure replaced a .grad (zero_grad inside it) — the
+            # arena holds the sum so far (zeros before the first sample), so the ordinary path continues from it
             if not self._store_gradients(grad_scaler):   # unscale (if AMP) + gather-accumulate, one launch per group
                 return None
         acc_loss /= self.mc_samples
@@ -197,6 +217,10 @@ class iVONOptimizer(BayesianOptimizer):
 
     def get_base_optimizer(self):
         return self
+
+    def _grads_still_bound(self) -> bool:
+        return all(param.grad is gview for group, ar in zip(self.param_groups, self._arenas)
+                   for param, gview in zip(group["params"], ar["views"]["acc_grad"]))
 
     def _store_gradients(self, grad_scaler=None):
         """acc_grad (+)= grad, gathered straight from the scattered .grad tensors (ivorn.py:120-127); under AMP the

@@ -116,17 +116,35 @@ class SVGDOptimizer(BayesianOptimizer):
         n = self.state["__particle_count"]
         base = self.state["__base_optimizer"]
         plist = list(self._params())
-        total_loss = torch.zeros((), device=self._params_device())   # no host-to-device copy
+        losses = []
+        prebind = self._prebind_active(grad_scaler, self._layout.size)
+        scaler_on = grad_scaler is not None and grad_scaler.is_enabled()
+        if prebind:
+            self._G.zero_()   # ONE memset for all particles; autograd then accumulates straight into the arena rows
         for particle_idx in range(n):
-            self._set_grad_scaler_state(grad_scaler, OptState.READY, base)
-            self._use_particle(particle_idx)
-            base.zero_grad()
+            if scaler_on:
+                self._set_grad_scaler_state(grad_scaler, OptState.READY, base)
+            xviews = self._xviews[particle_idx]
+            if prebind:
+                gviews = self._gviews[particle_idx]
+                for param, xview, gview in zip(plist, xviews, gviews):
+                    param.data = xview           # _use_particle (svgd.py:120-127): alias, no copy
+                    param.grad = gview           # what base.zero_grad() + the gather of svgd.py:74,129-133 amount to
+            else:
+                for param, xview in zip(plist, xviews):
+                    param.data = xview
+                base.zero_grad()
 
             loss = forward_closure()
-            total_loss += loss.detach()
+            losses.append(loss.detach())
             backward_closure(loss)
+            if prebind and all(p.grad is g for p, g in zip(plist, gviews)):
+                continue                         # the gradients already sit in row particle_idx of G
+            # gather: the closure replaced a .grad (zero_grad(set_to_none=True) inside it), AMP, or prebinding off
             if not self._store_grads(particle_idx, plist, grad_scaler, base):   # unscale (if AMP) + gather, one launch
                 return None
+        # mean over the particles (svgd.py:105) in ONE reduction instead of n accumulate launches
+        mean_loss = torch.stack(losses).mean() if n > 1 else losses[0].clone()
 
         if self._scratch.peers is not None:
             self._scratch.peers.check()   # an abandoned in-kernel exchange (straggler rank) is an error, never silent
@@ -171,7 +189,7 @@ class SVGDOptimizer(BayesianOptimizer):
                     else:
                         base.step()
 
-        return total_loss / n
+        return mean_loss
 
     @property
     def _out(self):

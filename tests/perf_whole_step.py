@@ -236,12 +236,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--eager-only-cpu", action="store_true", help="debug: run only the eager port, on the CPU")
+    ap.add_argument("--prebind", default="auto", choices=["auto", "on", "off"],
+                    help="zero-copy gradient capture of SVGD / iVON (BayesianOptimizer.prebind_grads): A/B runs")
     args = ap.parse_args()
     global KINDS
     if args.eager_only_cpu:
         KINDS = ("eager",)
     import beyond_deep_ensembles_b200 as bde
     from beyond_deep_ensembles_b200 import util as butil
+    from beyond_deep_ensembles_b200.algo import BayesianOptimizer
+    BayesianOptimizer.prebind_grads = {"auto": "auto", "on": True, "off": False}[args.prebind]
     dev = torch.device("cpu") if args.eager_only_cpu else torch.device("cuda", 0)
     out = {}
     want = set(args.configs.split(","))
@@ -386,7 +390,7 @@ def main():
             torch.cuda.empty_cache()
         out["C5_svgd_update_only_n10"] = res5
 
-    out["_meta"] = {"gpu": torch.cuda.get_device_name(0) if torch.cuda.is_available() else "cpu", "torch": torch.__version__,
+    out["_meta"] = {"prebind_grads": args.prebind, "gpu": torch.cuda.get_device_name(0) if torch.cuda.is_available() else "cpu", "torch": torch.__version__,
                     "timing": "wall clock per step, best of 3 timed loops, synchronised before and after each loop",
                     "eager": "reference op sequence in eager PyTorch on the same GPU (tests-only port)"}
     print(json.dumps(out, indent=1))

@@ -108,6 +108,32 @@ def build_svgd(env, g, base_cls=torch.optim.Adam, **base_kw):
     return model, opt
 
 
+@pytest.mark.parametrize("capture", ["prebound", "gather", "closure-zeroes-grads"])
+def test_svgd_gradient_capture_forms_match_reference(env, golden, capture):
+    """the particles' gradients reach the G arena through pre-bound `.grad` views (autograd accumulates
+    into the zeroed arena row: no gather launch), through the gather launch, or — when the closure clears the
+    gradients itself — through the gather as a fallback; all three reproduce the reference's steps."""
+    g = golden("svgd_steps.npz")
+    n, D = g["init"].shape
+    model, opt = build_svgd(env, g)
+    opt.prebind_grads = capture != "gather"
+    for s in range(g["losses"].size):
+        fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+        if capture == "closure-zeroes-grads":
+            inner = fwd
+
+            def fwd(inner=inner):
+                model.zero_grad(set_to_none=True)
+                return inner()
+        n_gathers = env.calls("mtc")
+        loss = opt.step(fwd, bwd)
+        if env.fake is not None:
+            assert env.calls("mtc") - n_gathers == (0 if capture == "prebound" else n)
+        np.testing.assert_allclose(loss.item(), g["losses"][s], rtol=1e-5)
+        parts = np.stack([flat(opt._params_for_particle(i)) for i in range(n)])
+        np.testing.assert_allclose(parts, g["particles"][s], rtol=3e-5, atol=3e-6)
+
+
 @pytest.mark.parametrize("mode", ["train-step", "fused-base", "base-step"])
 def test_svgd_steps_match_reference(env, golden, mode):
     """Three reference steps with a shared Adam base optimizer (10 Adam steps per SVGD step); fused-base = the
@@ -597,14 +623,28 @@ def ivon_tape(g, model):
     return tape(g["eps"], [per_call] * (g["eps"].size // per_call))
 
 
-def test_ivon_matches_reference(env, golden):
+@pytest.mark.parametrize("capture", ["prebound", "gather", "closure-zeroes-grads"])
+def test_ivon_matches_reference(env, golden, capture):
+    """capture: how the gradients reach the accumulation arena — autograd accumulating straight into
+    pre-bound `.grad` views, the gather-accumulate launch, or pre-binding defeated by a closure that calls
+    zero_grad() itself (falls back to the gather on the same arena)."""
     g = golden("ivon_steps.npz")
     model, opt = build_ivon(env, g)
+    opt.prebind_grads = capture != "gather"
     assert opt.get_base_optimizer() is opt
     with noise.inject(ivon_tape(g, model)):
         for s in range(g["losses"].size):
             fwd, bwd = gm.mse_closures(model, env.t(g["xs"][s]), env.t(g["ys"][s]))
+            if capture == "closure-zeroes-grads":
+                inner = fwd
+
+                def fwd(inner=inner):
+                    model.zero_grad(set_to_none=True)
+                    return inner()
+            n_gathers = env.calls("mtc")
             loss = opt.step(fwd, bwd)
+            if env.fake is not None:   # launches per step: 0 gathers when pre-bound, one per MC sample otherwise
+                assert env.calls("mtc") - n_gathers == (0 if capture == "prebound" else opt.mc_samples)
             np.testing.assert_allclose(loss.item(), g["losses"][s], rtol=1e-5)
             st = [opt.state[p] for p in model.parameters()]
             for name, key in (("mean", "means"), ("momentum", "momenta"), ("precision", "precisions")):
