@@ -1,0 +1,94 @@
+"""the local-reparameterisation forward of the reference's BBBLinear on the tensor cores.
+
+Reference: src/algos/bbb_layers.py:61-88 (sampling == "activations", CUDA branch): two stacked matrix products
+(`baddbmm` over [x, clamp(x^2)] and [W_mu^T, clamp(softplus(W_rho)^2)^T]) followed by sqrt and the noise epilogue —
+about twelve eager launches.  `bbb_linear_forward` runs all of it as ONE tcgen05 kernel (`bde_bbb_linear_fwd`,
+csrc/bbb_linear.cu); `install()` rebinds `BBBLinear.forward` of the reference to `patched_forward` below, which keeps
+every other branch of the reference's forward (parameter sampling, CPU tensors, layers without bias, inputs that are not
+[batch, in] fp32) on the reference's own code.
+
+Backward: plain library GEMMs on the saved activations (torch.matmul), the formulas of autograd through the same graph.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import noise, ops
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Zero-filled split-K workspace per device, grown on demand (the kernel leaves its tickets at zero)."""
+    ws = _WORKSPACES.get(device)
+    if ws is None or ws.numel() * 8 < nbytes:
+        ws = _WORKSPACES[device] = ops.zeros_bytes(nbytes, device)
+    return ws
+
+
+class _BBBLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_mu, w_rho, b_mu, b_rho, mc_sample, eps):
+        out, act_std, eps_used = ops.bbb_linear_fwd(x, w_mu, w_rho, b_mu, b_rho, eps=eps, seed=noise.seed(),
+                                                    stream_id=0 if eps is not None else noise.next_stream_id(),
+                                                    mc_sample=mc_sample, workspace=_workspace)
+        ctx.save_for_backward(x, w_mu, w_rho, b_rho, act_std, eps_used)
+        ctx.mc = float(mc_sample)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w_mu, w_rho, b_rho, act_std, eps = ctx.saved_tensors
+        g = grad_out / ctx.mc                                  # output / mc_sample
+        d_var = g * eps / (2.0 * act_std)                      # sqrt, then * eps
+        sig_w = F.softplus(w_rho)
+        var_w = (sig_w * sig_w).clamp(min=1e-4)
+        xsq = x * x
+        dx = g @ w_mu + (d_var @ var_w) * (2.0 * x) * (xsq >= 1e-4)
+        d_wmu = g.t() @ x
+        d_varw = d_var.t() @ xsq.clamp(min=1e-4)
+        d_wrho = d_varw * (sig_w * sig_w >= 1e-4) * (2.0 * sig_w) * torch.sigmoid(w_rho)
+        sig_b = F.softplus(b_rho)
+        d_bmu = g.sum(0)
+        d_brho = d_var.sum(0) * (sig_b * sig_b >= 1e-4) * (2.0 * sig_b) * torch.sigmoid(b_rho)
+        return dx, d_wmu, d_wrho, d_bmu, d_brho, None, None
+
+
+def fused_forward_applies(layer, input: torch.Tensor) -> bool:
+    return (getattr(layer, "sampling", None) == "activations" and getattr(layer, "use_bias", False) and input.is_cuda
+            and input.dim() == 2 and input.dtype == torch.float32 and layer.in_features % 4 == 0
+            and layer.weight.mean.dtype == torch.float32 and layer.weight.mean.is_contiguous()
+            and layer.weight.rho.is_contiguous())
+
+
+def bbb_linear_forward(layer, input: torch.Tensor) -> torch.Tensor:
+    """bbb_layers.py:61-88 for one BBBLinear (reference class or a look-alike with .weight / .bias GaussianParameters)."""
+    x = input if input.stride(1) == 1 and input.stride(0) % 4 == 0 and input.data_ptr() % 16 == 0 else input.contiguous()
+    shape = (x.shape[0], layer.out_features)
+    if not layer.training and layer.freeze_on_eval:
+        # one noise vector shared by the whole batch (bbb_layers.py:76-77)
+        e = noise.draw("bbb_act", layer.out_features, x.device)
+        if e is None:
+            e = torch.empty(layer.out_features, device=x.device)
+            ops.philox_normal(e, noise.seed(), noise.next_stream_id())
+        eps = e.unsqueeze(0).expand(shape).contiguous()
+    else:
+        eps = noise.draw("bbb_act", shape[0] * shape[1], x.device)       # None: Philox inside the kernel
+        if eps is not None:
+            eps = eps.view(shape)
+    out = _BBBLinear.apply(x, layer.weight.mean, layer.weight.rho, layer.bias.mean, layer.bias.rho,
+                           float(layer.mc_sample), eps)
+    if layer.training or layer.kl_on_eval:   # bbb_layers.py:81-86 (BBBOptimizer collects the KL itself and never reads this)
+        layer.kl = layer.weight.kl_divergence(layer.weight_prior) + layer.bias.kl_divergence(layer.bias_prior)
+    return out
+
+
+def make_patched_forward(reference_forward):
+    def patched_forward(self, input):
+        if fused_forward_applies(self, input):
+            self.kl = 0
+            return bbb_linear_forward(self, input)
+        return reference_forward(self, input)
+    patched_forward._bde_fused = True
+    return patched_forward

@@ -336,6 +336,35 @@ def gauss_sample_bwd(grad_w, rho, grad_rho, *, eps=None, seed: int = 0, stream_i
               int(seed), int(stream_id), int(elem0), _s(rho))
 
 
+def bbb_linear_fwd(x, w_mu, w_rho, b_mu, b_rho, *, eps=None, seed: int = 0, stream_id: int = 0, mc_sample: float = 1.0,
+                   workspace=None):
+    """f4: BBBLinear's local-reparameterisation forward (bbb_layers.py:61-88) as one tcgen05 kernel.
+    x [batch, in] (rows contiguous), w_mu / w_rho [out, in], b_mu / b_rho [out] (or both None), eps [batch, out] or
+    None (Philox).  Returns (out, act_std, eps_used), each [batch, out].  workspace: callable (device, nbytes) ->
+    zero-filled int64 tensor, or None to allocate one."""
+    require_cuda(x, w_mu, w_rho, b_mu, b_rho, eps)
+    _lib.require_f32(x, w_mu, w_rho, b_mu, b_rho, eps)
+    batch, fin, ldx = _rows(x)
+    fout = w_mu.shape[0]
+    if tuple(w_mu.shape) != (fout, fin) or tuple(w_rho.shape) != (fout, fin) or not (w_mu.is_contiguous() and w_rho.is_contiguous()):
+        raise ValueError("w_mu / w_rho must be contiguous [out_features, in_features]")
+    for t in (b_mu, b_rho):
+        if t is not None and _vec(t).numel() != fout:
+            raise ValueError("bias parameters must be [out_features]")
+    if eps is not None and (tuple(eps.shape) != (batch, fout) or not eps.is_contiguous()):
+        raise ValueError("eps must be contiguous [batch, out_features]")
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.get().bde_bbb_linear_workspace_bytes(batch, fin, fout, C.byref(nbytes)), "bde_bbb_linear_workspace_bytes")
+    ws = workspace(x.device, nbytes.value) if workspace is not None else zeros_bytes(nbytes.value, x.device)
+    out = torch.empty((batch, fout), dtype=torch.float32, device=x.device)
+    act_std = torch.empty_like(out)
+    eps_used = torch.empty_like(out)
+    _lib.call("bde_bbb_linear_fwd", x.data_ptr(), ldx, batch, fin, fout, w_mu.data_ptr(), w_rho.data_ptr(), _lib.ptr(b_mu),
+              _lib.ptr(b_rho), _lib.ptr(eps), int(seed), int(stream_id), float(mc_sample), out.data_ptr(), act_std.data_ptr(),
+              eps_used.data_ptr(), ws.data_ptr(), ws.numel() * 8, _s(x))
+    return out, act_std, eps_used
+
+
 def value_workspace(device) -> torch.Tensor:
     nbytes = C.c_size_t(0)
     _lib.check(_lib.get().bde_value_workspace_bytes(C.byref(nbytes)), "bde_value_workspace_bytes")

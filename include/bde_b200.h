@@ -402,6 +402,22 @@ int bde_multi_tensor_unscale_copy(float* flat, const uint64_t* ptrs_host, const 
                                   const int64_t* sizes_host, int count, int mode, const float* inv_scale,
                                   float* found_inf, bde_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * f4: BBBLinear's local-reparameterisation forward, src/algos/bbb_layers.py:61-88 (CUDA branch)
+ *   mean = b_mu + x W_mu^T;  var = clamp(softplus(b_rho)^2, 1e-4) + clamp(x^2, 1e-4) clamp(softplus(W_rho)^2, 1e-4)^T
+ *   out  = (mean + sqrt(var) * eps) / mc_sample
+ * as one tcgen05 kernel (3xTF32 tensor-core products with fp32-level accuracy, TMEM accumulators, tensor-map TMA
+ * loads, deterministic split-K over in_features / 32).  x: [batch, in] row-major with row stride ldx; W_mu, W_rho:
+ * [out, in] contiguous; b_mu / b_rho: [out] or both null; eps: [batch, out] injected noise or null (Philox keyed by
+ * (seed, stream_id), counter = element index / 4); act_std / eps_out (nullable) receive sqrt(var) and the noise used,
+ * for the backward pass.  in_features % 4 == 0 and 16-byte aligned x / W (BDE_ERR_ALIGNMENT otherwise — callers then
+ * keep the reference's own forward).  workspace: bde_bbb_linear_workspace_bytes, zero-filled once by the caller. */
+int bde_bbb_linear_workspace_bytes(int batch, int in_features, int out_features, size_t* bytes);
+int bde_bbb_linear_fwd(const float* x, int64_t ldx, int batch, int in_features, int out_features, const float* w_mu,
+                       const float* w_rho, const float* b_mu, const float* b_rho, const float* eps, uint64_t seed,
+                       uint64_t stream_id, double mc_sample, float* out, float* act_std, float* eps_out, void* workspace,
+                       size_t workspace_bytes, bde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

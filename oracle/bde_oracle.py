@@ -23,6 +23,7 @@ import math
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 # --------------------------------------------------------------------------------------
 # SVGD — reference: src/algos/svgd.py
@@ -314,3 +315,15 @@ def philox_normal(count: int, seed: int, stream_id: int, elem0: int = 0) -> np.n
     z0, z1 = bm(r[:, 0], r[:, 1])
     z2, z3 = bm(r[:, 2], r[:, 3])
     return np.stack([z0, z1, z2, z3], axis=1).reshape(-1)[:count].astype(np.float32)
+
+
+def bbb_linear_fwd(x, w_mu, w_rho, b_mu, b_rho, eps, mc_sample: float = 1.0, dtype=torch.float32):
+    """BBBLinear.forward, sampling == "activations" (bbb_layers.py:61-88; the CPU branch :72-74 states the same
+    arithmetic as the stacked baddbmm of the CUDA branch :66-71).  Returns (out, act_std)."""
+    x, w_mu, w_rho, eps = x.to(dtype), w_mu.to(dtype), w_rho.to(dtype), eps.to(dtype)
+    b_mean = b_mu.to(dtype) if b_mu is not None else None
+    b_var = (F.softplus(b_rho.to(dtype)) ** 2).clamp(min=1e-4) if b_rho is not None else None
+    mean = F.linear(x, w_mu, b_mean)
+    var = F.linear((x ** 2).clamp(min=1e-4), (F.softplus(w_rho) ** 2).clamp(min=1e-4), b_var)
+    std = torch.sqrt(var)
+    return (mean + std * eps) / mc_sample, std

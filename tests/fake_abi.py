@@ -325,6 +325,29 @@ class FakeLib:
             self._emit(grad, D, g, self._scale(gs, gsd), accumulate)
         return 0
 
+    def bde_bbb_linear_workspace_bytes(self, batch, fin, fout, bytes_ref):
+        bytes_ref._obj.value = 1024
+        return 0
+
+    def bde_bbb_linear_fwd(self, x, ldx, batch, fin, fout, w_mu, w_rho, b_mu, b_rho, eps, seed, sid, mc, out, act_std, eps_out,
+                           ws, wsb, stream):
+        self.calls.append("bbb_linear")
+        X = _mat(x, batch, fin, ldx)
+        Wm, Wr = _f32(w_mu, fout * fin).view(fout, fin), _f32(w_rho, fout * fin).view(fout, fin)
+        bm = _f32(b_mu, fout) if b_mu else None
+        br = _f32(b_rho, fout) if b_rho else None
+        if eps:
+            E = _f32(eps, batch * fout).view(batch, fout)
+        else:
+            E = torch.from_numpy(O.philox_normal(batch * fout, seed, sid)).view(batch, fout)
+        y, sd = O.bbb_linear_fwd(X, Wm, Wr, bm, br, E, mc)
+        _f32(out, batch * fout).copy_(y.reshape(-1))
+        if act_std:
+            _f32(act_std, batch * fout).copy_(sd.reshape(-1))
+        if eps_out:
+            _f32(eps_out, batch * fout).copy_(E.reshape(-1))
+        return 0
+
     def bde_philox_normal(self, out, count, seed, sid, elem0, stream):
         _f32(out, count).copy_(torch.from_numpy(O.philox_normal(count, seed, sid, elem0)))
         return 0

@@ -165,6 +165,8 @@ def snapshot(algo, model, opt):
         for key in ("momentum_buffer", "exp_avg", "exp_avg_sq"):
             if bparams and all(key in base.state[p] for p in bparams):
                 out[f"base.{key}"] = cat(base.state[p][key] for p in bparams)
+        if isinstance(base, (torch.optim.Adam, torch.optim.AdamW)):
+            out["_adam_lr"] = np.array(max(g["lr"] for g in base.param_groups))
     return out
 
 
@@ -206,7 +208,11 @@ def run(task, algo, dev, forced=None):
     ens = models.get_model(algo, cfg, dev)
     model, opt = ens.models_and_optimizers[0]
     if task == "civilcomments":
-        model.eval()     # dropout off: the optimizer path is under test, not torch's dropout stream
+        # dropout off (the optimizer path is under test, not torch's dropout stream); every other module stays in
+        # training mode, so the Bayesian layers draw per-activation noise through normal_like (bbb_layers.py:78-79)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.eval()
     losses, snaps = [], [snapshot(algo, model, opt)]   # snaps[0] = state before the first step
     for s, (x, y) in enumerate(batches(task, dev)):
         if forced is not None and s >= 1:
@@ -293,12 +299,29 @@ def main():
     for s in range(STEPS):
         np.testing.assert_allclose(our_losses[s], ref_losses[s], rtol=2e-5, err_msg=f"loss of step {s}")
         for key, ref in ref_snaps[s + 1].items():
+            if key.startswith("_"):
+                continue
             ours = our_snaps[s + 1][key]
             rt, at = (RTOL, ATOL) if (s == 0 or forced is not None) and algo != "svgd" else (RTOL_C, ATOL_C)
+            adam_lr = ref_snaps[s + 1].get("_adam_lr")
+            if key == "params" and adam_lr is not None and algo in ("bbb", "rank1"):
+                # Adam's early updates are lr * g / (|g| + eps): for the handful of weights whose gradient is ~0 the SIGN
+                # of rounding noise decides a full +-lr step, so a forward that differs from the reference's in the last
+                # fp32 bits (the fused tensor-core BBBLinear does) flips a few of them.  Gradients themselves are compared
+                # below through base.exp_avg = (1 - beta1) g, which is linear in g; here a vanishing fraction of the
+                # weights may differ by at most two steps' worth.
+                bad = np.abs(ours - ref) > rt * np.abs(ref) + at
+                assert bad.mean() <= 2e-5 and float(np.abs(ours - ref).max()) <= 2.5 * float(adam_lr), \
+                    (f"params after step {s}: {int(bad.sum())} of {bad.size} differ, worst {float(np.abs(ours - ref).max()):.3e}")
+                continue
+            if key.startswith("base.exp_avg"):
+                at = max(at * 1e-2, 1e-5 * float(np.abs(ref).max()))     # moments are O(gradient), far below 1e-6
             np.testing.assert_allclose(ours, ref, rtol=rt, atol=at, err_msg=f"{key} after step {s}")
             # the UPDATE itself (a small correction of the state when the learning rate is small): both runs started
             # this step from the same state (initial, or teacher-forced), so the two differences are comparable
             src = ref_snaps[s] if (s == 0 or forced is None) else forced[s - 1]
+            if key == "params" and adam_lr is not None and algo in ("bbb", "rank1"):
+                continue
             if (forced is not None or s == 0) and key in src:   # base-optimizer state only exists after a step
                 before = src[key]
                 d_ref, d_our = ref - before, ours - before
