@@ -250,11 +250,30 @@ def other_paths(ops, peak_gbs, dev):
     res = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def rec(name, ms, nbytes, cfg):
+    copy_cache = {}
+
+    def same_size_copy(nbytes):
+        """GB/s of a plain device copy that moves the SAME number of bytes (half read, half written): a 0.1 ms kernel
+        cannot reach the rate MEASURED_PEAKS.json quotes for a 4 GB copy (launch ramp and tail are ~8 % of it)."""
+        key = int(nbytes) >> 20
+        if key not in copy_cache:
+            a = torch.empty(max(int(nbytes) // 8, 1), dtype=torch.float32, device=dev)
+            b = torch.empty_like(a)
+            ms = time_kernel(lambda: b.copy_(a), 20, 3, flush if nbytes < (200 << 20) else None)
+            copy_cache[key] = 8.0 * a.numel() / (ms * 1e-3) / 1e9
+            del a, b
+        return copy_cache[key]
+
+    def rec(name, ms, nbytes, cfg, size_ref=False):
         gbs = nbytes / (ms * 1e-3) / 1e9
         res[name] = {"ms": ms, "GBps": gbs, "frac_of_measured_peak": gbs / peak_gbs, "algorithmic_bytes": nbytes,
                      "config": cfg}
-        log(f"[bench] {name}: {ms:.4f} ms  {gbs:.0f} GB/s  ({gbs / peak_gbs:.2%} of measured copy peak)")
+        extra = ""
+        if size_ref:
+            ref = same_size_copy(nbytes)
+            res[name].update(same_size_copy_GBps=ref, frac_of_same_size_copy=gbs / ref)
+            extra = f", {gbs / ref:.2%} of a torch copy of the same {nbytes / 1e6:.0f} MB"
+        log(f"[bench] {name}: {ms:.4f} ms  {gbs:.0f} GB/s  ({gbs / peak_gbs:.2%} of measured copy peak{extra})")
 
     g = torch.Generator(device=dev).manual_seed(1)
     # C3 SWAG, ResNet-50 + fc182, K = 10
@@ -271,9 +290,9 @@ def other_paths(ops, peak_gbs, dev):
         u[0] += 1
         ops.swag_update(theta, mean, sq, ring[(u[0] - 1) % K], u[0])
 
-    rec("swag_update", time_kernel(swag_upd, 20, 3), 24 * Dp, f"ResNet-50 D={D}, K={K}")
+    rec("swag_update", time_kernel(swag_upd, 20, 3), 24 * Dp, f"ResNet-50 D={D}, K={K}", size_ref=True)
     rec("swag_sample", time_kernel(lambda: ops.swag_sample(mean, sq, ring, 3, out, seed=1, stream_id=2), 20, 3),
-        4 * (K + 3) * Dp, f"ResNet-50 D={D}, K={K}, Philox noise")
+        4 * (K + 3) * Dp, f"ResNet-50 D={D}, K={K}, Philox noise", size_ref=True)
     # f3: 16 draws from the same posterior in one pass (DeepEnsemble.predict) vs 16 single launches
     S = 16
     outs = torch.empty(S, Dp, device=dev)
@@ -295,8 +314,8 @@ def other_paths(ops, peak_gbs, dev):
     grad = torch.randn(Dp, device=dev, generator=g) * 1e-3
     kw = dict(n_eff=269038.0)
     rec("ivon_sample", time_kernel(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=1, stream_id=3, **kw), 20, 3),
-        20 * Dp, f"DistilBERT D={D}, Philox noise")
-    rec("ivon_accumulate", time_kernel(lambda: ops.ivon_accumulate(acc, grad, first=False), 20, 3), 12 * Dp, f"D={D}")
+        20 * Dp, f"DistilBERT D={D}, Philox noise", size_ref=True)
+    rec("ivon_accumulate", time_kernel(lambda: ops.ivon_accumulate(acc, grad, first=False), 20, 3), 12 * Dp, f"D={D}", size_ref=True)
     # the two timing loops above accumulated 23 samples / gradients into dsum and acc: put a
     # mid-training state back so that the update runs on realistic magnitudes (finite everywhere)
     dsum.normal_(0.0, 0.3, generator=g)
@@ -308,7 +327,7 @@ def other_paths(ops, peak_gbs, dev):
         ops.ivon_update(acc, dsum, mean, mom, prec, mc_samples=2, step=100 + step[0], lr=1e-5, beta1=0.9, beta2=0.999,
                         prior_prec=10.0, n_eff=269038.0, tempering=1.0, damping=1e-3)
 
-    rec("ivon_update", time_kernel(ivon_upd, 20, 3), 32 * Dp, f"DistilBERT D={D}")
+    rec("ivon_update", time_kernel(ivon_upd, 20, 3), 32 * Dp, f"DistilBERT D={D}", size_ref=True)
     del mean, prec, mom, dsum, theta, acc, grad
     # C4a BBB last layer: P = 592,130 Gaussian weights; deterministic DistilBERT body 66.36 M
     P = 592_130
@@ -325,6 +344,33 @@ def other_paths(ops, peak_gbs, dev):
     rec("kl_gauss_value_and_grad",
         time_kernel(lambda: ops.kl_gauss(mu, rho, 0.0, 1.0, value=val, grad_mu=gmu, grad_rho=grho, accumulate=True, ws=ws), 20, 3, flush),
         24 * Pp, f"BBB head P={P} (launch-bound)")
+    # f4: BBBLinear local-reparameterisation forward of the Civil head (768 x 768, batch 16) as one tcgen05 kernel, next to
+    # the reference layer's eager CUDA branch (bbb_layers.py:66-79: stacks, pow, clamps, softplus, baddbmm, sqrt, noise)
+    try:
+        from beyond_deep_ensembles_b200 import bbb_layers
+        xb = torch.randn(16, 768, device=dev, generator=g)
+        wmu = 0.1 * torch.randn(768, 768, device=dev, generator=g)
+        wrho = torch.full((768, 768), -3.0, device=dev)
+        bmu, brho = torch.zeros(768, device=dev), torch.full((768,), -3.0, device=dev)
+
+        def ref_layer():
+            sw, sb = torch.nn.functional.softplus(wrho), torch.nn.functional.softplus(brho)
+            bin_ = torch.stack((xb, (xb ** 2).clamp(min=1e-4)))
+            bmat = torch.stack((wmu.transpose(0, 1), (sw.transpose(0, 1) ** 2).clamp(min=1e-4)))
+            badd = torch.stack((bmu.expand((16, 768)), (sb ** 2).clamp(min=1e-4).expand((16, 768))))
+            bo = torch.baddbmm(badd, bin_, bmat)
+            return bo[0] + torch.sqrt(bo[1]) * torch.empty_like(bo[0]).normal_(0, 1)
+
+        ms_f = time_kernel(lambda: ops.bbb_linear_fwd(xb, wmu, wrho, bmu, brho, seed=1, stream_id=2, workspace=bbb_layers._workspace), 30, 5, flush)
+        ms_r = time_kernel(ref_layer, 30, 5, flush)
+        res["bbb_linear_fwd_civil_head"] = {
+            "fused_tcgen05_ms": ms_f, "reference_eager_cuda_ms": ms_r, "speedup": ms_r / ms_f,
+            "config": "BBBLinear(768, 768), batch 16, fp32: one tcgen05 kernel (exact 3-way tf32 split, TMEM accumulators, "
+                      "tensor-map TMA) vs the reference layer's own eager CUDA branch incl. torch.baddbmm; L2 flushed"}
+        log(f"[bench] bbb_linear_fwd (Civil head): fused {1e3 * ms_f:.1f} us vs reference eager {1e3 * ms_r:.1f} us ({ms_r / ms_f:.2f}x)")
+        del xb, wmu, wrho
+    except Exception as e:  # noqa: BLE001
+        res["bbb_linear_fwd_civil_head"] = {"error": str(e)}
     Dd = 66_362_880
     body = torch.randn(Dd, device=dev, generator=g) * 0.02
     gbody = torch.zeros(Dd, device=dev)
@@ -734,9 +780,10 @@ def main():
                          "peak_source": peak_src, "frac_of_nominal_8TBps": k2_gbs / 8000.0,
                          "algorithmic_bytes_per_launch": k2_bytes, "ms_per_launch": k2_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                         # at n=10, D=1e8 (profiles/r01_ncu_summary.md): 8.001 GB + 3.968 GB per launch
-                         "traffic": 11.969e9 * (D / 1e8) if n == 10 else None,
-                         "traffic_source": "profiles/r01_ncu_summary.md (prof_n10_all.ncu-rep, session 29)"},
+                         # at n=10, D=1e8 (profiles/r02_ncu_summary.md, tensor-map kernel): 8.000 GB + 3.970 GB per launch.
+                         # A citation of that capture, not a live counter: ncu cannot run inside the timed region.
+                         "traffic": 11.970e9 * (D / 1e8) if n == 10 else None,
+                         "traffic_source": "profiles/r02_ncu_summary.md (r02_prof_n10.ncu-rep, tools/sessions/r02_s11.sh)"},
             "kernels": {
                 "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
                                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,

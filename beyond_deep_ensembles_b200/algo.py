@@ -88,17 +88,21 @@ class BayesianOptimizer(Optimizer):
 
     #: zero-copy gradient capture: before each backward pass every `param.grad` is bound to its slice of
     #: the flat gradient arena (zeroed once per step), so autograd accumulates straight into the arena and the
-    #: per-particle / per-sample gather launch disappears.  "auto" = only while the arena row is small enough that the
-    #: launch and its host-side marshalling cost more than the extra HBM traffic of accumulate-into-zeros (12 D bytes
-    #: per pass against 8 D for a gather: measured A/B in profiles/r02_prebind_ab.json); True / False force it.
-    #: Never used with an active GradScaler (the gather then also unscales).
+    #: per-particle / per-sample gather launch disappears.  "auto" = only for FEW, SMALL tensors: with a bound .grad
+    #: autograd's AccumulateGrad launches one in-place add per parameter (96 per backward pass for ResNet-20, where the
+    #: gather is ONE multi-tensor launch) and moves 12 D bytes per pass against 8 D for the gather.  Measured A/B with
+    #: real closures (profiles/r02_prebind_ab.json): UCI MLP (4 tensors) overhead 1.20 -> 0.34 ms per step, ResNet-20
+    #: x 20 particles 3.8 -> 4.4-6.4 ms, DistilBERT iVON +0.74 ms.  True / False force it.  Never used with an active
+    #: GradScaler (the gather then also unscales).
     prebind_grads = "auto"
     prebind_auto_max_elements = 8_000_000
+    prebind_auto_max_tensors = 16
 
-    def _prebind_active(self, grad_scaler, row_elements: int) -> bool:
+    def _prebind_active(self, grad_scaler, row_elements: int, tensors: int = 0) -> bool:
         if _scaler_active(grad_scaler) or self.prebind_grads is False:
             return False
-        return self.prebind_grads is True or row_elements <= self.prebind_auto_max_elements
+        return self.prebind_grads is True or (row_elements <= self.prebind_auto_max_elements
+                                              and tensors <= self.prebind_auto_max_tensors)
 
     def _unscale_and_gather(self, grad_scaler, optimizer, row, grads, layout, accumulate=False):
         """Gradients of the pass that just ran -> the flat arena `row` (gather, or gather-add).  Returns what

@@ -266,19 +266,26 @@ bbb_linear_fwd_kernel(const __grid_constant__ CUtensorMap map_wmu, const __grid_
         double sm[BC], sv[BC];
 #pragma unroll
         for (int j = 0; j < BC; ++j) sm[j] = sv[j] = 0.0;
-        for (int s = 0; s < p.ksplits; ++s) {
-            const float* ps = base + static_cast<size_t>(s) * 2 * NB * kBlM + tid;
-            float vm[BC], vv[BC];
+        // four k splits per round: 4 x 2 x 16 independent L2 loads in flight per thread, summed in split order
+        for (int s0 = 0; s0 < p.ksplits; s0 += 4) {
+            float vm[4][BC], vv[4][BC];
 #pragma unroll
-            for (int j = 0; j < BC; ++j) {
-                vm[j] = __ldcg(ps + static_cast<size_t>(bc + j) * kBlM);
-                vv[j] = __ldcg(ps + (static_cast<size_t>(NB) + bc + j) * kBlM);
+            for (int u = 0; u < 4; ++u) {
+                const bool on = s0 + u < p.ksplits;
+                const float* ps = base + static_cast<size_t>(on ? s0 + u : s0) * 2 * NB * kBlM + tid;
+#pragma unroll
+                for (int j = 0; j < BC; ++j) {
+                    vm[u][j] = on ? __ldcg(ps + static_cast<size_t>(bc + j) * kBlM) : 0.f;
+                    vv[u][j] = on ? __ldcg(ps + (static_cast<size_t>(NB) + bc + j) * kBlM) : 0.f;
+                }
             }
 #pragma unroll
-            for (int j = 0; j < BC; ++j) {
-                sm[j] += static_cast<double>(vm[j]);
-                sv[j] += static_cast<double>(vv[j]);
-            }
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < BC; ++j) {
+                    sm[j] += static_cast<double>(vm[u][j]);
+                    sv[j] += static_cast<double>(vv[u][j]);
+                }
         }
 #pragma unroll
         for (int j = 0; j < BC; ++j) {

@@ -71,7 +71,8 @@ class iVONOptimizer(BayesianOptimizer):
         self._drop_presampled(release=True)   # training does not keep the prediction-time sample buffers
 
         acc_loss = None
-        prebind = self._prebind_active(grad_scaler, max(ar["layout"].size for ar in self._arenas))
+        prebind = self._prebind_active(grad_scaler, max(ar["layout"].size for ar in self._arenas),
+                                       sum(len(g["params"]) for g in self.param_groups))
         if prebind:
             # zero-copy capture: every MC sample's backward accumulates straight into acc_grad (ivorn.py:120-127 is
             # "acc = grad; acc += grad ..."): one memset per group and step, no gather / accumulate launches

@@ -117,7 +117,7 @@ class SVGDOptimizer(BayesianOptimizer):
         base = self.state["__base_optimizer"]
         plist = list(self._params())
         losses = []
-        prebind = self._prebind_active(grad_scaler, self._layout.size)
+        prebind = self._prebind_active(grad_scaler, self._layout.size, len(plist))
         scaler_on = grad_scaler is not None and grad_scaler.is_enabled()
         if prebind:
             self._G.zero_()   # ONE memset for all particles; autograd then accumulates straight into the arena rows
