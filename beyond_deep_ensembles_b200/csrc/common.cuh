@@ -79,6 +79,17 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// explicitly rounded packed add / mul: ptxas may contract the un-suffixed forms into an FFMA2, these it may not
+__device__ __forceinline__ f32x2 mul2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rn(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     f32x2 r;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
@@ -431,6 +442,35 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// The same function with the ten round keys precomputed (they depend on the seed only): kernels that draw many streams
+// per thread (the batched samplers) build them once before their element loop instead of once per call.
+struct PhiloxKeys {
+    uint2 rk[10];
+};
+__device__ __forceinline__ PhiloxKeys philox_round_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint2 key = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        k.rk[r] = key;
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys& k) {
+    constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = static_cast<unsigned long long>(M0) * ctr.x;
+        const unsigned long long p1 = static_cast<unsigned long long>(M1) * ctr.z;
+        const unsigned int hi0 = static_cast<unsigned int>(p0 >> 32), lo0 = static_cast<unsigned int>(p0);
+        const unsigned int hi1 = static_cast<unsigned int>(p1 >> 32), lo1 = static_cast<unsigned int>(p1);
+        ctr = make_uint4(hi1 ^ ctr.y ^ k.rk[r].x, lo1, hi0 ^ ctr.w ^ k.rk[r].y, lo0);
+    }
+    return ctr;
+}
+
 __device__ __forceinline__ float u01_open(unsigned int r) {
     // (r>>8) * 2^-24 + 2^-25  in (0, 1]
     return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
@@ -463,6 +503,16 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t stream_
                                  static_cast<unsigned int>(stream_id), static_cast<unsigned int>(stream_id >> 32));
     const uint2 key = make_uint2(static_cast<unsigned int>(seed), static_cast<unsigned int>(seed >> 32));
     const uint4 r = philox4x32_10(ctr, key);
+    float4 z;
+    box_muller(r.x, r.y, z.x, z.y);
+    box_muller(r.z, r.w, z.z, z.w);
+    return z;
+}
+
+__device__ __forceinline__ float4 philox_normal4(const PhiloxKeys& k, uint64_t stream_id, uint64_t quad) {
+    const uint4 ctr = make_uint4(static_cast<unsigned int>(quad), static_cast<unsigned int>(quad >> 32),
+                                 static_cast<unsigned int>(stream_id), static_cast<unsigned int>(stream_id >> 32));
+    const uint4 r = philox4x32_10(ctr, k);
     float4 z;
     box_muller(r.x, r.y, z.x, z.y);
     box_muller(r.z, r.w, z.z, z.w);

@@ -58,6 +58,7 @@ ivon_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
                          float* __restrict__ theta, int64_t ld_out, int64_t D, int S, float n_eff, int first,
                          int deterministic, const float* __restrict__ eps, int64_t ld_eps, uint64_t seed,
                          uint64_t stream_id, uint64_t stream_stride, int64_t quad0) {
+    const PhiloxKeys pk = philox_round_keys(seed);
     BDE_QUAD_LOOP(q, D) {
         const int64_t b = q << 2;
         const float4 m = load_quad<VEC, true>(mean, b, D);
@@ -80,7 +81,7 @@ ivon_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
                 if (inj)
                     e = load_quad<VEC, true>(eps + sidx * ld_eps, b, D);
                 else
-                    e = philox_normal4(seed, stream_id + sidx * stream_stride, static_cast<uint64_t>(quad0 + q));
+                    e = philox_normal4(pk, stream_id + sidx * stream_stride, static_cast<uint64_t>(quad0 + q));
                 dl = BDE_LANES(__fmul_rn(c.x, e.x), __fmul_rn(c.y, e.y), __fmul_rn(c.z, e.z), __fmul_rn(c.w, e.w));
             }
             const float4 th = BDE_LANES(__fadd_rn(m.x, dl.x), __fadd_rn(m.y, dl.y), __fadd_rn(m.z, dl.z), __fadd_rn(m.w, dl.w));

@@ -202,6 +202,103 @@ swag_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
     }
 }
 
+// Fast path of K4 batched: every pointer 16-byte aligned, all SB draws of the pass in use, whole quads only (the launcher
+// sends a ragged tail and partial passes to the general kernel above).  Same arithmetic, bit for bit — the low-rank chain
+// runs as packed FFMA2 (IEEE per lane, same k order), the epilogue as packed add / mul without contraction — but none of
+// the per-draw predicates, guarded loads and 64-bit address recomputation of the general form: measured 0.99 -> see
+// profiles/r02_bench_n1.json (16 draws at ResNet-50 size).
+template <int SB, bool INJ>
+__global__ void __launch_bounds__(kEwThreads, SB >= 16 ? 2 : 3)
+swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
+                              int head, int64_t nquads, int64_t ld, const float* __restrict__ eps_k,
+                              const float* __restrict__ eps_d, int64_t ld_eps, uint64_t seed, uint64_t stream_id, int64_t quad0,
+                              float inv_norm_den, float* __restrict__ theta, int64_t ld_out) {
+    __shared__ __align__(16) float zc[kMaxSwagRank][SB];
+    __shared__ int64_t rowoff[kMaxSwagRank];
+    for (int e = threadIdx.x; e < K * SB; e += blockDim.x) {
+        const int k = e / SB, sidx = e - k * SB;
+        float z;
+        if (eps_k) {
+            z = eps_k[static_cast<int64_t>(sidx) * K + k];
+        } else {
+            const float4 z4 = philox_normal4(seed, (stream_id + sidx) ^ 0x5741ull, static_cast<uint64_t>(k >> 2));
+            z = (k & 3) == 0 ? z4.x : (k & 3) == 1 ? z4.y : (k & 3) == 2 ? z4.z : z4.w;
+        }
+        zc[k][sidx] = __fdiv_rn(z, inv_norm_den);
+    }
+    for (int k = threadIdx.x; k < K; k += blockDim.x) rowoff[k] = static_cast<int64_t>((head + k) % K) * ld;
+    __syncthreads();
+
+    const PhiloxKeys pk = philox_round_keys(seed);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+        const int64_t b = q << 2;
+        const V4 m = ldg_stream_v4(mean + b);
+        const V4 sv = ldg_stream_v4(sq + b);
+        f32x2 lo[SB], hi[SB];
+#pragma unroll
+        for (int sidx = 0; sidx < SB; ++sidx) lo[sidx] = hi[sidx] = 0ull;
+        constexpr int KU = 5;
+        for (int k0 = 0; k0 < K; k0 += KU) {
+            V4 d[KU];
+#pragma unroll
+            for (int u = 0; u < KU; ++u)
+                if (k0 + u < K) d[u] = ldg_stream_v4(dev + rowoff[k0 + u] + b);
+#pragma unroll
+            for (int u = 0; u < KU; ++u) {
+                if (k0 + u < K) {
+#pragma unroll
+                    for (int s4 = 0; s4 < SB; s4 += (SB >= 4 ? 4 : 2)) {
+                        float z[4];
+                        if constexpr (SB >= 4) {
+                            const float4 zz = *reinterpret_cast<const float4*>(&zc[k0 + u][s4]);
+                            z[0] = zz.x, z[1] = zz.y, z[2] = zz.z, z[3] = zz.w;
+                        } else {
+                            const float2 zz = *reinterpret_cast<const float2*>(&zc[k0 + u][s4]);
+                            z[0] = zz.x, z[1] = zz.y, z[2] = z[3] = 0.0f;
+                        }
+#pragma unroll
+                        for (int t = 0; t < (SB >= 4 ? 4 : 2); ++t) {
+                            lo[s4 + t] = fma2s(z[t], d[u].lo, lo[s4 + t]);   // fmaf(d, z, low) per lane, k ascending
+                            hi[s4 + t] = fma2s(z[t], d[u].hi, hi[s4 + t]);
+                        }
+                    }
+                }
+            }
+        }
+        float m0, m1, m2, m3, s0, s1, s2, s3;
+        unpack2(m.lo, m0, m1);
+        unpack2(m.hi, m2, m3);
+        unpack2(sv.lo, s0, s1);
+        unpack2(sv.hi, s2, s3);
+        auto sdev = [&](float mv, float sq2) {   // sqrt(0.5 (relu(sq - mean^2) + 1e-6)), swag.py:112
+            float v = __fsub_rn(sq2, __fmul_rn(mv, mv));
+            v = fmaxf(v, 0.0f);
+            return __fsqrt_rn(__fmul_rn(0.5f, __fadd_rn(v, 1e-6f)));
+        };
+        const float sd0 = sdev(m0, s0), sd1 = sdev(m1, s1), sd2 = sdev(m2, s2), sd3 = sdev(m3, s3);
+        float* out = theta + b;
+        const float* ein = INJ ? eps_d + b : nullptr;
+#pragma unroll
+        for (int sidx = 0; sidx < SB; ++sidx) {
+            float4 z;
+            if constexpr (INJ) {
+                z = ldg_stream_f4(ein);
+                ein += ld_eps;
+            } else {
+                z = philox_normal4(pk, stream_id + sidx, static_cast<uint64_t>(quad0 + q));
+            }
+            // (mean + low) + sqrt(diag) * eps, each operation rounded on its own.  The products stay scalar: ptxas contracts a
+            // packed mul followed by a packed add into FFMA2 even when both carry .rn (seen in SASS), which changes the bits.
+            V4 o;
+            o.lo = add2_rn(add2_rn(m.lo, lo[sidx]), pack2(__fmul_rn(sd0, z.x), __fmul_rn(sd1, z.y)));
+            o.hi = add2_rn(add2_rn(m.hi, hi[sidx]), pack2(__fmul_rn(sd2, z.z), __fmul_rn(sd3, z.w)));
+            stg_stream_v4(out, o);
+            out += ld_out;
+        }
+    }
+}
+
 }  // namespace bde
 
 using namespace bde;
@@ -292,6 +389,31 @@ extern "C" int bde_swag_sample_batch(const float* mean, const float* sq, const f
         const float* ek = eps_k ? eps_k + static_cast<int64_t>(s0) * K : nullptr;
         const float* ed = eps_d ? eps_d + s0 * ld_eps : nullptr;
         float* out = theta + s0 * ld_out;
+        const int64_t nq = D >> 2;
+        if (vec && c == sb && nq > 0 && tuning().swag_batch != 1) {   // whole passes of aligned data: fast kernel for the full quads ...
+            int rf = BDE_OK;
+#define BDE_SWAG_FAST(SB_)                                                                                                     \
+    rf = ed ? launch_ew(swag_sample_batch_fast_kernel<SB_, true>, nq * 4, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, seed, \
+                        stream_id + s0, elem0 >> 2, den, out, ld_out)                                                          \
+            : launch_ew(swag_sample_batch_fast_kernel<SB_, false>, nq * 4, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, seed, \
+                        stream_id + s0, elem0 >> 2, den, out, ld_out)
+            switch (sb) {
+                case 2: BDE_SWAG_FAST(2); break;
+                case 4: BDE_SWAG_FAST(4); break;
+                case 8: BDE_SWAG_FAST(8); break;
+                default: BDE_SWAG_FAST(16); break;
+            }
+#undef BDE_SWAG_FAST
+            if (rf != BDE_OK) return rf;
+            const int64_t d4 = nq << 2;
+            if (d4 < D) {   // ... and the general kernel for the last D % 4 elements
+                const int rt = launch_swag_batch<false>(sb, D - d4, st, mean + d4, sq + d4, dev + d4, K, head, ld, c, ek,
+                                                        ed ? ed + d4 : nullptr, ld_eps, seed, stream_id + s0, (elem0 + d4) >> 2, den,
+                                                        out + d4, ld_out);
+                if (rt != BDE_OK) return rt;
+            }
+            continue;
+        }
         const int rc_ = vec ? launch_swag_batch<true>(sb, D, st, mean, sq, dev, K, head, ld, c, ek, ed, ld_eps, seed,
                                                       stream_id + s0, elem0 >> 2, den, out, ld_out)
                             : launch_swag_batch<false>(sb, D, st, mean, sq, dev, K, head, ld, c, ek, ed, ld_eps, seed,
