@@ -70,6 +70,7 @@ def main():
         }
         if nk is not None:
             forms["train_sgd"] = lambda: ops.svgd_apply_sgd(X, G, sc, buf, buf_initialized=True, next_kernel=nk, **kw)
+            forms["train_adam"] = lambda: ops.svgd_apply_adam(X, G, sc, buf, buf2, step0=10, lr=1e-7, next_kernel=nk)
         times = {f: {"A": [], "B": []} for f in forms}
         for _ in range(args.rounds):
             for f, fn in forms.items():
