@@ -1241,8 +1241,14 @@ int launch_apply_tma(const float* X, const float* G, float* out, const float* K,
     if (rc == BDE_OK) rc = encode_rows_tensor_map(&mapG, G, N, d4, ldg, kTmaBoxCols);
     if (rc != BDE_OK) return rc;
     int nst = apply_stages(N, OPT, TC);
-    if (tuning().ring_kb > 0) {   // shallower ring (A/B knob): fewer tile loads in flight per SM
-        const int want = tuning().ring_kb * 1024 / apply_stage_bytes(N, OPT, TC);
+    // Ring depth in use.  With tensor-map loads the producer is no longer the limit, and for the plain K2 at n <= 12 a
+    // ~128 KB ring streams faster than the whole ~164-200 KB one (interleaved same-build A/B, profiles/r02_ring_ab.jsonl:
+    // n = 10 -5.6 %, n = 5 -1.4 %, n = 8 +-0; n = 16 / 20 and the fused forms are best or mixed at full depth) — fewer
+    // reads in flight leave the DRAM queues room for the write stream.  bde_tune("ring_kb") overrides (A/B runs).
+    int ring_kb = tuning().ring_kb;
+    if (ring_kb == 0 && OPT == kOptNone && !NEXT && N <= 12) ring_kb = 128;
+    if (ring_kb > 0) {
+        const int want = ring_kb * 1024 / apply_stage_bytes(N, OPT, TC);
         if (want < nst) nst = want > TS + 1 ? want : TS + 1;
     }
     int64_t grid = sm_count_cached();
