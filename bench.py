@@ -499,6 +499,7 @@ def strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel, steps):
                 ops.svgd_pairdist(X_, scr)
                 bdist.allreduce_dist(scr)
                 ops.svgd_bandwidth(scr, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
+            ops.svgd_chain_next(X_)
             ops.svgd_apply(X_, G_, O_, scr)
 
         for _ in range(3):
@@ -630,6 +631,9 @@ def main():
             ops.svgd_bandwidth(sc, L2_REG, KERNEL_GRAD_SCALE, DATASET_SIZE)
         if events is not None:
             events[1].record()
+        # K2 is launched as a programmatic dependent of K1 (its ring fills during K1's tail); the event between the two
+        # is a marker on the stream and takes its timestamp when K1 completes
+        ops.svgd_chain_next(X)
         ops.svgd_apply(X, G, out, sc)
         if events is not None:
             events[2].record()

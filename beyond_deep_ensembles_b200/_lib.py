@@ -51,6 +51,7 @@ SIGNATURES = {
     "bde_svgd_pairdist_bandwidth": [_p, _i, _i64, _i64, _d, _d, _d, _d, _p, _p, _p, _p, _p, _p, _sz, _p],
     "bde_svgd_host_pairdist": [_p, _i, _i64, _i64, _i64, _p, _p, _p, _sz],
     "bde_svgd_host_apply": [_p, _p, _i, _i64, _i64, _d, _d, _d, _d, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "bde_svgd_chain_next": [_p],
     "bde_svgd_step": [_p, _p, _p, _i, _i64, _i64, _d, _d, _d, _d, _p, _p, _p, _p, _p, _p, _sz, _p],
     "bde_svgd_step_host": [_p, _p, _p, _i, _i64, _i64, _d, _d, _d, _d, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz,
                            _p, _p],

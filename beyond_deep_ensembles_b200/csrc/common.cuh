@@ -214,6 +214,21 @@ __device__ __forceinline__ V4 lds_v4(const float* p) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (K1 -> K2): K1 calls griddep_launch() once its streaming loop is done, so that a K2
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization becomes resident during K1's tail (grid reduction,
+// cross-rank exchange, K1b) and fills its shared-memory ring; K2 calls griddep_wait() — which returns when the WHOLE
+// preceding grid has completed and its writes are visible — before it reads K / A or writes anything.  Both are no-ops
+// for ordinary launches.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// host: did the caller declare (bde_svgd_chain_next) that the next apply launch on `st` directly follows this library's
+// K1 launch, nothing else enqueued in between?  Consumed by the first apply launch that asks.
+bool take_chain_hint(cudaStream_t st);
+// set by apply_impl / apply_opt_impl from the hint for the launch they are about to make; read (and cleared) by the staged launcher
+bool& pdl_for_this_apply();
+
+// ----------------------------------------------------------------------------
 // reductions
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

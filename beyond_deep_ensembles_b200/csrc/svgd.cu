@@ -55,6 +55,7 @@ svgd_apply_scalar_kernel(const float* __restrict__ X, const float* __restrict__ 
                          int64_t ldg, int64_t ldo) {
     __shared__ float sK[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
     __shared__ float sA[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    griddep_wait();
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         sK[e] = K[e];
         sA[e] = A[e];
@@ -86,6 +87,7 @@ svgd_apply_opt_scalar_kernel(float* X, const float* __restrict__ G, const float*
                              const __grid_constant__ BaseOptParams o) {
     __shared__ float sK[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
     __shared__ float sA[BDE_MAX_PARTICLES * BDE_MAX_PARTICLES];
+    griddep_wait();
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
         sK[e] = K[e];
         sA[e] = A[e];
@@ -201,6 +203,7 @@ int pairdist_impl(const float* X, int n, int64_t D, int64_t ld, double* dist, in
 
 int apply_impl(const float* X, const float* G, float* out, const float* K, const float* A, int n, int64_t D,
                int64_t ldx, int64_t ldg, int64_t ldo, cudaStream_t st) {
+    pdl_for_this_apply() = take_chain_hint(st);   // consumed by whichever apply launch comes first (only the staged kernel uses it)
     if (!X || !G || !out || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ldx < D || ldg < D || ldo < D)
         return BDE_ERR_INVALID_ARG;
     if (D == 0) return BDE_OK;
@@ -230,6 +233,7 @@ int apply_impl(const float* X, const float* G, float* out, const float* K, const
 
 int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int n, int64_t D, int64_t ldx,
                    int64_t ldg, const BaseOptParams& o, cudaStream_t st, const NextDistParams* next, size_t ws_bytes) {
+    pdl_for_this_apply() = take_chain_hint(st);
     if (!X || !G || !K || !A || n < 1 || n > BDE_MAX_PARTICLES || D < 0 || ldx < D || ldg < D) return BDE_ERR_INVALID_ARG;
     if (o.kind != kOptSgd && o.kind != kOptAdam) return BDE_ERR_INVALID_ARG;
     const bool needs_s0 = o.kind == kOptAdam || o.momentum != 0.0f;
@@ -279,9 +283,30 @@ int apply_opt_impl(float* X, const float* G, const float* K, const float* A, int
     }
 }
 
+// --- chain hint (programmatic dependent launch of K2 behind K1) ---
+namespace {
+thread_local cudaStream_t g_chain_stream = nullptr;
+thread_local bool g_chain_armed = false;
+}  // namespace
+bool take_chain_hint(cudaStream_t st) {
+    const bool ok = g_chain_armed && g_chain_stream == st;
+    g_chain_armed = false;
+    return ok;
+}
+bool& pdl_for_this_apply() {
+    thread_local bool v = false;
+    return v;
+}
+
 }  // namespace bde
 
 using namespace bde;
+
+extern "C" int bde_svgd_chain_next(bde_stream_t stream) {
+    g_chain_stream = static_cast<cudaStream_t>(stream);
+    g_chain_armed = true;
+    return BDE_OK;
+}
 
 extern "C" int bde_svgd_workspace_bytes(int n, size_t* bytes) {
     if (!bytes || n < 1 || n > BDE_MAX_PARTICLES) return BDE_ERR_INVALID_ARG;
@@ -330,6 +355,7 @@ extern "C" int bde_svgd_step(const float* X, const float* G, float* out, int n, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = pairdist_impl(X, n, D, ld, dist, 0, workspace, workspace_bytes, 1, bp, st);
     if (rc != BDE_OK) return rc;
+    bde_svgd_chain_next(stream);   // K2 directly behind K1: programmatic dependent launch
     return apply_impl(X, G, out, K, A, n, D, ld, ld, ld, st);
 }
 

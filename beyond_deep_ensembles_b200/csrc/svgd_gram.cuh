@@ -285,6 +285,7 @@ svgd_pairgram_kernel(const __grid_constant__ CUtensorMap tmap, int64_t D, double
         if constexpr (SHIFT) reg_inc<kGramRegsLaunch>();   // waits until the consumers have shrunk back
     }
     __syncthreads();
+    griddep_launch();   // streaming done: dependents may become resident during the tail
 
     // entry e of group grp was accumulated by that group's two warps (one per column half)
     for (int e = tid; e < EN; e += nthreads) {

@@ -406,6 +406,7 @@ svgd_pairdist_kernel(const float* __restrict__ X, int64_t D, int64_t ld, double*
 
     group_dispatch<N, 0>(g, X, D, ld, wacc[g * WPG + warp_in_group]);
     __syncthreads();
+    griddep_launch();   // streaming done: a dependent K2 may become resident during the tail
 
     for (int p = tid; p < P; p += TPB * NG) {
         const int i = pair_row(p, N), j = p - pair_index(i, i + 1, N) + i + 1;
@@ -601,6 +602,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
         pairdist_tma_dispatch<N, 0>(g, X, D, ld, tiles, full_bar, empty_bar, wacc[wid], qi);
     }
     __syncthreads();
+    griddep_launch();   // streaming done: a dependent K2 may become resident during the tail
 
     // pair p of group grp is accumulated by that group's warps only
     for (int p = tid; p < P; p += nthreads) {
@@ -844,6 +846,7 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
     __shared__ __align__(16) float sKT[N][NP];
     __shared__ __align__(16) float sAT[N][NP];
     __shared__ double wacc[NEXT ? 4 : 1][NEXT ? pair_count(N) : 1];
+    griddep_wait();   // K / A come from the preceding K1 launch
     for (int e = threadIdx.x; e < N * NP; e += blockDim.x) {
         const int j = e / NP, i = e - j * NP;
         sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
@@ -1012,11 +1015,6 @@ svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     __shared__ double wacc[NEXT ? CWARPS : 1][NEXT ? pair_count(N) : 1];
 
     const int tid = threadIdx.x;
-    for (int e = tid; e < N * NP; e += blockDim.x) {
-        const int j = e / NP, i = e - j * NP;
-        sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
-        sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
-    }
     if constexpr (NEXT) {
         for (int k = tid; k < CWARPS * pair_count(N); k += blockDim.x) (&wacc[0][0])[k] = 0.0;
     }
@@ -1031,6 +1029,8 @@ svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
         tma_prefetch_map(&mapG);
     }
     __syncthreads();
+    // From here the producer streams X / G tiles at once — neither is written by a K1 that may still be in its tail
+    // (programmatic dependent launch) — while the consumers first wait for that K1 to complete, then fetch K and A.
 
     const int64_t d4 = D & ~static_cast<int64_t>(3);
     const int64_t ntiles = (d4 + TC - 1) / TC;
@@ -1062,7 +1062,15 @@ svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
                 }
             }
         }
+        griddep_wait();   // before the common tail (training-step form) touches the workspace
     } else {
+        griddep_wait();
+        for (int e = tid; e < N * NP; e += CONSUMERS) {   // transposed coefficients: sKT[j][i] = K[i][j]
+            const int j = e / NP, i = e - j * NP;
+            sKT[j][i] = (i < N) ? K[i * N + j] : 0.0f;
+            sAT[j][i] = (i < N) ? A[i * N + j] : 0.0f;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");   // consumers only: the producer lane is in its loop
         const int lane = tid & 31;
         const int set = tid / QT, q = tid - set * QT;   // tile set and quad within the tile
         f32x2 pacc[PN];
@@ -1254,8 +1262,19 @@ int launch_apply_tma(const float* X, const float* G, float* out, const float* K,
     int64_t grid = sm_count_cached();
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) grid = 1;
-    svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC><<<static_cast<unsigned>(grid), TS * (TC / 4) + 32, smem, st>>>(mapX, mapG, X, G, out, K, A, D, ldx, ldg, ldo, o, nd, nst);
-    BDE_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(TS * (TC / 4) + 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_for_this_apply() ? 1 : 0;   // only when the caller vouched that K1 is the preceding launch
+    pdl_for_this_apply() = false;
+    BDE_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, svgd_apply_tma_kernel<N, OPT, NEXT, TS, TC>, mapX, mapG, X, G, out, K, A, D, ldx,
+                                          ldg, ldo, o, nd, nst));
     return BDE_OK;
 }
 

@@ -203,9 +203,17 @@ def svgd_pairdist_bandwidth(X: torch.Tensor, sc: SvgdScratch, l2_reg: float, ker
 
 def svgd_step(X: torch.Tensor, G: torch.Tensor, out: torch.Tensor, sc: SvgdScratch, l2_reg: float,
               kernel_grad_scale: float, dataset_size: float, h_override: float = 0.0) -> torch.Tensor:
-    """Single-GPU posterior update: K1(+K1b) then K2 — two launches."""
+    """Single-GPU posterior update: K1(+K1b) then K2 — two launches, K2 as a programmatic dependent of K1 (it fills
+    its ring during K1's tail)."""
     svgd_pairdist_bandwidth(X, sc, l2_reg, kernel_grad_scale, dataset_size, h_override)
+    svgd_chain_next(X)
     return svgd_apply(X, G, out, sc)
+
+
+def svgd_chain_next(t: torch.Tensor) -> None:
+    """The next svgd_apply* launch on t's stream directly follows the K1 / K1b launch just made, nothing in between
+    (bde_svgd_chain_next): call it only back to back with both."""
+    _lib.get().bde_svgd_chain_next(_s(t))
 
 
 # --------------------------------------------------------------------------------------

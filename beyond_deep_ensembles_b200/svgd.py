@@ -154,12 +154,17 @@ class SVGDOptimizer(BayesianOptimizer):
             if cached is not None and self._cached_versions != self._write_versions(plist):
                 cached = None   # something else wrote a particle since the cache was computed
             self._cached = None
+            # (the base optimizer's state is bound BEFORE K1 is enqueued: binding may launch torch fills, and the apply
+            # kernel below may only be chained to K1 if nothing else sits between the two on the stream)
+            plan = self._plan_for(base, grad_scaler, plist)
+            bound = plan.bind_state() if plan is not None else None
+            if bound is None:
+                _ = self._out   # allocate the [n, size] output arena (first unfused step) before K1 as well
             if cached != "kernel":
                 # svgd.py:83-89 on the arenas: K1 -> (all-reduce of n*n doubles when D-sharded) -> K1b
                 bdist.svgd_kernel_sharded(self._X, self._scratch, *hyper, 0.0, self._group,
                                           have_partial=(cached == "partial"))
-            plan = self._plan_for(base, grad_scaler, plist)
-            bound = plan.bind_state() if plan is not None else None
+                ops.svgd_chain_next(self._X)   # K2 / K2f follows directly: programmatic dependent launch
             if bound is not None:
                 # f1: K2 + the n shared-state base-optimizer steps of svgd.py:92-103 in one pass; X in place.
                 # Training-step form (n <= 10): the pass also leaves the next step's pair distances in the

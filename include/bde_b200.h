@@ -110,6 +110,13 @@ int bde_svgd_pairdist_bandwidth(const float* X, int n, int64_t D, int64_t ld, do
 /*
  * Single-GPU convenience: K1(+K1b) + K2 on one stream (no collective in between).
  */
+/* Declares that the NEXT bde_svgd_apply / bde_svgd_apply_sgd / _adam / bde_svgd_train_step_* launch on `stream` directly
+ * follows a bde_svgd_pairdist_bandwidth / bde_svgd_bandwidth launch of this library on the same stream, with NOTHING
+ * else enqueued in between.  The staged apply kernel is then launched as a programmatic dependent of K1: it becomes
+ * resident and fills its shared-memory ring with X / G tiles while K1 is still in its tail (grid reduction, cross-rank
+ * exchange, K1b), and waits for K1's completion before it reads K / A or writes anything.  The hint is consumed by the
+ * next apply launch of the calling thread whatever kernel that launch selects.  bde_svgd_step does this itself. */
+int bde_svgd_chain_next(bde_stream_t stream);
 int bde_svgd_step(const float* X, const float* G, float* out, int n, int64_t D, int64_t ld,
                   double l2_reg, double kernel_grad_scale, double dataset_size,
                   double h_override, double* dist, float* K, float* A, double* info,

@@ -75,6 +75,9 @@ class FakeLib:
     bde_peer_alloc = bde_peer_open = bde_peer_close = bde_peer_free = _no_peer
     bde_peer_attach = bde_peer_detach = bde_peer_status = bde_peer_wait_stats = _no_peer
 
+    def bde_svgd_chain_next(self, stream):
+        return 0
+
     def bde_svgd_pairdist(self, X, n, D, ld, dist, accumulate, ws, wsb, stream):
         self.calls.append("pairdist")
         d = O.svgd_pairdist(_mat(X, n, D, ld))
