@@ -70,6 +70,7 @@ SIGNATURES = {
     "bde_prior_terms_value_and_grad": [_i, _p, _p, _p, _p, _p, _p, _p, _d, _d, _d, _p, _d, _p, _i, _p, _sz, _p],
     "bde_bbb_linear_workspace_bytes": [_i, _i, _i, C.POINTER(_sz)],
     "bde_bbb_linear_fwd": [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _u64, _u64, _d, _p, _p, _p, _p, _sz, _p],
+    "bde_rank1_linear_fwd": [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _u64, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "bde_philox_normal": [_p, _i64, _u64, _u64, _i64, _p],
     "bde_multi_tensor_copy": [_p, _p, _p, _p, _i, _i, _p],
     "bde_multi_tensor_unscale_copy": [_p, _p, _p, _p, _i, _i, _p, _p, _p],

@@ -7,6 +7,11 @@ csrc/bbb_linear.cu); `install()` rebinds `BBBLinear.forward` of the reference to
 every other branch of the reference's forward (parameter sampling, CPU tensors, layers without bias, inputs that are not
 [batch, in] fp32) on the reference's own code.
 
+The Rank-1 VI layer (src/algos/rank1.py:50-64, `Rank1Linear.forward`: sample s and r, `linear(input * s) * r + bias`) gets
+the same treatment: `rank1_linear_forward` is one launch of `bde_rank1_linear_fwd` — both Gaussian samples, the prologue
+scaling of the x operand and the epilogue scaling fused around the tensor-core product — and `install()` rebinds
+`Rank1Linear.forward` to `make_patched_rank1_forward`.
+
 Backward: plain library GEMMs on the saved activations (torch.matmul), the formulas of autograd through the same graph.
 """
 from __future__ import annotations
@@ -89,6 +94,63 @@ def make_patched_forward(reference_forward):
         if fused_forward_applies(self, input):
             self.kl = 0
             return bbb_linear_forward(self, input)
+        return reference_forward(self, input)
+    patched_forward._bde_fused = True
+    return patched_forward
+
+
+class _Rank1Linear(torch.autograd.Function):
+    """out = linear(x * s, W) * r + bias with s = s_mu + eps_s * softplus(s_rho), r likewise (rank1.py:50-64)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, s_mu, s_rho, r_mu, r_rho, bias, eps_s, eps_r, sid_s, sid_r):
+        out, lin, s, r, es, er = ops.rank1_linear_fwd(x, weight, s_mu, s_rho, r_mu, r_rho, bias, eps_s=eps_s, eps_r=eps_r,
+                                                      seed=noise.seed(), stream_id_s=sid_s, stream_id_r=sid_r,
+                                                      workspace=_workspace)
+        ctx.save_for_backward(x, weight, s_rho, r_rho, lin, s, r, es, er)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, weight, s_rho, r_rho, lin, s, r, es, er = ctx.saved_tensors
+        d_lin = grad_out * r
+        d_r = (grad_out * lin).sum(0)
+        d_xs = d_lin @ weight
+        d_w = d_lin.t() @ (x * s)
+        d_s = (d_xs * x).sum(0)
+        d_bias = grad_out.sum(0) if ctx.has_bias else None
+        return (d_xs * s, d_w, d_s, d_s * es * torch.sigmoid(s_rho), d_r, d_r * er * torch.sigmoid(r_rho), d_bias,
+                None, None, None, None)
+
+
+def rank1_forward_applies(layer, input: torch.Tensor) -> bool:
+    w = layer.layer.weight
+    return (input.is_cuda and input.dim() == 2 and input.dtype == torch.float32 and layer.in_features % 4 == 0
+            and w.dtype == torch.float32 and w.is_contiguous() and layer.layer.bias is None)
+
+
+def rank1_linear_forward(layer, input: torch.Tensor) -> torch.Tensor:
+    """rank1.py:50-64 for one Rank1Linear (reference class or a look-alike): component `component_counter`'s s, r and
+    bias row, then the counter advances."""
+    x = input if input.stride(1) == 1 and input.stride(0) % 4 == 0 and input.data_ptr() % 16 == 0 else input.contiguous()
+    c = layer.component_counter
+    sp, rp = layer.s[c], layer.r[c]
+    # the draws of the two GaussianParameter.sample() calls, in the reference's order (s first)
+    eps_s = noise.draw("gauss", layer.in_features, x.device)
+    sid_s = noise.next_stream_id()
+    eps_r = noise.draw("gauss", layer.out_features, x.device)
+    sid_r = noise.next_stream_id()
+    out = _Rank1Linear.apply(x, layer.layer.weight, sp.mean, sp.rho, rp.mean, rp.rho,
+                             layer.bias[c] if layer.bias is not None else None, eps_s, eps_r, sid_s, sid_r)
+    layer.component_counter = (c + 1) % layer.components
+    return out
+
+
+def make_patched_rank1_forward(reference_forward):
+    def patched_forward(self, input):
+        if rank1_forward_applies(self, input):
+            return rank1_linear_forward(self, input)
         return reference_forward(self, input)
     patched_forward._bde_fused = True
     return patched_forward

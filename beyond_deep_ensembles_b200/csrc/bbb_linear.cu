@@ -102,9 +102,69 @@ struct BblParams {
     float* partials;        // workspace: [mtiles][btiles][ksplits][2][NB][128]
     unsigned int* tickets;  // workspace: [mtiles * btiles], zero between launches
     int batch, in_features, out_features, nb, ksplits;
+    int two_phase;          // 1: partials only, bbb_linear_reduce_kernel sums them (many k splits)
     float mc;               // BBBLinear.mc_sample: the output is divided by it (bbb_layers.py:88)
     uint64_t seed, stream_id;
 };
+
+// fixed-order sum over the k splits of one (out-feature tile, batch tile), batch columns [bc_begin, bc_end), then the
+// epilogue; thread = out-feature row.  Called by the last CTA of the tile (few splits) or by the reduce kernel (many)
+template <int NB, int BC>
+__device__ __forceinline__ void bbl_reduce_epilogue(const BblParams& p, int mt, int bt, int nbt, int tid, int bc_begin, int bc_end) {
+    const int o0 = mt * kBlM, b0 = bt * NB, o = o0 + tid;
+    const float* base = p.partials + ((static_cast<size_t>(mt) * nbt + bt) * p.ksplits * 2) * NB * kBlM;
+    float bmean = 0.f, bvar = 0.f;
+    if (o < p.out_features && p.b_mu) {
+        bmean = p.b_mu[o];
+        bvar = var_of_rho(p.b_rho[o]);
+    }
+    // BC batch columns reduced together: 2 x BC independent loads in flight per k split
+    for (int bc = bc_begin; bc < bc_end && b0 + bc < p.batch; bc += BC) {
+        double sm[BC], sv[BC];
+#pragma unroll
+        for (int j = 0; j < BC; ++j) sm[j] = sv[j] = 0.0;
+        // four k splits per round: 4 x 2 x 16 independent L2 loads in flight per thread, summed in split order
+        for (int s0 = 0; s0 < p.ksplits; s0 += 4) {
+            float vm[4][BC], vv[4][BC];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool on = s0 + u < p.ksplits;
+                const float* ps = base + static_cast<size_t>(on ? s0 + u : s0) * 2 * NB * kBlM + tid;
+#pragma unroll
+                for (int j = 0; j < BC; ++j) {
+                    vm[u][j] = on ? __ldcg(ps + static_cast<size_t>(bc + j) * kBlM) : 0.f;
+                    vv[u][j] = on ? __ldcg(ps + (static_cast<size_t>(NB) + bc + j) * kBlM) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < BC; ++j) {
+                    sm[j] += static_cast<double>(vm[u][j]);
+                    sv[j] += static_cast<double>(vv[u][j]);
+                }
+        }
+#pragma unroll
+        for (int j = 0; j < BC; ++j) {
+            const int b = bc + j;
+            if (o < p.out_features && b0 + b < p.batch) {
+                const float mean = __fadd_rn(bmean, static_cast<float>(sm[j]));          // baddbmm: add + matmul
+                const float sd = __fsqrt_rn(__fadd_rn(bvar, static_cast<float>(sv[j])));
+                const int64_t e = static_cast<int64_t>(b0 + b) * p.out_features + o;
+                float z;
+                if (p.eps) {
+                    z = p.eps[e];
+                } else {
+                    const float4 z4 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(e >> 2));
+                    z = (e & 3) == 0 ? z4.x : (e & 3) == 1 ? z4.y : (e & 3) == 2 ? z4.z : z4.w;
+                }
+                p.out[e] = __fdiv_rn(__fadd_rn(mean, __fmul_rn(sd, z)), p.mc);
+                if (p.act_std) p.act_std[e] = sd;
+                if (p.eps_out) p.eps_out[e] = z;
+            }
+        }
+    }
+}
 
 template <int NB>
 __global__ void __launch_bounds__(kBlThreads, 1)
@@ -227,6 +287,7 @@ bbb_linear_fwd_kernel(const __grid_constant__ CUtensorMap map_wmu, const __grid_
     mbar_wait(&mma_bar, phase);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }   // k blocks
+    if (p.two_phase) griddep_launch();   // the reduce kernel's CTAs may take their places; they wait for this grid to finish
 
     // accumulators -> split-K partial tile in the workspace: [2][NB][128], thread = out-feature row (TMEM lane)
     float* part = p.partials + (((static_cast<size_t>(mt) * gridDim.z + bt) * p.ksplits + ks) * 2) * NB * kBlM;
@@ -245,6 +306,7 @@ bbb_linear_fwd_kernel(const __grid_constant__ CUtensorMap map_wmu, const __grid_
     __threadfence();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (p.two_phase) return;   // the reduce kernel (launched behind this grid) sums the partial tiles
     if (tid == 0) {
         const unsigned int prev = atomicAdd(&p.tickets[mt * gridDim.z + bt], 1u);
         is_last = prev == static_cast<unsigned int>(p.ksplits) - 1;
@@ -253,61 +315,223 @@ bbb_linear_fwd_kernel(const __grid_constant__ CUtensorMap map_wmu, const __grid_
     if (!is_last) return;
     __threadfence();
 
-    // last CTA of this (out-feature tile, batch tile): fixed-order sum over the k blocks, then the epilogue
-    const int o = o0 + tid;
-    const float* base = p.partials + ((static_cast<size_t>(mt) * gridDim.z + bt) * p.ksplits * 2) * NB * kBlM;
-    float bmean = 0.f, bvar = 0.f;
-    if (o < p.out_features && p.b_mu) {
-        bmean = p.b_mu[o];
-        bvar = var_of_rho(p.b_rho[o]);
+    bbl_reduce_epilogue<NB, 16>(p, mt, bt, gridDim.z, tid, 0, NB);
+    if (tid == 0) p.tickets[mt * gridDim.z + bt] = 0u;   // workspace reusable by the next launch
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Rank-1 VI linear layer (src/algos/rank1.py:50-64): out = (linear(x * s, W) * r) + bias with s = mu_s + eps_s *
+// softplus(rho_s) (one value per INPUT feature) and r likewise per OUTPUT feature — the prologue / epilogue scaling of
+// SURVEY §8 f4 fused around the same tensor-core product: s is sampled and multiplied into the x operand while the tile is
+// rewritten into its tf32 triples, r and the bias are applied in the fixed-order split-K epilogue.
+// ------------------------------------------------------------------------------------------------------------------
+struct R1Params {
+    const float* s_mu;      // [in]
+    const float* s_rho;
+    const float* r_mu;      // [out]
+    const float* r_rho;
+    const float* bias;      // [out] or null
+    const float* eps_s;     // [in] injected or null (Philox stream sid_s)
+    const float* eps_r;     // [out] injected or null (Philox stream sid_r)
+    float* out;             // [batch, out]
+    float* lin;             // [batch, out]: linear(x * s, W) before r and bias (backward needs it)
+    float* s_out;           // [in], [out]: the sampled vectors and the noise they used
+    float* r_out;
+    float* eps_s_out;
+    float* eps_r_out;
+    float* partials;        // workspace: [mtiles][btiles][ksplits][NB][128]
+    unsigned int* tickets;
+    int batch, in_features, out_features, ksplits, two_phase;
+    uint64_t seed, sid_s, sid_r;
+};
+
+__device__ __forceinline__ float philox_normal1(uint64_t seed, uint64_t stream_id, int64_t e) {
+    const float4 z4 = philox_normal4(seed, stream_id, static_cast<uint64_t>(e >> 2));
+    return (e & 3) == 0 ? z4.x : (e & 3) == 1 ? z4.y : (e & 3) == 2 ? z4.z : z4.w;
+}
+
+template <int NB, int BC>
+__device__ __forceinline__ void r1_reduce_epilogue(const R1Params& p, int mt, int bt, int nbt, int tid, int bc_begin, int bc_end) {
+    const int o0 = mt * kBlM, b0 = bt * NB, o = o0 + tid;
+    const float* base = p.partials + (static_cast<size_t>(mt) * nbt + bt) * p.ksplits * NB * kBlM;
+    float rv = 0.f, bias = 0.f;
+    if (o < p.out_features) {
+        const float e = p.eps_r ? p.eps_r[o] : philox_normal1(p.seed, p.sid_r, o);
+        rv = __fadd_rn(p.r_mu[o], __fmul_rn(e, softplus_ref(p.r_rho[o])));
+        if (p.bias) bias = p.bias[o];
+        if (bt == 0 && bc_begin == 0) {
+            p.r_out[o] = rv;
+            p.eps_r_out[o] = e;
+        }
     }
-    constexpr int BC = 16;   // batch columns reduced together: 2 x 16 independent loads in flight per k split
-    for (int bc = 0; bc < NB && b0 + bc < p.batch; bc += BC) {
-        double sm[BC], sv[BC];
+    for (int bc = bc_begin; bc < bc_end && b0 + bc < p.batch; bc += BC) {
+        double sm[BC];
 #pragma unroll
-        for (int j = 0; j < BC; ++j) sm[j] = sv[j] = 0.0;
-        // four k splits per round: 4 x 2 x 16 independent L2 loads in flight per thread, summed in split order
+        for (int j = 0; j < BC; ++j) sm[j] = 0.0;
         for (int s0 = 0; s0 < p.ksplits; s0 += 4) {
-            float vm[4][BC], vv[4][BC];
+            float vm[4][BC];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const bool on = s0 + u < p.ksplits;
-                const float* ps = base + static_cast<size_t>(on ? s0 + u : s0) * 2 * NB * kBlM + tid;
+                const float* ps = base + static_cast<size_t>(on ? s0 + u : s0) * NB * kBlM + tid;
 #pragma unroll
-                for (int j = 0; j < BC; ++j) {
-                    vm[u][j] = on ? __ldcg(ps + static_cast<size_t>(bc + j) * kBlM) : 0.f;
-                    vv[u][j] = on ? __ldcg(ps + (static_cast<size_t>(NB) + bc + j) * kBlM) : 0.f;
-                }
+                for (int j = 0; j < BC; ++j) vm[u][j] = on ? __ldcg(ps + static_cast<size_t>(bc + j) * kBlM) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int j = 0; j < BC; ++j) {
-                    sm[j] += static_cast<double>(vm[u][j]);
-                    sv[j] += static_cast<double>(vv[u][j]);
-                }
+                for (int j = 0; j < BC; ++j) sm[j] += static_cast<double>(vm[u][j]);
         }
 #pragma unroll
         for (int j = 0; j < BC; ++j) {
             const int b = bc + j;
             if (o < p.out_features && b0 + b < p.batch) {
-                const float mean = __fadd_rn(bmean, static_cast<float>(sm[j]));          // baddbmm: add + matmul
-                const float sd = __fsqrt_rn(__fadd_rn(bvar, static_cast<float>(sv[j])));
                 const int64_t e = static_cast<int64_t>(b0 + b) * p.out_features + o;
-                float z;
-                if (p.eps) {
-                    z = p.eps[e];
-                } else {
-                    const float4 z4 = philox_normal4(p.seed, p.stream_id, static_cast<uint64_t>(e >> 2));
-                    z = (e & 3) == 0 ? z4.x : (e & 3) == 1 ? z4.y : (e & 3) == 2 ? z4.z : z4.w;
-                }
-                p.out[e] = __fdiv_rn(__fadd_rn(mean, __fmul_rn(sd, z)), p.mc);
-                if (p.act_std) p.act_std[e] = sd;
-                if (p.eps_out) p.eps_out[e] = z;
+                const float lin = static_cast<float>(sm[j]);
+                p.lin[e] = lin;
+                const float y = __fmul_rn(lin, rv);                       // self.layer(input * s) * r
+                p.out[e] = p.bias ? __fadd_rn(y, bias) : y;               // output += bias[component]
             }
         }
     }
-    if (tid == 0) p.tickets[mt * gridDim.z + bt] = 0u;   // workspace reusable by the next launch
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kBlThreads, 1)
+rank1_linear_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
+                        const __grid_constant__ R1Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float* a_w[3];    // W as h / m / l tiles [128][32]
+    float* b_x[3];    // x * s as h / m / l tiles [NB][32]
+    {
+        float* t = reinterpret_cast<float*>(smem);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a_w[i] = t + i * kBlM * kBlK;
+        t += 3 * kBlM * kBlK;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) b_x[i] = t + i * NB * kBlK;
+    }
+    __shared__ __align__(8) uint64_t load_bar, mma_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ bool is_last;
+    __shared__ float s_blk[kBlK];
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int mt = blockIdx.x, ks = blockIdx.y, bt = blockIdx.z;
+    const int o0 = mt * kBlM, b0 = bt * NB;
+    constexpr int TMEM_COLS = NB < 32 ? 32 : NB;
+
+    if (tid == 0) {
+        mbar_init(&load_bar, 1);
+        mbar_init(&mma_bar, 1);
+        mbar_fence_init();
+        tma_prefetch_map(&map_w);
+        tma_prefetch_map(&map_x);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int nkb = (p.in_features + kBlK - 1) / kBlK;
+    int it = 0;
+    for (int kb_idx = ks; kb_idx < nkb; kb_idx += p.ksplits, ++it) {
+        const int k0 = kb_idx * kBlK;
+        const uint32_t phase = static_cast<uint32_t>(it & 1);
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&load_bar, (kBlM + NB) * kBlK * 4);
+            tma_load_2d_sw(a_w[0], &map_w, k0, o0, &load_bar);
+            tma_load_2d(b_x[0], &map_x, k0, b0, &load_bar);
+        }
+        if (tid < kBlK) {   // s for this k block: mean + eps * softplus(rho) (util.py:170-171), 0 beyond in_features
+            const int k = k0 + tid;
+            float sv = 0.f;
+            if (k < p.in_features) {
+                const float e = p.eps_s ? p.eps_s[k] : philox_normal1(p.seed, p.sid_s, k);
+                sv = __fadd_rn(p.s_mu[k], __fmul_rn(e, softplus_ref(p.s_rho[k])));
+                if (mt == 0 && bt == 0) {
+                    p.s_out[k] = sv;
+                    p.eps_s_out[k] = e;
+                }
+            }
+            s_blk[tid] = sv;
+        }
+        mbar_wait(&load_bar, phase);
+        __syncthreads();   // s_blk visible
+        for (int c = tid; c < kBlM * 8; c += kBlThreads) split3(reinterpret_cast<float4*>(a_w[0])[c], a_w, c);
+        for (int c = tid; c < NB * 8; c += kBlThreads) {
+            const float4 x = reinterpret_cast<float4*>(b_x[0])[c];
+            const int kc = ((c & 7) ^ ((c >> 3) & 7)) * 4;   // logical k of this swizzled chunk inside the block
+            const float4 xs = make_float4(__fmul_rn(x.x, s_blk[kc]), __fmul_rn(x.y, s_blk[kc + 1]), __fmul_rn(x.z, s_blk[kc + 2]),
+                                          __fmul_rn(x.w, s_blk[kc + 3]));   // input * s, rounded to fp32 like the reference
+            split3(xs, b_x, c);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(kBlM, NB);
+#pragma unroll
+            for (int kk = 0; kk < kBlK / 8; ++kk) {
+                const int kb = kk * 32;
+                constexpr int PA[6] = {2, 0, 1, 1, 0, 0}, PB[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+                for (int t = 0; t < 6; ++t)
+                    umma_tf32(tmem_base, umma_desc_k_sw128(a_w[PA[t]], kb), umma_desc_k_sw128(b_x[PB[t]], kb), idesc, (it | kk | t) > 0);
+            }
+            umma_commit(&mma_bar);
+        }
+        mbar_wait(&mma_bar, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (p.two_phase) griddep_launch();
+
+    float* part = p.partials + ((static_cast<size_t>(mt) * gridDim.z + bt) * p.ksplits + ks) * NB * kBlM;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < NB; c0 += 16) {
+        float v[16];
+        tmem_ld16(lane_base + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) part[static_cast<size_t>(c0 + j) * kBlM + tid] = v[j];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __threadfence();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (p.two_phase) return;   // the reduce kernel (launched behind this grid) sums the partial tiles
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(&p.tickets[mt * gridDim.z + bt], 1u);
+        is_last = prev == static_cast<unsigned int>(p.ksplits) - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+
+    r1_reduce_epilogue<NB, 16>(p, mt, bt, gridDim.z, tid, 0, NB);
+    if (tid == 0) p.tickets[mt * gridDim.z + bt] = 0u;
+}
+
+// second phase for many k splits: grid (out tiles, NB / 4 column groups, batch tiles) — the partial tiles (L2-resident) are
+// summed by many small CTAs instead of one CTA per tile; launched programmatically behind the product kernel
+constexpr int kBlReduceCols = 4;
+template <int NB>
+__global__ void __launch_bounds__(kBlThreads) bbb_linear_reduce_kernel(const __grid_constant__ BblParams p) {
+    griddep_wait();
+    bbl_reduce_epilogue<NB, kBlReduceCols>(p, blockIdx.x, blockIdx.z, gridDim.z, threadIdx.x, blockIdx.y * kBlReduceCols,
+                                           (blockIdx.y + 1) * kBlReduceCols);
+}
+template <int NB>
+__global__ void __launch_bounds__(kBlThreads) rank1_linear_reduce_kernel(const __grid_constant__ R1Params p) {
+    griddep_wait();
+    r1_reduce_epilogue<NB, kBlReduceCols>(p, blockIdx.x, blockIdx.z, gridDim.z, threadIdx.x, blockIdx.y * kBlReduceCols,
+                                          (blockIdx.y + 1) * kBlReduceCols);
 }
 
 // tensor map over a row-major fp32 matrix [rows, cols] (row stride ld), box = 32 columns x box_rows, 128-byte swizzle
@@ -340,17 +564,33 @@ static int bde::encode_sw128_map(CUtensorMap* map, const float* base, int64_t ro
 
 static int bbl_nb(int batch) { return batch <= 16 ? 16 : (batch <= 32 ? 32 : (batch <= 64 ? 64 : 128)); }
 
-// split-K factor: one k block per CTA while that fills the GPU without drowning the last CTA in partial tiles (its
-// fixed-order sum reads ksplits x 2 x NB x 128 floats: capped at ~512 KB), otherwise a CTA walks several k blocks
+// split-K factor: one k block per CTA while that helps to fill the GPU (~two CTAs per SM in total), otherwise a CTA walks
+// several k blocks.  Up to kBlTicketSplits splits the last CTA of a tile sums the partial tiles itself (ticket); beyond
+// that the sum is a second, programmatically launched kernel spread over (tiles x NB / 4) CTAs — one CTA reading
+// ksplits x 2 x NB x 128 floats through its own L2 port was the dominant cost at batch >= 64
+constexpr int kBlTicketSplits = 4;
 static int bbl_ksplits(int batch, int in_features, int out_features) {
     const int nb = bbl_nb(batch);
     const int nkb = (in_features + kBlK - 1) / kBlK;
     const int mtiles = (out_features + kBlM - 1) / kBlM, btiles = (batch + nb - 1) / nb;
-    int ks = (2 * 148 + mtiles * btiles - 1) / (mtiles * btiles);      // ~two CTAs per SM in total
-    const int cap = 512 / nb > 1 ? 512 / nb : 1;
-    if (ks > cap) ks = cap;
+    int ks = (2 * 148 + mtiles * btiles - 1) / (mtiles * btiles);
     if (ks > nkb) ks = nkb;
     return ks < 1 ? 1 : ks;
+}
+
+template <typename Params>
+static int launch_reduce(void (*kernel)(const Params), const Params& p, dim3 grid, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kBlThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    BDE_RETURN_IF_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    return BDE_OK;
 }
 
 extern "C" int bde_bbb_linear_workspace_bytes(int batch, int in_features, int out_features, size_t* bytes) {
@@ -372,6 +612,7 @@ static int launch_bbl(const CUtensorMap& mw, const CUtensorMap& mr, const CUtens
     }
     bbb_linear_fwd_kernel<NB><<<grid, kBlThreads, smem, st>>>(mw, mr, mx, p);
     BDE_CHECK_LAUNCH();
+    if (p.two_phase) return launch_reduce(bbb_linear_reduce_kernel<NB>, p, dim3(grid.x, NB / kBlReduceCols, grid.z), st);
     return BDE_OK;
 }
 
@@ -400,6 +641,7 @@ extern "C" int bde_bbb_linear_fwd(const float* x, int64_t ldx, int batch, int in
     p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256 +
                                           ((static_cast<size_t>(mtiles) * btiles * sizeof(unsigned int) + 255) & ~static_cast<size_t>(255)));
     p.batch = batch, p.in_features = in_features, p.out_features = out_features, p.nb = nb, p.ksplits = ks;
+    p.two_phase = ks > kBlTicketSplits;
     p.mc = static_cast<float>(mc_sample > 0.0 ? mc_sample : 1.0);
     p.seed = seed, p.stream_id = stream_id;
     const dim3 grid(mtiles, ks, btiles);
@@ -409,5 +651,57 @@ extern "C" int bde_bbb_linear_fwd(const float* x, int64_t ldx, int batch, int in
         case 32: return launch_bbl<32>(mw, mr, mx, p, grid, st);
         case 64: return launch_bbl<64>(mw, mr, mx, p, grid, st);
         default: return launch_bbl<128>(mw, mr, mx, p, grid, st);
+    }
+}
+
+template <int NB>
+static int launch_r1(const CUtensorMap& mw, const CUtensorMap& mx, const R1Params& p, dim3 grid, cudaStream_t st) {
+    constexpr int smem = (3 * kBlM + 3 * NB) * kBlK * 4 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        BDE_RETURN_IF_CUDA(cudaFuncSetAttribute(rank1_linear_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    rank1_linear_fwd_kernel<NB><<<grid, kBlThreads, smem, st>>>(mw, mx, p);
+    BDE_CHECK_LAUNCH();
+    if (p.two_phase) return launch_reduce(rank1_linear_reduce_kernel<NB>, p, dim3(grid.x, NB / kBlReduceCols, grid.z), st);
+    return BDE_OK;
+}
+
+extern "C" int bde_rank1_linear_fwd(const float* x, int64_t ldx, int batch, int in_features, int out_features, const float* W,
+                                    const float* s_mu, const float* s_rho, const float* r_mu, const float* r_rho,
+                                    const float* bias, const float* eps_s, const float* eps_r, uint64_t seed, uint64_t sid_s,
+                                    uint64_t sid_r, float* out, float* lin, float* s_out, float* r_out, float* eps_s_out,
+                                    float* eps_r_out, void* workspace, size_t workspace_bytes, bde_stream_t stream) {
+    if (!x || !W || !s_mu || !s_rho || !r_mu || !r_rho || !out || !lin || !s_out || !r_out || !eps_s_out || !eps_r_out ||
+        !workspace || batch < 1 || in_features < 1 || out_features < 1 || ldx < in_features)
+        return BDE_ERR_INVALID_ARG;
+    if (!aligned16(x) || !aligned16(W) || (ldx % 4) != 0 || (in_features % 4) != 0) return BDE_ERR_ALIGNMENT;
+    size_t need = 0;
+    bde_bbb_linear_workspace_bytes(batch, in_features, out_features, &need);   // same tiling, half the partials
+    if (workspace_bytes < need) return BDE_ERR_WORKSPACE;
+    const int nb = bbl_nb(batch);
+    const int mtiles = (out_features + kBlM - 1) / kBlM, btiles = (batch + nb - 1) / nb;
+    const int ks = bbl_ksplits(batch, in_features, out_features);
+    CUtensorMap mw, mx;
+    int rc = encode_sw128_map(&mw, W, out_features, in_features, in_features, kBlM);
+    if (rc == BDE_OK) rc = encode_sw128_map(&mx, x, batch, in_features, ldx, nb);
+    if (rc != BDE_OK) return rc;
+    R1Params p{};
+    p.s_mu = s_mu, p.s_rho = s_rho, p.r_mu = r_mu, p.r_rho = r_rho, p.bias = bias, p.eps_s = eps_s, p.eps_r = eps_r;
+    p.out = out, p.lin = lin, p.s_out = s_out, p.r_out = r_out, p.eps_s_out = eps_s_out, p.eps_r_out = eps_r_out;
+    p.tickets = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + 256);
+    p.partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256 +
+                                          ((static_cast<size_t>(mtiles) * btiles * sizeof(unsigned int) + 255) & ~static_cast<size_t>(255)));
+    p.batch = batch, p.in_features = in_features, p.out_features = out_features, p.ksplits = ks;
+    p.two_phase = ks > kBlTicketSplits;
+    p.seed = seed, p.sid_s = sid_s, p.sid_r = sid_r;
+    const dim3 grid(mtiles, ks, btiles);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (nb) {
+        case 16: return launch_r1<16>(mw, mx, p, grid, st);
+        case 32: return launch_r1<32>(mw, mx, p, grid, st);
+        case 64: return launch_r1<64>(mw, mx, p, grid, st);
+        default: return launch_r1<128>(mw, mx, p, grid, st);
     }
 }

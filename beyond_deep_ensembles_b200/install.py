@@ -64,4 +64,14 @@ def install(reference_root: str | None = None) -> list[str]:
         patched.append("src.algos.bbb_layers.BBBLinear.forward")
     except Exception:
         pass
+    # ... and Rank1Linear (rank1.py:50-64): both samples, the x * s prologue and the * r + bias epilogue in the same kernel
+    try:
+        from . import bbb_layers
+        ref_rank1 = importlib.import_module("src.algos.rank1")
+        fwd = ref_rank1.Rank1Linear.forward
+        if not getattr(fwd, "_bde_fused", False):
+            ref_rank1.Rank1Linear.forward = bbb_layers.make_patched_rank1_forward(fwd)
+        patched.append("src.algos.rank1.Rank1Linear.forward")
+    except Exception:
+        pass
     return patched

@@ -373,6 +373,36 @@ def bbb_linear_fwd(x, w_mu, w_rho, b_mu, b_rho, *, eps=None, seed: int = 0, stre
     return out, act_std, eps_used
 
 
+def rank1_linear_fwd(x, weight, s_mu, s_rho, r_mu, r_rho, bias=None, *, eps_s=None, eps_r=None, seed: int = 0,
+                     stream_id_s: int = 0, stream_id_r: int = 0, workspace=None):
+    """f4 (second half): Rank1Linear.forward (rank1.py:50-64) as one tcgen05 kernel — s and r sampled inside, the x * s
+    prologue and the * r + bias epilogue fused around the product.  x [batch, in] (rows contiguous), weight [out, in],
+    s_* [in], r_* [out], bias [out] or None, eps_s [in] / eps_r [out] or None (Philox).
+    Returns (out, lin, s, r, eps_s_used, eps_r_used) with lin = linear(x * s, weight)."""
+    require_cuda(x, weight, s_mu, s_rho, r_mu, r_rho, bias, eps_s, eps_r)
+    _lib.require_f32(x, weight, s_mu, s_rho, r_mu, r_rho, bias, eps_s, eps_r)
+    batch, fin, ldx = _rows(x)
+    fout = weight.shape[0]
+    if tuple(weight.shape) != (fout, fin) or not weight.is_contiguous():
+        raise ValueError("weight must be contiguous [out_features, in_features]")
+    for t, size, name in ((s_mu, fin, "s_mu"), (s_rho, fin, "s_rho"), (r_mu, fout, "r_mu"), (r_rho, fout, "r_rho"),
+                          (bias, fout, "bias"), (eps_s, fin, "eps_s"), (eps_r, fout, "eps_r")):
+        if t is not None and (_vec(t).numel() != size or not t.is_contiguous()):
+            raise ValueError(f"{name} must be a contiguous vector of {size} elements")
+    nbytes = C.c_size_t(0)
+    _lib.check(_lib.get().bde_bbb_linear_workspace_bytes(batch, fin, fout, C.byref(nbytes)), "bde_bbb_linear_workspace_bytes")
+    ws = workspace(x.device, nbytes.value) if workspace is not None else zeros_bytes(nbytes.value, x.device)
+    out = torch.empty((batch, fout), dtype=torch.float32, device=x.device)
+    lin = torch.empty_like(out)
+    s, es = torch.empty(fin, dtype=torch.float32, device=x.device), torch.empty(fin, dtype=torch.float32, device=x.device)
+    r, er = torch.empty(fout, dtype=torch.float32, device=x.device), torch.empty(fout, dtype=torch.float32, device=x.device)
+    _lib.call("bde_rank1_linear_fwd", x.data_ptr(), ldx, batch, fin, fout, weight.data_ptr(), s_mu.data_ptr(), s_rho.data_ptr(),
+              r_mu.data_ptr(), r_rho.data_ptr(), _lib.ptr(bias), _lib.ptr(eps_s), _lib.ptr(eps_r), int(seed), int(stream_id_s),
+              int(stream_id_r), out.data_ptr(), lin.data_ptr(), s.data_ptr(), r.data_ptr(), es.data_ptr(), er.data_ptr(),
+              ws.data_ptr(), ws.numel() * 8, _s(x))
+    return out, lin, s, r, es, er
+
+
 def value_workspace(device) -> torch.Tensor:
     nbytes = C.c_size_t(0)
     _lib.check(_lib.get().bde_value_workspace_bytes(C.byref(nbytes)), "bde_value_workspace_bytes")

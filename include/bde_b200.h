@@ -425,6 +425,19 @@ int bde_bbb_linear_fwd(const float* x, int64_t ldx, int batch, int in_features, 
                        uint64_t stream_id, double mc_sample, float* out, float* act_std, float* eps_out, void* workspace,
                        size_t workspace_bytes, bde_stream_t stream);
 
+/* f4, second half: the Rank-1 VI linear layer src/algos/rank1.py:50-64 —
+ *   s = s_mu + eps_s * softplus(s_rho) [in],  r = r_mu + eps_r * softplus(r_rho) [out],  out = linear(x * s, W) * r + bias
+ * — with the prologue / epilogue scaling fused around the same tcgen05 product as bde_bbb_linear_fwd (exact 3-way tf32
+ * split, TMEM accumulator, deterministic split-K).  W: [out, in] contiguous; bias: [out] (the component's row) or null;
+ * eps_s / eps_r: injected noise or null (Philox streams sid_s / sid_r, counter = element index / 4, i.e. the values
+ * bde_gauss_sample_fwd draws for the same stream ids).  lin receives linear(x * s, W); s_out / r_out / eps_s_out /
+ * eps_r_out the sampled vectors and their noise (backward pass).  Workspace: bde_bbb_linear_workspace_bytes. */
+int bde_rank1_linear_fwd(const float* x, int64_t ldx, int batch, int in_features, int out_features, const float* W,
+                         const float* s_mu, const float* s_rho, const float* r_mu, const float* r_rho, const float* bias,
+                         const float* eps_s, const float* eps_r, uint64_t seed, uint64_t sid_s, uint64_t sid_r, float* out,
+                         float* lin, float* s_out, float* r_out, float* eps_s_out, float* eps_r_out, void* workspace,
+                         size_t workspace_bytes, bde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -327,3 +327,16 @@ def bbb_linear_fwd(x, w_mu, w_rho, b_mu, b_rho, eps, mc_sample: float = 1.0, dty
     var = F.linear((x ** 2).clamp(min=1e-4), (F.softplus(w_rho) ** 2).clamp(min=1e-4), b_var)
     std = torch.sqrt(var)
     return (mean + std * eps) / mc_sample, std
+
+
+def rank1_linear_fwd(x, weight, s_mu, s_rho, r_mu, r_rho, bias, eps_s, eps_r, dtype=torch.float32):
+    """Rank1Linear.forward (rank1.py:50-64) with GaussianParameter.sample (util.py:170-171) written out:
+    s = s_mu + eps_s * softplus(s_rho), r likewise; out = linear(x * s, weight) * r (+ bias).  Returns (out, lin, s, r)."""
+    c = lambda t: t.to(dtype)
+    s = c(s_mu) + c(eps_s) * F.softplus(c(s_rho))
+    r = c(r_mu) + c(eps_r) * F.softplus(c(r_rho))
+    lin = F.linear(c(x) * s, c(weight))
+    out = lin * r
+    if bias is not None:
+        out = out + c(bias).unsqueeze(0)
+    return out, lin, s, r

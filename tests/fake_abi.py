@@ -351,6 +351,23 @@ class FakeLib:
             _f32(eps_out, batch * fout).copy_(E.reshape(-1))
         return 0
 
+    def bde_rank1_linear_fwd(self, x, ldx, batch, fin, fout, W, s_mu, s_rho, r_mu, r_rho, bias, eps_s, eps_r, seed, sid_s, sid_r,
+                             out, lin, s_out, r_out, es_out, er_out, ws, wsb, stream):
+        self.calls.append("rank1_linear")
+        X = _mat(x, batch, fin, ldx)
+        Wt = _f32(W, fout * fin).view(fout, fin)
+        es = _f32(eps_s, fin) if eps_s else torch.from_numpy(O.philox_normal(fin, seed, sid_s))
+        er = _f32(eps_r, fout) if eps_r else torch.from_numpy(O.philox_normal(fout, seed, sid_r))
+        y, l, s, r = O.rank1_linear_fwd(X, Wt, _f32(s_mu, fin), _f32(s_rho, fin), _f32(r_mu, fout), _f32(r_rho, fout),
+                                        _f32(bias, fout) if bias else None, es, er)
+        _f32(out, batch * fout).copy_(y.reshape(-1))
+        _f32(lin, batch * fout).copy_(l.reshape(-1))
+        _f32(s_out, fin).copy_(s)
+        _f32(r_out, fout).copy_(r)
+        _f32(es_out, fin).copy_(es)
+        _f32(er_out, fout).copy_(er)
+        return 0
+
     def bde_philox_normal(self, out, count, seed, sid, elem0, stream):
         _f32(out, count).copy_(torch.from_numpy(O.philox_normal(count, seed, sid, elem0)))
         return 0

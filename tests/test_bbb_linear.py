@@ -152,3 +152,139 @@ def test_bbb_linear_host_logic_on_the_abi_double(monkeypatch):
     assert fake.calls.count("bbb_linear") == 2
     with pytest.raises(AssertionError):
         fwd(layer, torch.randn(2, 3, 8))       # not [batch, in]: the layer's own forward
+
+
+# ---- Rank1Linear (src/algos/rank1.py:50-64): sample s / r, linear(x * s) * r + bias ----------------------------------------
+
+def _rank1_case(batch, fin, fout, seed, bias=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, fin, generator=g)
+    w = torch.randn(fout, fin, generator=g) / fin ** 0.5
+    s_mu = torch.where(torch.rand(fin, generator=g) < 0.5, -1.0, 1.0)         # GaussianParameter.sign_init (util.py:163-166)
+    r_mu = torch.where(torch.rand(fout, generator=g) < 0.5, -1.0, 1.0)
+    s_rho = -3.0 + 0.5 * torch.randn(fin, generator=g)
+    r_rho = -3.0 + 0.5 * torch.randn(fout, generator=g)
+    s_rho[0], r_rho[0] = 25.0, -30.0                                            # softplus threshold / underflow
+    b = 0.1 * torch.randn(fout, generator=g) if bias else None
+    return x, w, s_mu, s_rho, r_mu, r_rho, b, torch.randn(fin, generator=g), torch.randn(fout, generator=g)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,fin,fout", [s for s in SHAPES if s[1] % 4 == 0] + [(16, 64, 10), (256, 1024, 512)])
+def test_rank1_linear_fwd_vs_oracle(cuda_lib, batch, fin, fout):
+    from beyond_deep_ensembles_b200 import ops
+    for bias in (True, False):
+        case = _rank1_case(batch, fin, fout, seed=batch + 3 * fin + 7 * fout, bias=bias)
+        x, w, s_mu, s_rho, r_mu, r_rho, b, es, er = case
+        d = [t.cuda() if t is not None else None for t in case]
+        out, lin, s, r, es_used, er_used = ops.rank1_linear_fwd(*d[:7], eps_s=d[7], eps_r=d[8])
+        # the two samples: the oracle's statement within fp32 tolerance (softplus is a libm call on either side), and
+        # bit-identical to what GaussianParameter.sample's own kernel (K8) gives for the same noise
+        _, _, s_ref, r_ref = O.rank1_linear_fwd(x, w, s_mu, s_rho, r_mu, r_rho, b, es, er, dtype=torch.float64)
+        np.testing.assert_allclose(s.cpu().numpy(), s_ref.numpy(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(r.cpu().numpy(), r_ref.numpy(), rtol=RTOL, atol=ATOL)
+        s_k8, r_k8 = torch.empty_like(d[2]), torch.empty_like(d[4])
+        ops.gauss_sample_fwd(d[2], d[3], s_k8, eps=d[7], seed=0, stream_id=0)
+        ops.gauss_sample_fwd(d[4], d[5], r_k8, eps=d[8], seed=0, stream_id=0)
+        assert torch.equal(s, s_k8) and torch.equal(r, r_k8)
+        assert torch.equal(es_used.cpu(), es) and torch.equal(er_used.cpu(), er)
+        s32, r32 = s.cpu(), r.cpu()
+        # the product against the fp64 evaluation of the same formula on the SAME fp32 operand x * s; tolerance of an
+        # fp32 dot product: rtol on the result plus 1e-7 of the sum of |terms| (the dot product's condition)
+        xs = x * s32
+        ref_lin = xs.double() @ w.double().t()
+        scale = xs.abs().double() @ w.abs().double().t()
+        err = (lin.cpu().double() - ref_lin).abs()
+        assert bool((err <= RTOL * ref_lin.abs() + 1e-7 * scale + ATOL * 0.1).all()), float(err.max())
+        lin32 = xs @ w.t()
+        assert float(err.max()) <= 10.0 * float((lin32.double() - ref_lin).abs().max()) + 1e-6
+        # epilogue: elementwise on the kernel's own lin, bit-exact
+        exp = lin.cpu() * r32
+        if bias:
+            exp = exp + b.unsqueeze(0)
+        assert torch.equal(out.cpu(), exp)
+        out2 = ops.rank1_linear_fwd(*d[:7], eps_s=d[7], eps_r=d[8])[0]
+        assert torch.equal(out, out2)                      # deterministic split-K, workspace left clean
+
+
+@pytest.mark.gpu
+def test_rank1_linear_philox_draws_are_those_of_gauss_sample(cuda_lib):
+    """Without injected noise the fused layer draws s and r from the same Philox streams GaussianParameter.sample (K8)
+    would use, so switching the fusion on or off does not change a seeded run."""
+    from beyond_deep_ensembles_b200 import ops
+    x, w, s_mu, s_rho, r_mu, r_rho, b, _, _ = [t.cuda() for t in _rank1_case(8, 96, 40, seed=4)]
+    out, lin, s, r, es, er = ops.rank1_linear_fwd(x, w, s_mu, s_rho, r_mu, r_rho, b, seed=11, stream_id_s=3, stream_id_r=4)
+    s_k8, r_k8 = torch.empty_like(s_mu), torch.empty_like(r_mu)
+    ops.gauss_sample_fwd(s_mu, s_rho, s_k8, eps=None, seed=11, stream_id=3)
+    ops.gauss_sample_fwd(r_mu, r_rho, r_k8, eps=None, seed=11, stream_id=4)
+    assert torch.equal(s, s_k8) and torch.equal(r, r_k8)
+    np.testing.assert_allclose(es.cpu().numpy(), O.philox_normal(96, 11, 3), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_rank1_linear_backward_matches_autograd_of_the_reference_formula(cuda_lib):
+    from beyond_deep_ensembles_b200.bbb_layers import _Rank1Linear
+    case = _rank1_case(16, 96, 40, seed=9)
+    leaves = [t.cuda().requires_grad_(True) for t in case[:7]]
+    es, er = case[7].cuda(), case[8].cuda()
+    out = _Rank1Linear.apply(*leaves, es, er, 0, 0)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    grads = torch.autograd.grad(out, leaves, g)
+    ref_leaves = [t.detach().double().requires_grad_(True) for t in leaves]
+    ref_out, _, _, _ = O.rank1_linear_fwd(*ref_leaves, es.double(), er.double(), dtype=torch.float64)
+    ref_grads = torch.autograd.grad(ref_out, ref_leaves, g.double())
+    for got, ref, name in zip(grads, ref_grads, ("x", "weight", "s_mu", "s_rho", "r_mu", "r_rho", "bias")):
+        scale = float(ref.abs().max())
+        np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=2e-5, atol=2e-6 * max(scale, 1.0), err_msg=name)
+
+
+def test_rank1_linear_host_logic_on_the_abi_double(monkeypatch):
+    """CPU: the patched Rank1Linear.forward over the oracle-backed ABI double — draw order (s, then r), the component
+    counter and its bias row, gradients reaching every parameter, fall-back for inputs the kernel does not take."""
+    import fake_abi
+    fake = fake_abi.install(monkeypatch)
+    from beyond_deep_ensembles_b200 import bbb_layers, noise, util
+
+    class Layer(torch.nn.Module):     # the attributes of the reference's Rank1Linear (rank1.py:10-34)
+        def __init__(self, fin, fout, components):
+            super().__init__()
+            self.in_features, self.out_features, self.components = fin, fout, components
+            self.layer = torch.nn.Linear(fin, fout, bias=False)
+            self.s = torch.nn.ModuleList([util.GaussianParameter(fin) for _ in range(components)])
+            self.r = torch.nn.ModuleList([util.GaussianParameter(fout) for _ in range(components)])
+            for p in list(self.s) + list(self.r):
+                p.sign_init()
+            self.bias = torch.nn.Parameter(torch.randn(components, fout))
+            self.component_counter = 0
+
+        def forward(self, x):
+            raise AssertionError("the reference forward must not be reached for a supported input")
+
+    monkeypatch.setattr(bbb_layers, "rank1_forward_applies", lambda layer, inp: inp.dim() == 2)
+    layer = Layer(8, 5, components=2)
+    fwd = bbb_layers.make_patched_rank1_forward(Layer.forward)
+    x = torch.randn(4, 8)
+    draws = [torch.randn(8), torch.randn(5), torch.randn(8), torch.randn(5)]
+    tape = iter(draws)
+    kinds = []
+
+    def inj(kind, numel):
+        kinds.append((kind, numel))
+        return next(tape)
+
+    with noise.inject(inj):
+        for c in range(2):
+            y = fwd(layer, x)
+            ref, _, _, _ = O.rank1_linear_fwd(x, layer.layer.weight, layer.s[c].mean, layer.s[c].rho, layer.r[c].mean,
+                                              layer.r[c].rho, layer.bias[c], draws[2 * c], draws[2 * c + 1])
+            np.testing.assert_allclose(y.detach().numpy(), ref.detach().numpy(), rtol=1e-6, atol=1e-7)
+            assert layer.component_counter == (c + 1) % 2
+        y.sum().backward()
+    assert kinds == [("gauss", 8), ("gauss", 5)] * 2
+    assert layer.bias.grad is not None and bool((layer.bias.grad[0] == 0).all()) and bool((layer.bias.grad[1] == 4).all())
+    for p in (layer.layer.weight, layer.s[1].mean, layer.s[1].rho, layer.r[1].mean, layer.r[1].rho):
+        assert p.grad is not None and bool(p.grad.abs().sum() > 0)
+    assert layer.s[0].rho.grad is None
+    assert fake.calls.count("rank1_linear") == 2
+    with pytest.raises(AssertionError):
+        fwd(layer, torch.randn(2, 3, 8))

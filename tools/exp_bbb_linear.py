@@ -53,3 +53,39 @@ for batch, fin, fout in ((16, 768, 768), (16, 768, 2), (128, 768, 768), (16, 204
     rec["fwd_speedup"] = round(rec["reference_eager_fwd_us"] / rec["fused_fwd_us"], 2)
     rec["weights_bytes"] = 8 * fin * fout
     print(json.dumps(rec), flush=True)
+
+
+# ---- Rank1Linear.forward (rank1.py:50-64): fused (one launch) against the reference's expression in eager PyTorch ----------
+def rank1_reference_forward(x, w, s_mu, s_rho, r_mu, r_rho, bias):
+    s = s_mu + torch.empty_like(s_mu).normal_(0, 1) * F.softplus(s_rho)      # util.py:170-171, twice
+    r = r_mu + torch.empty_like(r_mu).normal_(0, 1) * F.softplus(r_rho)
+    out = F.linear(x * s, w) * r
+    out += bias.unsqueeze(0)
+    return out
+
+
+for batch, fin, fout in ((16, 768, 768), (16, 768, 2), (128, 768, 768), (128, 64, 10)):
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = torch.randn(batch, fin, device=dev, generator=g)
+    w = torch.randn(fout, fin, device=dev, generator=g) / fin ** 0.5
+    s_mu, r_mu = torch.ones(fin, device=dev), torch.ones(fout, device=dev)
+    s_rho, r_rho = torch.full((fin,), -3.0, device=dev), torch.full((fout,), -3.0, device=dev)
+    bias = torch.zeros(fout, device=dev)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, s_mu, s_rho, r_mu, r_rho, bias)]
+    rec = {"layer": "Rank1Linear", "batch": batch, "in": fin, "out": fout}
+    with torch.no_grad():
+        rec["fused_fwd_us"] = round(1e3 * time_kernel(lambda: ops.rank1_linear_fwd(x, w, s_mu, s_rho, r_mu, r_rho, bias, seed=1,
+                                                                                   stream_id_s=2, stream_id_r=3,
+                                                                                   workspace=bbb_layers._workspace), 30, 5, flush), 2)
+        rec["reference_eager_fwd_us"] = round(1e3 * time_kernel(lambda: rank1_reference_forward(x, w, s_mu, s_rho, r_mu, r_rho, bias), 30, 5, flush), 2)
+
+    def fb_fused_r1():
+        bbb_layers._Rank1Linear.apply(*leaves, None, None, 2, 3).sum().backward()
+
+    def fb_ref_r1():
+        rank1_reference_forward(*leaves).sum().backward()
+    rec["fused_fwd_bwd_us"] = round(1e3 * time_kernel(fb_fused_r1, 20, 5, flush), 2)
+    rec["reference_eager_fwd_bwd_us"] = round(1e3 * time_kernel(fb_ref_r1, 20, 5, flush), 2)
+    rec["fwd_speedup"] = round(rec["reference_eager_fwd_us"] / rec["fused_fwd_us"], 2)
+    rec["weights_bytes"] = 4 * fin * fout
+    print(json.dumps(rec), flush=True)
