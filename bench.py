@@ -368,6 +368,24 @@ def other_paths(ops, peak_gbs, dev):
             "config": "BBBLinear(768, 768), batch 16, fp32: one tcgen05 kernel (exact 3-way tf32 split, TMEM accumulators, "
                       "tensor-map TMA) vs the reference layer's own eager CUDA branch incl. torch.baddbmm; L2 flushed"}
         log(f"[bench] bbb_linear_fwd (Civil head): fused {1e3 * ms_f:.1f} us vs reference eager {1e3 * ms_r:.1f} us ({ms_r / ms_f:.2f}x)")
+        # Rank1Linear.forward (rank1.py:50-64) at the same head: both samples + x * s + product + * r + bias in one launch
+        smu, srho = torch.ones(768, device=dev), torch.full((768,), -3.0, device=dev)
+
+        def ref_rank1():
+            s1 = smu + torch.empty_like(smu).normal_(0, 1) * torch.nn.functional.softplus(srho)
+            r1 = smu + torch.empty_like(smu).normal_(0, 1) * torch.nn.functional.softplus(srho)
+            o1 = torch.nn.functional.linear(xb * s1, wmu) * r1
+            o1 += bmu.unsqueeze(0)
+            return o1
+
+        ms_f1 = time_kernel(lambda: ops.rank1_linear_fwd(xb, wmu, smu, srho, smu, srho, bmu, seed=1, stream_id_s=2, stream_id_r=3,
+                                                         workspace=bbb_layers._workspace), 30, 5, flush)
+        ms_r1 = time_kernel(ref_rank1, 30, 5, flush)
+        res["rank1_linear_fwd_civil_head"] = {
+            "fused_tcgen05_ms": ms_f1, "reference_eager_cuda_ms": ms_r1, "speedup": ms_r1 / ms_f1,
+            "config": "Rank1Linear(768, 768), batch 16, fp32: one tcgen05 kernel vs the reference layer's expression in eager "
+                      "PyTorch (2 samples, mul, F.linear, mul, add); L2 flushed"}
+        log(f"[bench] rank1_linear_fwd (Civil head): fused {1e3 * ms_f1:.1f} us vs reference eager {1e3 * ms_r1:.1f} us ({ms_r1 / ms_f1:.2f}x)")
         del xb, wmu, wrho
     except Exception as e:  # noqa: BLE001
         res["bbb_linear_fwd_civil_head"] = {"error": str(e)}

@@ -632,6 +632,9 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
 // ---------------------------------------------------------------------------------
 // n > 16: the j-loop of K2 stays rolled (see apply_row)
 __host__ __device__ constexpr bool apply_rolled(int n) { return n > 16; }
+// the staged kernel with a fused optimizer also rolls at n = 16: rolled it fits four tile sets into the 168-register
+// budget of nine warps, and the serial chain of n shared-state optimizer steps needs the extra warps to hide behind
+__host__ __device__ constexpr bool apply_rolled(int n, int opt) { return n > 16 || (n == 16 && opt != kOptNone); }
 __host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : (n <= 16 ? 8 : 4); }
 
 // out_i += K_ij g_j + A_ij x_j for one source row j of a column quad.  n <= 12: fully unrolled over j by the
@@ -641,10 +644,10 @@ __host__ __device__ constexpr int apply_row_chunk(int n) { return n <= 12 ? n : 
 #ifndef BDE_APPLY_J_UNROLL
 #define BDE_APPLY_J_UNROLL 5   // source rows per iteration of the rolled j-loop (n = 20: 4 iterations of 400 FFMA2)
 #endif
-template <int N>
+template <int N, bool ROLLED = apply_rolled(N)>
 __device__ __forceinline__ void apply_row(f32x2 (&acc)[N][2], const V4& g, const V4& x, const float* __restrict__ kt,
                                           const float* __restrict__ at) {
-    if constexpr (N % 4 == 0 && apply_rolled(N)) {
+    if constexpr (N % 4 == 0 && ROLLED) {
 #pragma unroll
         for (int c = 0; c < N / 4; ++c) {
             const float4 k4 = *reinterpret_cast<const float4*>(kt + 4 * c);
@@ -966,7 +969,8 @@ svgd_apply_kernel(const float* X, const float* __restrict__ G, float* out, const
 // (6 consumer warps + producer = 7 warps: still two warps per sub-partition at most, i.e. the 255-register budget
 // that its n(n-1)/2 extra accumulators need).  n > 12: 3 sets for the same reason — with 4 sets (9 warps) one
 // sub-partition holds three warps and the kernel is capped at 168 registers.
-// Measured on B200 (profiles/r01_tilesets_n16_n20.jsonl): n = 16 is fastest fully unrolled on 3 sets, n = 20 rolled
+// Measured on B200 (profiles/r01_tilesets_n16_n20.jsonl): plain K2 at n = 16 is fastest fully unrolled on 3 sets (its fused
+// forms rolled on 4: profiles/r02_k2f_n16_ab.jsonl, -24..-29 %), n = 20 rolled
 // (see apply_row) on 4 sets.  n <= 12: 3 x 256 wins for plain K2 at n >= 8 (+3..5 %) and for the training-step form
 // at n >= 9, where a stage is large enough that the 8-stage ring still keeps ~150 KB in flight; the fused K2f forms
 // and small n stay on 1 x 512 (at n = 5 it is 10-25 % faster).
@@ -976,7 +980,7 @@ __host__ __device__ constexpr bool apply_small_tiles(int n, int opt, bool next) 
 }
 __host__ __device__ constexpr int apply_tile_cols(int n, int opt, bool next) { return apply_small_tiles(n, opt, next) ? 256 : 512; }
 __host__ __device__ constexpr int apply_default_tile_sets(int n, int opt, bool next) {
-    return !apply_small_tiles(n, opt, next) ? 1 : (apply_rolled(n) ? 4 : 3);
+    return !apply_small_tiles(n, opt, next) ? 1 : (apply_rolled(n, opt) ? 4 : 3);
 }
 __host__ __device__ constexpr int apply_stage_bytes(int n, int opt, int tc) {
     return (2 * n + opt_state_rows(opt)) * tc * 4;
@@ -996,8 +1000,8 @@ svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
     constexpr int PN = NEXT ? pair_count(N) : 1;
     constexpr int NP = (N + 3) & ~3;
     constexpr int STAGES = apply_stages(N, OPT, TC);
-    constexpr bool kApplyRolled = apply_rolled(N);
-    constexpr int kApplyJUnroll = BDE_APPLY_J_UNROLL;
+    constexpr bool kApplyRolled = apply_rolled(N, OPT);
+    constexpr int kApplyJUnroll = N == 16 ? 4 : BDE_APPLY_J_UNROLL;
     constexpr int ROWS = 2 * N + opt_state_rows(OPT);
     constexpr int QT = TC / 4;              // threads of one tile set; one column quad each
     constexpr int BW = kTmaBoxCols;         // a stage holds X and G as TC / BW boxes of [N][BW] each, then the state rows [.][TC]
@@ -1100,7 +1104,7 @@ svgd_apply_tma_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_con
             if (active) {
                 if constexpr (kApplyRolled) {
 #pragma unroll(kApplyJUnroll)
-                    for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * BW), lds_v4(sx + j * BW), sKT[j], sAT[j]);
+                    for (int j = 0; j < N; ++j) apply_row<N, true>(acc, lds_v4(sg + j * BW), lds_v4(sx + j * BW), sKT[j], sAT[j]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < N; ++j) apply_row<N>(acc, lds_v4(sg + j * BW), lds_v4(sx + j * BW), sKT[j], sAT[j]);
