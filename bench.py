@@ -576,7 +576,8 @@ def strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel, steps):
             entry["speedup"] = t1.item() / t.item()
             entry["efficiency"] = t1.item() / t.item() / world
         res[f"D{D_total:.0e}".replace("+0", "").replace("+", "")] = entry
-        log(f"[bench] strong D_total={D_total}: {entry}")
+        if rank == 0:
+            log(f"[bench] strong D_total={D_total}: {entry}")
     return res
 
 
