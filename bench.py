@@ -316,6 +316,14 @@ def other_paths(ops, peak_gbs, dev):
     rec("ivon_sample", time_kernel(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=1, stream_id=3, **kw), 20, 3),
         20 * Dp, f"DistilBERT D={D}, Philox noise", size_ref=True)
     rec("ivon_accumulate", time_kernel(lambda: ops.ivon_accumulate(acc, grad, first=False), 20, 3), 12 * Dp, f"D={D}", size_ref=True)
+    # f3: 16 MC draws in one pass (DeepEnsemble.predict on an iVON member): mean / precision read once, delta_sum RMW once
+    S = 16
+    outs = torch.empty(S, Dp, device=dev)
+    ms_b = time_kernel(lambda: ops.ivon_sample_batch(mean, prec, dsum, outs, first=False, seed=1, stream_id=3, **kw), 10, 3)
+    rec("ivon_sample_batch16", ms_b, 4 * (4 + S) * Dp,
+        f"DistilBERT D={D}, {S} draws in one pass (fast kernel: unrolled independent Philox chains; bound by the {S} x D "
+        f"normals, not by HBM); {S} single launches move {20 * S} x D bytes and take {S * res['ivon_sample']['ms']:.3f} ms")
+    del outs
     # the two timing loops above accumulated 23 samples / gradients into dsum and acc: put a
     # mid-training state back so that the update runs on realistic magnitudes (finite everywhere)
     dsum.normal_(0.0, 0.3, generator=g)

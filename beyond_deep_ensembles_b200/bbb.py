@@ -9,7 +9,8 @@ from __future__ import annotations
 
 import torch
 
-from . import util
+from . import dist as bdist
+from . import noise, util
 from .algo import BayesianOptimizer
 
 
@@ -68,7 +69,12 @@ class BBBOptimizer(BayesianOptimizer):
     util.GaussianParameter for the layers that should be treated as Bayesian."""
 
     def __init__(self, params, base_optimizer, prior, dataset_size, mc_samples=1, kl_rescaling=1, components=1,
-                 l2_scale=0):
+                 l2_scale=0, process_group=None):
+        """`process_group` (extension, default None = like the reference): the torch.distributed group whose ranks
+        each hold a COLUMN SLICE of every parameter.  Sampling, the KL / L2 gradients and the base
+        optimizer stay local; the group (i) places every Gaussian tensor's slice in the job-wide Philox stream, so
+        the ranks draw disjoint noise, and (ii) sums the prior term's VALUE (one scalar all-reduce; only the logged
+        loss needs it — each rank differentiates its own slice)."""
         defaults = {"prior": prior, "l2_scale": l2_scale}
         super().__init__(params, defaults)
         self.state["__base_optimizer"] = base_optimizer
@@ -76,6 +82,29 @@ class BBBOptimizer(BayesianOptimizer):
         self.kl_rescaling = kl_rescaling
         self.components = components
         self.dataset_size = dataset_size
+        self._group = bdist.SINGLE if process_group is None else process_group
+        if bdist.world(self._group) > 1:
+            self._place_gaussian_slices()
+
+    def _place_gaussian_slices(self):
+        """Collective (one all_gather_object): per Gaussian tensor, the exclusive prefix over the ranks of the
+        slice lengths (rounded up to whole Philox quads) becomes the owner's `column_offset`."""
+        import torch.distributed as dist
+        owners = []
+        for param in self._params():
+            owner = getattr(getattr(param, "get_parameter_kl", None), "__self__", None)
+            if owner is not None and hasattr(owner, "column_offset") and getattr(owner, "mean", None) is param:
+                owners.append(owner)
+        world, rank = bdist.world(self._group), dist.get_rank(self._group)
+        rows = [None] * world
+        mine = ([(o.mean.numel() + 3) // 4 * 4 for o in owners], noise.seed(), noise.stream_position())
+        dist.all_gather_object(rows, mine, group=self._group)
+        if any(len(r[0]) != len(owners) for r in rows):
+            raise ValueError("the ranks of a D-sharded BBB optimizer hold different numbers of Gaussian tensors")
+        noise.restore_stream_position(max(r[2] for r in rows))
+        for k, owner in enumerate(owners):
+            owner.column_offset = sum(r[0][k] for r in rows[:rank])
+            owner.noise_seed = int(rows[0][1])
 
     def step(self, forward_closure, backward_closure, grad_scaler=None):
         base = self.state["__base_optimizer"]
@@ -118,6 +147,9 @@ class BBBOptimizer(BayesianOptimizer):
             deterministic = []
         if deterministic:
             total_kl_loss += util.prior_terms([], None, deterministic)
+
+        # D-sharded: the other ranks' share of the prior term, as a value (no gradient crosses ranks)
+        total_kl_loss = bdist.allreduce_scalar_value(total_kl_loss, self._group)
 
         pi = self.kl_rescaling / self.dataset_size
         # the KL is not divided by the MC sample count: it was collected once (bbb.py:79-80)

@@ -126,6 +126,9 @@ class _Rank1Linear(torch.autograd.Function):
 
 def rank1_forward_applies(layer, input: torch.Tensor) -> bool:
     w = layer.layer.weight
+    c = layer.component_counter
+    if getattr(layer.s[c], "column_offset", 0) or getattr(layer.r[c], "column_offset", 0):
+        return False   # slices of a D-sharded job (BBBOptimizer(process_group=...)): the samples carry stream offsets
     return (input.is_cuda and input.dim() == 2 and input.dtype == torch.float32 and layer.in_features % 4 == 0
             and w.dtype == torch.float32 and w.is_contiguous() and layer.layer.bias is None)
 

@@ -441,15 +441,23 @@ inline size_t grid_reduce_ws_bytes(int max_ctas, int count) { return kWsHeaderBy
 // with q = global element index / 4; key = 64-bit seed.  One call -> 4 normals for
 // elements 4q .. 4q+3.
 // ----------------------------------------------------------------------------
+// 32 x 32 -> 64-bit product as ONE IMAD.WIDE.U32 with both halves used.  (Written as a C++ 64-bit multiply, ptxas keeps a
+// dead "+ 0" on the high word of every product — the zero-extended operand's upper half — one extra IADD3 per product,
+// 20 per Philox call; seen in SASS.)
+__device__ __forceinline__ void mul_wide_u32(unsigned int a, unsigned int b, unsigned int& hi, unsigned int& lo) {
+    unsigned long long p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(a), "r"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(p));
+}
+
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         // one IMAD.WIDE.U32 per product (hi and lo halves together); the key schedule is uniform
-        const unsigned long long p0 = static_cast<unsigned long long>(M0) * ctr.x;
-        const unsigned long long p1 = static_cast<unsigned long long>(M1) * ctr.z;
-        const unsigned int hi0 = static_cast<unsigned int>(p0 >> 32), lo0 = static_cast<unsigned int>(p0);
-        const unsigned int hi1 = static_cast<unsigned int>(p1 >> 32), lo1 = static_cast<unsigned int>(p1);
+        unsigned int hi0, lo0, hi1, lo1;
+        mul_wide_u32(M0, ctr.x, hi0, lo0);
+        mul_wide_u32(M1, ctr.z, hi1, lo1);
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
         key.x += W0;
         key.y += W1;
@@ -477,10 +485,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys& k) {
     constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const unsigned long long p0 = static_cast<unsigned long long>(M0) * ctr.x;
-        const unsigned long long p1 = static_cast<unsigned long long>(M1) * ctr.z;
-        const unsigned int hi0 = static_cast<unsigned int>(p0 >> 32), lo0 = static_cast<unsigned int>(p0);
-        const unsigned int hi1 = static_cast<unsigned int>(p1 >> 32), lo1 = static_cast<unsigned int>(p1);
+        unsigned int hi0, lo0, hi1, lo1;
+        mul_wide_u32(M0, ctr.x, hi0, lo0);
+        mul_wide_u32(M1, ctr.z, hi1, lo1);
         ctr = make_uint4(hi1 ^ ctr.y ^ k.rk[r].x, lo1, hi0 ^ ctr.w ^ k.rk[r].y, lo0);
     }
     return ctr;
@@ -496,6 +503,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp
     return r;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+    // MUFU.LG2 alone.  __log2f() wraps it in a denormal-input path (FSETP, predicated FMUL by 2^24, predicated FADD -24: three
+    // issue slots per call that never execute for our inputs, u >= 2^-25); for normal inputs the result is the same bits.
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.RSQ, ~1 ulp
@@ -508,7 +522,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 __device__ __forceinline__ void box_muller(unsigned int r0, unsigned int r1, float& z0, float& z1) {
     const float u = u01_open(r0);
     const float ang = fmaf(static_cast<float>(r1 >> 8), 3.7450702829239286e-07f, -3.14159265358979323846f);
-    const float rad = sqrt_approx(fmaxf(-1.3862943611198906f * __log2f(u), 0.0f));  // sqrt(-2 ln u)
+    const float rad = sqrt_approx(fmaxf(-1.3862943611198906f * lg2_approx(u), 0.0f));  // sqrt(-2 ln u)
     z0 = rad * __cosf(ang);
     z1 = rad * __sinf(ang);
 }

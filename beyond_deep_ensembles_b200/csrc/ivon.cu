@@ -95,6 +95,54 @@ ivon_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
     }
 }
 
+// Fast path of K5 batched (production form: Philox noise, 16-byte-aligned pointers, whole quads, exactly SB draws per
+// pass — the launcher splits S into passes of 16 / 8 / 4 / 2 and sends a last odd draw, a ragged tail, injected noise and
+// the deterministic mode to the general kernel above).  Same arithmetic bit for bit; what is gone is the rolled draw loop
+// with its per-draw predicates, guarded accesses and 64-bit address arithmetic: the SB Philox chains of a quad are
+// independent and fully unrolled (instruction-level parallelism instead of one serial 10-round chain at a time), the
+// round keys sit in uniform registers, mean / delta_sum move as packed pairs (FADD2).
+template <int SB, bool FIRST>
+__global__ void __launch_bounds__(kEwThreads)
+ivon_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __restrict__ prec, float* __restrict__ delta_sum,
+                              float* __restrict__ theta, int64_t ld_out, int64_t nquads, float n_eff, uint64_t seed,
+                              uint64_t stream_id, uint64_t stream_stride, int64_t quad0) {
+    const PhiloxKeys pk = philox_round_keys(seed);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+        const int64_t b = q << 2;
+        const V4 m = ldg_stream_v4(mean + b);
+        const float4 p = ldg_stream_f4(prec + b);
+        auto f = [&](float pv) { return rsqrt_approx(__fmul_rn(n_eff, fmaxf(pv, 1e-4f))); };   // ivon_delta's factor
+        const float c0 = f(p.x), c1 = f(p.y), c2 = f(p.z), c3 = f(p.w);
+        V4 ds;
+        if constexpr (FIRST) {
+            ds.lo = ds.hi = 0ull;
+        } else {
+            ds = ldg_stream_v4(delta_sum + b);
+        }
+        float* out = theta + b;
+        const uint64_t quad = static_cast<uint64_t>(quad0 + q);
+#pragma unroll
+        for (int sidx = 0; sidx < SB; ++sidx) {
+            const float4 z = philox_normal4(pk, stream_id + sidx * stream_stride, quad);
+            V4 dl, th;
+            dl.lo = pack2(__fmul_rn(c0, z.x), __fmul_rn(c1, z.y));
+            dl.hi = pack2(__fmul_rn(c2, z.z), __fmul_rn(c3, z.w));
+            th.lo = add2_rn(m.lo, dl.lo);
+            th.hi = add2_rn(m.hi, dl.hi);
+            stg_stream_v4(out, th);
+            out += ld_out;
+            if (FIRST && sidx == 0) {
+                ds = dl;
+            } else {
+                ds.lo = add2_rn(ds.lo, dl.lo);
+                ds.hi = add2_rn(ds.hi, dl.hi);
+            }
+        }
+        stg_stream_v4(delta_sum + b, ds);
+    }
+}
+
 // K5, TMA-staged (ew_tma.cuh): inputs mean, prec, [delta_sum unless FIRST], [eps if EPS]
 template <bool FIRST, bool EPS>
 struct IvonSampleOp {
@@ -280,6 +328,45 @@ extern "C" int bde_ivon_sample_batch(const float* mean, const float* prec, float
                      (!eps || (aligned16(eps) && ld_eps % 4 == 0));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float nf = static_cast<float>(n_eff);
+    const int64_t nq = D >> 2;
+    if (vec && !eps && !deterministic && S >= 2 && nq > 0 && tuning().swag_batch != 1) {
+        // production form: passes of 16 / 8 / 4 / 2 draws through the fast kernel (delta_sum is carried from pass to pass in
+        // draw order, so the running sum is the one S single calls produce) ...
+        int s0 = 0;
+        while (S - s0 >= 2) {
+            const int left = S - s0;
+            const int sb = left >= 16 ? 16 : (left >= 8 ? 8 : (left >= 4 ? 4 : 2));
+            const bool f0 = first && s0 == 0;
+            float* out = theta + s0 * ld_out;
+            const uint64_t sid = stream_id + static_cast<uint64_t>(s0) * stream_stride;
+            int rf = BDE_OK;
+#define BDE_IVON_FAST(SB_)                                                                                                       \
+    rf = f0 ? launch_ew(ivon_sample_batch_fast_kernel<SB_, true>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, nf, seed, sid, \
+                        stream_stride, elem0 >> 2)                                                                               \
+            : launch_ew(ivon_sample_batch_fast_kernel<SB_, false>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, nf, seed, sid, \
+                        stream_stride, elem0 >> 2)
+            switch (sb) {
+                case 2: BDE_IVON_FAST(2); break;
+                case 4: BDE_IVON_FAST(4); break;
+                case 8: BDE_IVON_FAST(8); break;
+                default: BDE_IVON_FAST(16); break;
+            }
+#undef BDE_IVON_FAST
+            if (rf != BDE_OK) return rf;
+            s0 += sb;
+        }
+        if (s0 < S) {   // ... a last odd draw through the general kernel (over the same quads) ...
+            const int rl = launch_ew(ivon_sample_batch_kernel<true>, nq * 4, st, mean, prec, delta_sum, theta + s0 * ld_out, ld_out,
+                                     nq * 4, S - s0, nf, 0, 0, eps, ld_eps, seed,
+                                     stream_id + static_cast<uint64_t>(s0) * stream_stride, stream_stride, elem0 >> 2);
+            if (rl != BDE_OK) return rl;
+        }
+        const int64_t d4 = nq << 2;
+        if (d4 < D)     // ... and the general kernel for all S draws of the last D % 4 elements
+            return launch_ew(ivon_sample_batch_kernel<false>, D - d4, st, mean + d4, prec + d4, delta_sum + d4, theta + d4, ld_out,
+                             D - d4, S, nf, first, deterministic, eps, ld_eps, seed, stream_id, stream_stride, (elem0 + d4) >> 2);
+        return BDE_OK;
+    }
     if (vec)
         return launch_ew(ivon_sample_batch_kernel<true>, D, st, mean, prec, delta_sum, theta, ld_out, D, S, nf, first,
                          deterministic, eps, ld_eps, seed, stream_id, stream_stride, elem0 >> 2);

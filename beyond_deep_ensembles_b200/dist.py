@@ -48,6 +48,71 @@ def allreduce_dist(sc: "ops.SvgdScratch", group=None) -> None:
 
 
 # --------------------------------------------------------------------------------------
+# column shards of the elementwise family (SWAG, iVON, Gaussian parameters): no data-path collective
+# --------------------------------------------------------------------------------------
+class ColumnShard:
+    """Where this rank's slice of a flat state vector sits in the job-wide vector (second bullet).
+
+    The elementwise kernels need no exchange; what makes a D-sharded posterior ONE posterior is the noise: the
+    per-element Philox counter is `elem0` + local index (so the ranks draw disjoint parts of the same stream —
+    with elem0 = 0 everywhere every rank would replay the same normals on its slice), and everything drawn per
+    VECTOR rather than per element (SWAG's K low-rank coefficients) comes from the same (seed, stream id) on every
+    rank.  `seed` is rank 0's; the stream counter is advanced to the furthest rank's at construction."""
+
+    __slots__ = ("group", "world", "rank", "elem0", "local", "total", "seed")
+
+    def __init__(self, group, world_size, rank, elem0, local, total, seed):
+        self.group, self.world, self.rank = group, world_size, rank
+        self.elem0, self.local, self.total, self.seed = elem0, local, total, seed
+
+    def __repr__(self):
+        return f"ColumnShard(rank {self.rank}/{self.world}, columns [{self.elem0}, {self.elem0 + self.local}) of {self.total})"
+
+
+def column_shard(local_size: int, group=None) -> ColumnShard:
+    """Collective over `group` (one all_gather_object): exclusive prefix sum of the ranks' arena lengths.  Arena
+    lengths are multiples of layout.ALIGN, so every elem0 is a multiple of 4 as the kernels require.
+    group=None / SINGLE: this rank holds everything (elem0 = 0, seed follows torch)."""
+    from . import noise
+    if group is None:
+        group = SINGLE
+    w = world(group)
+    if w <= 1:
+        return ColumnShard(group, 1, 0, 0, int(local_size), int(local_size), None)
+    rank = dist.get_rank(group)
+    rows = [None] * w
+    dist.all_gather_object(rows, (int(local_size), noise.seed(), noise.stream_position()), group=group)
+    sizes = [r[0] for r in rows]
+    if any(s % 4 for s in sizes):
+        raise ValueError("column shards must be multiples of 4 elements long (flat arenas are)")
+    # per-vector draws must agree: one key for the whole group, and no rank re-uses a stream id another has spent
+    noise.restore_stream_position(max(r[2] for r in rows))
+    return ColumnShard(group, w, rank, sum(sizes[:rank]), sizes[rank], sum(sizes), int(rows[0][1]))
+
+
+def check_noise_in_step(shard: ColumnShard) -> None:
+    """Collective debugging aid: raise unless every rank of the shard's group stands at the same Philox stream
+    position (they do when all ranks make the same sampling calls — the SPMD contract of a D-sharded job)."""
+    from . import noise
+    if shard.world <= 1:
+        return
+    rows = [None] * shard.world
+    dist.all_gather_object(rows, noise.stream_position(), group=shard.group)
+    if len(set(rows)) != 1:
+        raise RuntimeError(f"ranks of a D-sharded posterior have drawn different numbers of noise streams: {rows}")
+
+
+def allreduce_scalar_value(value: torch.Tensor, group) -> torch.Tensor:
+    """Sum of a scalar over the ranks holding the other column slices, as a VALUE: the gradient flows to this
+    rank's term only (the other ranks differentiate theirs).  Used for the logged KL / L2 prior term of BBB."""
+    if world(group) <= 1:
+        return value
+    total = value.detach().clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return value + (total - value.detach())
+
+
+# --------------------------------------------------------------------------------------
 # in-kernel exchange over peer memory
 # --------------------------------------------------------------------------------------
 class PeerSet:

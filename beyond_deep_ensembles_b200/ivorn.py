@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 from torch.amp.grad_scaler import OptState
 
+from . import dist as bdist
 from . import noise, ops
 from .algo import BayesianOptimizer
 from .layout import ParamLayout
@@ -21,8 +22,13 @@ _ROWS = ("mean", "momentum", "precision", "delta", "acc_grad", "theta")
 
 
 class iVONOptimizer(BayesianOptimizer):
+    """`process_group` (extension, default None = this rank holds every parameter, like the reference): the
+    torch.distributed group whose ranks each hold a COLUMN SLICE of every parameter group's state.
+    Sampling, accumulation and the update stay local; the group only places each rank's slice in the job-wide
+    Philox stream (per-element counter = global column index), so the draw does not depend on the rank count."""
+
     def __init__(self, params, lr, prior_prec, dataset_size, betas=(0.9, 0.999), damping=0.0, tempering=1.0,
-                 augmentation=1.0, mc_samples=5, deterministic=False):
+                 augmentation=1.0, mc_samples=5, deterministic=False, process_group=None):
         defaults = {
             "lr": lr,
             "betas": betas,
@@ -58,7 +64,9 @@ class iVONOptimizer(BayesianOptimizer):
                 rows["theta"].copy_(rows["mean"])
                 for k, param in enumerate(plist):
                     param.data = views["theta"][k]
-            self._arenas.append({"layout": L, "rows": rows, "views": views, "n_samples": 0})
+            # collective over the group (if any), once per parameter group, in group order on every rank
+            shard = bdist.column_shard(L.size, process_group)
+            self._arenas.append({"layout": L, "rows": rows, "views": views, "n_samples": 0, "shard": shard})
 
         assert mc_samples > 0
         self.mc_samples = mc_samples
@@ -157,14 +165,19 @@ class iVONOptimizer(BayesianOptimizer):
                 if eps is not None:
                     eps = L.from_logical(eps)
             ops.ivon_sample(r["mean"], r["precision"], r["delta"], r["theta"], n_eff=group["N"] * group["augmentation"],
-                            first=first, deterministic=bool(group["deterministic"]), eps=eps, seed=noise.seed(),
-                            stream_id=noise.next_stream_id())
+                            first=first, deterministic=bool(group["deterministic"]), eps=eps,
+                            seed=self._noise_seed(ar), stream_id=noise.next_stream_id(), elem0=ar["shard"].elem0)
             ar["n_samples"] += 1
             plist = group["params"]
             if first or plist[0].data_ptr() != v["theta"][0].data_ptr():
                 for k, param in enumerate(plist):
                     param.data = v["theta"][k]
                     self.state[param]["delta"] = v["delta"][k]
+
+    @staticmethod
+    def _noise_seed(ar) -> int:
+        """The Philox key: torch's seed, or — D-sharded — the one the group agreed on (rank 0's)."""
+        return noise.seed() if ar["shard"].seed is None else ar["shard"].seed
 
     # ---- batched sampling (SURVEY §8 f3) ----
     #: upper bound of the presample buffers in bytes; larger requests are drawn in several batches
@@ -210,8 +223,8 @@ class iVONOptimizer(BayesianOptimizer):
                 raise ValueError("a noise injector must supply either every draw of a presampled batch or none")
             ops.ivon_sample_batch(r["mean"], r["precision"], r["delta"], ar["pre_buf"][:rows],
                                   n_eff=group["N"] * group["augmentation"], first=ar["n_samples"] == 0,
-                                  deterministic=bool(group["deterministic"]), eps=e, seed=noise.seed(),
-                                  stream_id=first_id + g, stream_stride=groups)
+                                  deterministic=bool(group["deterministic"]), eps=e, seed=self._noise_seed(ar),
+                                  stream_id=first_id + g, stream_stride=groups, elem0=ar["shard"].elem0)
             ar["n_samples"] += rows
         self._pre_next, self._pre_ready = 0, rows
         self._pre_pending -= rows

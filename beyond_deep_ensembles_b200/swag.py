@@ -16,13 +16,20 @@ import math
 
 import torch
 
+from . import dist as bdist
 from . import noise, ops
 from .algo import BayesianOptimizer
 from .layout import ParamLayout
 
 
 class SwagOptimizer(BayesianOptimizer):
-    def __init__(self, params, base_optimizer, update_interval, start_epoch=0, deviation_samples=30):
+    """`process_group` (extension, default None = this rank holds every parameter, like the reference): the
+    torch.distributed group whose ranks each hold a COLUMN SLICE of the weights and of every moment (SURVEY.md
+    §8e).  No kernel on this path exchanges data; the group only fixes the noise: the K low-rank coefficients are
+    identical on all ranks, the per-weight normals are the ranks' disjoint parts of one Philox stream."""
+
+    def __init__(self, params, base_optimizer, update_interval, start_epoch=0, deviation_samples=30,
+                 process_group=None):
         super().__init__(params, {})
 
         self.start_epoch = start_epoch
@@ -34,6 +41,7 @@ class SwagOptimizer(BayesianOptimizer):
         device = plist[0].device
         self._layout = ParamLayout(plist)
         L = self._layout
+        self._shard = bdist.column_shard(L.size, process_group)   # collective over the group (if any)
         self._theta = L.new_arena(1, device)[0]
         self._sample = L.new_arena(1, device)[0]
         self._mean = L.new_arena(1, device)[0]
@@ -101,9 +109,14 @@ class SwagOptimizer(BayesianOptimizer):
         if eps_d is not None:
             eps_d = self._layout.from_logical(eps_d)
         ops.swag_sample(self._mean, self._sq, self._dev, self.state["__updates"] % K, self._sample, eps_k=eps_k,
-                        eps_d=eps_d, seed=noise.seed(), stream_id=noise.next_stream_id())
+                        eps_d=eps_d, seed=self._noise_seed(), stream_id=noise.next_stream_id(),
+                        elem0=self._shard.elem0)
         for param, sview in zip(self._params(), self._sviews):
             param.data = sview
+
+    def _noise_seed(self) -> int:
+        """The Philox key: torch's seed, or — D-sharded — the one the group agreed on (rank 0's)."""
+        return noise.seed() if self._shard.seed is None else self._shard.seed
 
     # ---- batched sampling (SURVEY §8 f3) ----
     #: upper bound of the presample buffer in bytes; larger requests are drawn in several batches
@@ -146,7 +159,8 @@ class SwagOptimizer(BayesianOptimizer):
         if (ek is None and any(e is not None for e in eps_k)) or (ed is None and any(e is not None for e in eps_d)):
             raise ValueError("a noise injector must supply either every draw of a presampled batch or none")
         ops.swag_sample_batch(self._mean, self._sq, self._dev, self.state["__updates"] % K, self._pre_buf[:rows],
-                              eps_k=ek, eps_d=ed, seed=noise.seed(), stream_id=noise.reserve_stream_ids(rows))
+                              eps_k=ek, eps_d=ed, seed=self._noise_seed(), stream_id=noise.reserve_stream_ids(rows),
+                              elem0=self._shard.elem0)
         self._pre_next, self._pre_ready = 0, rows
         self._pre_pending -= rows
 

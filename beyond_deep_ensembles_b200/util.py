@@ -19,14 +19,14 @@ class _GaussSample(torch.autograd.Function):
     """K8: w = mu + eps * softplus(rho)."""
 
     @staticmethod
-    def forward(ctx, mean, rho):
+    def forward(ctx, mean, rho, elem0=0, seed=None):
         mu_c, rho_c = mean.detach().contiguous(), rho.detach().contiguous()
         w = torch.empty_like(mu_c)
         eps = noise.draw("gauss", mu_c.numel(), mu_c.device)
-        seed, sid = noise.seed(), noise.next_stream_id()
-        ops.gauss_sample_fwd(mu_c, rho_c, w, eps=eps, seed=seed, stream_id=sid)
+        seed, sid = (noise.seed() if seed is None else seed), noise.next_stream_id()
+        ops.gauss_sample_fwd(mu_c, rho_c, w, eps=eps, seed=seed, stream_id=sid, elem0=elem0)
         ctx.save_for_backward(rho_c, eps if eps is not None else torch.empty(0, device=mu_c.device))
-        ctx.philox = (seed, sid)
+        ctx.philox = (seed, sid, elem0)
         ctx.injected = eps is not None
         return w.view_as(mean)
 
@@ -35,9 +35,10 @@ class _GaussSample(torch.autograd.Function):
         rho_c, eps = ctx.saved_tensors
         g = grad_w.contiguous()
         grad_rho = torch.empty_like(rho_c)
-        seed, sid = ctx.philox
-        ops.gauss_sample_bwd(g, rho_c, grad_rho, eps=eps if ctx.injected else None, seed=seed, stream_id=sid)
-        return grad_w, grad_rho.view_as(grad_w)
+        seed, sid, elem0 = ctx.philox
+        ops.gauss_sample_bwd(g, rho_c, grad_rho, eps=eps if ctx.injected else None, seed=seed, stream_id=sid,
+                             elem0=elem0)
+        return grad_w, grad_rho.view_as(grad_w), None, None
 
 
 class _KLGauss(torch.autograd.Function):
@@ -184,8 +185,10 @@ def l2_penalty(param: torch.Tensor, l2_scale: float) -> torch.Tensor:
     return _L2.apply(param, float(l2_scale))
 
 
-def gaussian_sample(mean: torch.Tensor, rho: torch.Tensor) -> torch.Tensor:
-    return _GaussSample.apply(mean, rho)
+def gaussian_sample(mean: torch.Tensor, rho: torch.Tensor, elem0: int = 0, seed=None) -> torch.Tensor:
+    """elem0 / seed: position of this (slice of a) tensor in a D-sharded job's Philox stream and the group's key
+    (dist.ColumnShard); the defaults are the single-rank case."""
+    return _GaussSample.apply(mean, rho, int(elem0), seed)
 
 
 def gaussian_kl(mean: torch.Tensor, rho: torch.Tensor, prior) -> torch.Tensor:
@@ -213,6 +216,10 @@ class GaussianParameter(nn.Module):
     """
 
     _bde_fused_kl = True  # kl_divergence is util.gaussian_kl: BBBOptimizer may batch it with the other tensors
+    #: D-sharded jobs (BBBOptimizer(process_group=...)): where this rank's slice of the tensor sits in the job-wide
+    #: tensor, and the Philox key the group agreed on.  Class defaults = not sharded.
+    column_offset = 0
+    noise_seed = None
 
     def __init__(self, size, device=None):
         super().__init__()
@@ -230,7 +237,7 @@ class GaussianParameter(nn.Module):
         torch.nn.init.constant_(self.rho, -3)
 
     def sample(self) -> torch.Tensor:
-        return gaussian_sample(self.mean, self.rho)
+        return gaussian_sample(self.mean, self.rho, self.column_offset, self.noise_seed)
 
     def kl_divergence(self, prior):
         return gaussian_kl(self.mean, self.rho, prior)

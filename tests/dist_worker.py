@@ -172,3 +172,29 @@ def run(rank: int, world: int, port: int, n: int, D: int, out_path: str, backend
     dist.barrier()
     bdist.shutdown_peer_exchange()
     dist.destroy_process_group()
+
+
+def run_elementwise(rank: int, world: int, port: int, out_path: str, backend: str = "gloo"):
+    """D-sharded SWAG / iVON / BBB host classes (process_group=...): every rank runs tests/sharded_script.py on its
+    column slice; the test compares the concatenated slices with the unsharded run."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(1)
+        import fake_abi
+        fake_abi.install(_Patch())
+    import sharded_script
+    from beyond_deep_ensembles_b200 import dist as bdist
+    res = sharded_script.run(dev, world, rank, dist.group.WORLD)
+    # the SPMD contract held: every rank stands at the same Philox stream position
+    bdist.check_noise_in_step(bdist.column_shard(64, dist.group.WORLD))
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    torch.save(res, f"{out_path}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()

@@ -756,12 +756,14 @@ def test_ivon_kernels_vs_oracle(ops, ew_variant, D):
     assert torch.equal(d_theta, d_mean) and d_dsum.eq(0).all()
 
 
-@pytest.mark.parametrize("S,first,det", [(1, True, False), (3, True, False), (4, False, False), (7, False, False), (3, True, True)])
+@pytest.mark.parametrize("S,first,det", [(1, True, False), (3, True, False), (4, False, False), (7, False, False), (3, True, True),
+                                         (16, False, False), (19, True, False), (31, False, False)])
 @pytest.mark.parametrize("D,mis", [(100_003, 0), (4099, 0), (777, 1), (3_000_000, 0)])
 def test_ivon_sample_batch_equals_single_draws(ops, S, first, det, D, mis):
     """bde_ivon_sample_batch: draw s == bde_ivon_sample with stream_id + s * stride, and delta_sum ends as after S
     single calls, bit for bit — Philox and injected noise, first / continuing accumulation, deterministic groups,
-    ragged D, unaligned views, D large enough for the TMA-staged single-draw kernel."""
+    ragged D, unaligned views, D large enough for the TMA-staged single-draw kernel.  Aligned Philox cases run the fast
+    kernel in passes of 16 / 8 / 4 / 2 draws (+ the general kernel for an odd last draw and the D % 4 tail)."""
     g = torch.Generator().manual_seed(S * 13 + D)
     def vec(scale=1.0, shift=0.0):
         return (torch.randn(D + 8, generator=g) * scale + shift).cuda()[mis:mis + D]
