@@ -45,7 +45,9 @@ struct Tuning {
     int pairdist_variant = 0;  // same for K1; 3 = centred-Gram kernel (n = 16 / 20), 4 = Gram + forced redo (tests)
     int ew_variant = 0;        // same for the elementwise family (ew_tma.cuh)
     int apply_tile_sets = 0;   // staged K2: alternative consumer geometry (0 = default; see launch_apply_opt)
-    int swag_batch = 0;        // draws per pass of the batched SWAG sampler (0 = default 16; 2, 4, 8, 16)
+    int swag_batch = 0;        // draws per pass of the batched SWAG sampler (0 = default 16; 2, 4, 8, 16; 1 = general kernels, SWAG and iVON)
+    int batch_splits = 0;      // fast batched SWAG sampler: partner CTAs per pass (0 = default 1; 2, 4)
+    int batch_prefetch = 0;    // fast batched samplers: L2 prefetch distance in grid-stride iterations (0 = default 1; 9 = off)
     int gram_pairing = 0;      // centred-Gram K1: warp -> pair-group mapping (svgd_gram.cuh:gram_warp_role)
     int gram_fold = 0;         // Gram K1 register budget: 0 auto, 1 producer warpgroup + setmaxnreg (SHIFT), 2 plain ninth warp
     int gram_l2_promotion = 0; // tensor-map L2 promotion of the Gram kernel's tile loads: 0 none, 1 64 B, 2 128 B, 3 256 B
@@ -493,9 +495,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys& k) {
     return ctr;
 }
 
-__device__ __forceinline__ float u01_open(unsigned int r) {
-    // (r>>8) * 2^-24 + 2^-25  in (0, 1]
-    return fmaf(static_cast<float>(r >> 8), 5.9604644775390625e-08f, 2.98023223876953125e-08f);
+// 23 random bits -> the float 2^23 + x, x in [0, 2^23): ONE logic op, exact.  (An int -> float conversion is an XU-pipe
+// instruction like the MUFU transcendentals — quarter rate; four of them per normal quad made the XU pipe the co-limiter of
+// the batched samplers: ncu, math-pipe-throttle / dispatch stalls.)
+__device__ __forceinline__ float bits23_to_float(unsigned int r) {
+    unsigned int d;   // (r & mask) | magic as one LOP3 (from C, ptxas emits an AND and an OR: two immediates do not fit one LOP3)
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(r), "r"(0x007FFFFFu), "r"(0x4B000000u));
+    return __uint_as_float(d);
 }
 
 __device__ __forceinline__ float sqrt_approx(float x) {
@@ -503,6 +509,9 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // MUFU.SQRT, ~1 ulp
     return r;
 }
+// Pull the 128-byte line of `p` into L2 without occupying a register or a scoreboard slot (no data returns to the SM).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float lg2_approx(float x) {
     // MUFU.LG2 alone.  __log2f() wraps it in a denormal-input path (FSETP, predicated FMUL by 2^24, predicated FADD -24: three
     // issue slots per call that never execute for our inputs, u >= 2^-25); for normal inputs the result is the same bits.
@@ -516,12 +525,15 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return r;
 }
 
-// Box-Muller on the SFU: radius from MUFU.LG2 + MUFU.SQRT, angle uniform on [-pi, pi) where
-// MUFU.SIN/COS are accurate to 2^-21.4 absolute.  (Noise quality, not reference parity: parity
-// tests inject the reference's own noise.)
+// Box-Muller on the SFU: radius from MUFU.LG2 + MUFU.SQRT, angle uniform on [-pi, pi) where MUFU.SIN/COS are accurate to
+// 2^-21.4 absolute.  Both uniforms come from the low 23 bits of a Philox word through bits23_to_float and one FMA each:
+//   u   = (2 x0 + 1) 2^-24            in (0, 1), exact, symmetric, never 0 or 1   (|z| <= 5.77)
+//   ang = (2^23 + x1) 2 pi 2^-23 - 3 pi   in [-pi, pi)
+// (Noise quality, not reference parity: parity tests inject the reference's own noise.  oracle/bde_oracle.py:philox_normal
+// restates this function.)
 __device__ __forceinline__ void box_muller(unsigned int r0, unsigned int r1, float& z0, float& z1) {
-    const float u = u01_open(r0);
-    const float ang = fmaf(static_cast<float>(r1 >> 8), 3.7450702829239286e-07f, -3.14159265358979323846f);
+    const float u = fmaf(bits23_to_float(r0), 1.1920928955078125e-07f, 5.9604644775390625e-08f - 1.0f);
+    const float ang = fmaf(bits23_to_float(r1), 7.4901405658478572e-07f, -9.42477796076937972f);
     const float rad = sqrt_approx(fmaxf(-1.3862943611198906f * lg2_approx(u), 0.0f));  // sqrt(-2 ln u)
     z0 = rad * __cosf(ang);
     z1 = rad * __sinf(ang);

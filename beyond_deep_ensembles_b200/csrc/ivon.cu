@@ -95,21 +95,29 @@ ivon_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
     }
 }
 
-// Fast path of K5 batched (production form: Philox noise, 16-byte-aligned pointers, whole quads, exactly SB draws per
-// pass — the launcher splits S into passes of 16 / 8 / 4 / 2 and sends a last odd draw, a ragged tail, injected noise and
-// the deterministic mode to the general kernel above).  Same arithmetic bit for bit; what is gone is the rolled draw loop
-// with its per-draw predicates, guarded accesses and 64-bit address arithmetic: the SB Philox chains of a quad are
-// independent and fully unrolled (instruction-level parallelism instead of one serial 10-round chain at a time), the
-// round keys sit in uniform registers, mean / delta_sum move as packed pairs (FADD2).
+// Fast path of K5 batched (production form: Philox noise, 16-byte-aligned pointers, whole quads, up to SB draws per pass —
+// the launcher splits S into passes of at most 16 and sends a ragged tail, injected noise and the deterministic mode to
+// the general kernel above).  Same arithmetic bit for bit; what is gone is the rolled draw loop with its per-draw
+// predicates, guarded accesses and 64-bit address arithmetic: the Philox chains of a quad's draws are independent and
+// fully unrolled (instruction-level parallelism instead of one serial 10-round chain at a time), the round keys sit in
+// uniform registers, mean / delta_sum move as packed pairs (FADD2), and the next quad's lines are requested into L2 while
+// this quad's normals are computed.  `count` <= SB draws are produced (uniform early exit of the unrolled loop).
 template <int SB, bool FIRST>
 __global__ void __launch_bounds__(kEwThreads)
 ivon_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __restrict__ prec, float* __restrict__ delta_sum,
-                              float* __restrict__ theta, int64_t ld_out, int64_t nquads, float n_eff, uint64_t seed,
-                              uint64_t stream_id, uint64_t stream_stride, int64_t quad0) {
+                              float* __restrict__ theta, int64_t ld_out, int64_t nquads, int count, float n_eff, uint64_t seed,
+                              uint64_t stream_id, uint64_t stream_stride, int64_t quad0, int pf_dist) {
     const PhiloxKeys pk = philox_round_keys(seed);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += stride) {
         const int64_t b = q << 2;
+        const int64_t qn = q + pf_dist * stride;
+        if (pf_dist && qn < nquads) {
+            const int64_t bn = qn << 2;
+            prefetch_l2(mean + bn);
+            prefetch_l2(prec + bn);
+            if (!FIRST) prefetch_l2(delta_sum + bn);
+        }
         const V4 m = ldg_stream_v4(mean + b);
         const float4 p = ldg_stream_f4(prec + b);
         auto f = [&](float pv) { return rsqrt_approx(__fmul_rn(n_eff, fmaxf(pv, 1e-4f))); };   // ivon_delta's factor
@@ -124,6 +132,7 @@ ivon_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __res
         const uint64_t quad = static_cast<uint64_t>(quad0 + q);
 #pragma unroll
         for (int sidx = 0; sidx < SB; ++sidx) {
+            if (sidx >= SB / 2 && sidx >= count) break;   // passes are sized so that count > SB / 2 (or SB == 2)
             const float4 z = philox_normal4(pk, stream_id + sidx * stream_stride, quad);
             V4 dl, th;
             dl.lo = pack2(__fmul_rn(c0, z.x), __fmul_rn(c1, z.y));
@@ -330,21 +339,21 @@ extern "C" int bde_ivon_sample_batch(const float* mean, const float* prec, float
     const float nf = static_cast<float>(n_eff);
     const int64_t nq = D >> 2;
     if (vec && !eps && !deterministic && S >= 2 && nq > 0 && tuning().swag_batch != 1) {
-        // production form: passes of 16 / 8 / 4 / 2 draws through the fast kernel (delta_sum is carried from pass to pass in
+        // production form: passes of up to 16 draws through the fast kernel (delta_sum is carried from pass to pass in
         // draw order, so the running sum is the one S single calls produce) ...
-        int s0 = 0;
-        while (S - s0 >= 2) {
-            const int left = S - s0;
-            const int sb = left >= 16 ? 16 : (left >= 8 ? 8 : (left >= 4 ? 4 : 2));
+        const int pf = tuning().batch_prefetch == 0 ? 1 : (tuning().batch_prefetch >= 9 ? 0 : tuning().batch_prefetch);
+        for (int s0 = 0; s0 < S;) {
+            const int c = S - s0 < 16 ? S - s0 : 16;
+            const int sb = c <= 2 ? 2 : (c <= 4 ? 4 : (c <= 8 ? 8 : 16));   // c > sb / 2 unless sb == 2 (c = 1: a lone last draw)
             const bool f0 = first && s0 == 0;
             float* out = theta + s0 * ld_out;
             const uint64_t sid = stream_id + static_cast<uint64_t>(s0) * stream_stride;
             int rf = BDE_OK;
-#define BDE_IVON_FAST(SB_)                                                                                                       \
-    rf = f0 ? launch_ew(ivon_sample_batch_fast_kernel<SB_, true>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, nf, seed, sid, \
-                        stream_stride, elem0 >> 2)                                                                               \
-            : launch_ew(ivon_sample_batch_fast_kernel<SB_, false>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, nf, seed, sid, \
-                        stream_stride, elem0 >> 2)
+#define BDE_IVON_FAST(SB_)                                                                                                          \
+    rf = f0 ? launch_ew(ivon_sample_batch_fast_kernel<SB_, true>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, c, nf, seed, sid, \
+                        stream_stride, elem0 >> 2, pf)                                                                              \
+            : launch_ew(ivon_sample_batch_fast_kernel<SB_, false>, nq * 4, st, mean, prec, delta_sum, out, ld_out, nq, c, nf, seed, sid, \
+                        stream_stride, elem0 >> 2, pf)
             switch (sb) {
                 case 2: BDE_IVON_FAST(2); break;
                 case 4: BDE_IVON_FAST(4); break;
@@ -353,13 +362,7 @@ extern "C" int bde_ivon_sample_batch(const float* mean, const float* prec, float
             }
 #undef BDE_IVON_FAST
             if (rf != BDE_OK) return rf;
-            s0 += sb;
-        }
-        if (s0 < S) {   // ... a last odd draw through the general kernel (over the same quads) ...
-            const int rl = launch_ew(ivon_sample_batch_kernel<true>, nq * 4, st, mean, prec, delta_sum, theta + s0 * ld_out, ld_out,
-                                     nq * 4, S - s0, nf, 0, 0, eps, ld_eps, seed,
-                                     stream_id + static_cast<uint64_t>(s0) * stream_stride, stream_stride, elem0 >> 2);
-            if (rl != BDE_OK) return rl;
+            s0 += c;
         }
         const int64_t d4 = nq << 2;
         if (d4 < D)     // ... and the general kernel for all S draws of the last D % 4 elements

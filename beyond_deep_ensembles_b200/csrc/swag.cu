@@ -212,7 +212,16 @@ __global__ void __launch_bounds__(kEwThreads, SB >= 16 ? 2 : 3)
 swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
                               int head, int64_t nquads, int64_t ld, const float* __restrict__ eps_k,
                               const float* __restrict__ eps_d, int64_t ld_eps, uint64_t seed, uint64_t stream_id, int64_t quad0,
-                              float inv_norm_den, float* __restrict__ theta, int64_t ld_out) {
+                              float inv_norm_den, float* __restrict__ theta, int64_t ld_out, int pf_dist, int splits) {
+    // `splits` (1 by default) neighbouring CTAs share the quads of one CTA slot and take SB draws each (draws part * SB ..
+    // part * SB + SB - 1 of the pass).  The partner CTAs are co-resident and walk the same quads at the same time, so the
+    // second reader of a deviation row finds it in L2 (ncu: +19 % DRAM reads at 2 splits); see the launcher for why it is off.
+    const int part = static_cast<int>(blockIdx.x) % splits;
+    const int64_t slot = blockIdx.x / splits, nslots = gridDim.x / splits;
+    stream_id += static_cast<uint64_t>(part) * SB;
+    theta += static_cast<int64_t>(part) * SB * ld_out;
+    if (eps_k) eps_k += static_cast<int64_t>(part) * SB * K;
+    if (INJ) eps_d += static_cast<int64_t>(part) * SB * ld_eps;
     __shared__ __align__(16) float zc[kMaxSwagRank][SB];
     __shared__ int64_t rowoff[kMaxSwagRank];
     for (int e = threadIdx.x; e < K * SB; e += blockDim.x) {
@@ -230,9 +239,19 @@ swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __res
     __syncthreads();
 
     const PhiloxKeys pk = philox_round_keys(seed);
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+    const int64_t stride = nslots * blockDim.x;
+    for (int64_t q = slot * blockDim.x + threadIdx.x; q < nquads; q += stride) {
         const int64_t b = q << 2;
+        // The 128 registers of the 16 accumulator pairs leave two CTAs (4 warps per scheduler) to hide the K + 2 loads of a
+        // quad (ncu: long-scoreboard stalls 2.3 per issue).  The lines of the quad this thread visits `pf_dist` iterations
+        // from now are therefore requested into L2 here — ~2300 instructions ahead of their use, no register held.
+        const int64_t qn = q + pf_dist * stride;
+        if (pf_dist && qn < nquads) {
+            const int64_t bn = qn << 2;
+            prefetch_l2(mean + bn);
+            prefetch_l2(sq + bn);
+            for (int k = 0; k < K; ++k) prefetch_l2(dev + rowoff[k] + bn);
+        }
         const V4 m = ldg_stream_v4(mean + b);
         const V4 sv = ldg_stream_v4(sq + b);
         f32x2 lo[SB], hi[SB];
@@ -302,6 +321,19 @@ swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __res
 }  // namespace bde
 
 using namespace bde;
+
+// One full wave of CTAs like launch_ew, rounded down to a multiple of `splits` (partner CTAs share quads).
+template <typename... KArgs, typename... Args>
+static int launch_swag_fast(void (*kernel)(KArgs...), int splits, int64_t nquads, cudaStream_t st, Args... args) {
+    const int per_sm = ew_occupancy(reinterpret_cast<const void*>(kernel));
+    int64_t slots = (nquads + kEwThreads - 1) / kEwThreads;
+    const int64_t cap = (static_cast<int64_t>(sm_count_cached()) * per_sm) / splits;
+    if (slots > cap) slots = cap;
+    if (slots < 1) slots = 1;
+    kernel<<<static_cast<unsigned>(slots * splits), kEwThreads, 0, st>>>(args...);
+    BDE_CHECK_LAUNCH();
+    return BDE_OK;
+}
 
 extern "C" int bde_swag_update(const float* theta, float* mean, float* sq, float* dev_row, int64_t D, int64_t updates,
                                bde_stream_t stream) {
@@ -382,6 +414,7 @@ extern "C" int bde_swag_sample_batch(const float* mean, const float* sq, const f
     const float den = static_cast<float>(sqrt(2.0 * (K - 1)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int tb = tuning().swag_batch;
+    const int pf = tuning().batch_prefetch == 0 ? 1 : (tuning().batch_prefetch >= 9 ? 0 : tuning().batch_prefetch);
     const int per_pass = (tb == 2 || tb == 4 || tb == 8) ? tb : kSwagBatchMax;
     for (int s0 = 0; s0 < S; s0 += per_pass) {   // up to 16 draws per pass over the moments
         const int c = S - s0 < per_pass ? S - s0 : per_pass;
@@ -392,12 +425,18 @@ extern "C" int bde_swag_sample_batch(const float* mean, const float* sq, const f
         const int64_t nq = D >> 2;
         if (vec && c == sb && nq > 0 && tuning().swag_batch != 1) {   // whole passes of aligned data: fast kernel for the full quads ...
             int rf = BDE_OK;
+            // bde_tune("batch_splits"): a pass can be split over 2 / 4 partner CTAs (fewer draws and registers per thread, shared
+            // reads through L2).  Measured on B200 (profiles/r02_batch_samplers.jsonl): 16 draws x1 0.636 ms, x2 0.702, x4 0.835 —
+            // the redundant per-quad work (+12 % instructions) costs more than 3 CTAs per SM gain, so the default is one CTA.
+            int splits = tuning().batch_splits ? tuning().batch_splits : 1;
+            while (splits > 1 && sb / splits < 2) splits >>= 1;
+            const int sbk = sb / splits;
 #define BDE_SWAG_FAST(SB_)                                                                                                     \
-    rf = ed ? launch_ew(swag_sample_batch_fast_kernel<SB_, true>, nq * 4, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, seed, \
-                        stream_id + s0, elem0 >> 2, den, out, ld_out)                                                          \
-            : launch_ew(swag_sample_batch_fast_kernel<SB_, false>, nq * 4, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, seed, \
-                        stream_id + s0, elem0 >> 2, den, out, ld_out)
-            switch (sb) {
+    rf = ed ? launch_swag_fast(swag_sample_batch_fast_kernel<SB_, true>, splits, nq, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, \
+                               seed, stream_id + s0, elem0 >> 2, den, out, ld_out, pf, splits)                                 \
+            : launch_swag_fast(swag_sample_batch_fast_kernel<SB_, false>, splits, nq, st, mean, sq, dev, K, head, nq, ld, ek, ed, ld_eps, \
+                               seed, stream_id + s0, elem0 >> 2, den, out, ld_out, pf, splits)
+            switch (sbk) {
                 case 2: BDE_SWAG_FAST(2); break;
                 case 4: BDE_SWAG_FAST(4); break;
                 case 8: BDE_SWAG_FAST(8); break;

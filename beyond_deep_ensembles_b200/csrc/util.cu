@@ -124,6 +124,8 @@ extern "C" int bde_tune(const char* key, int value) {
     else if (k == "ew_variant") tuning().ew_variant = value;
     else if (k == "apply_tile_sets") tuning().apply_tile_sets = value;
     else if (k == "swag_batch") tuning().swag_batch = value;
+    else if (k == "batch_prefetch") tuning().batch_prefetch = value;
+    else if (k == "batch_splits") tuning().batch_splits = value;
     else if (k == "gram_pairing") tuning().gram_pairing = value;
     else if (k == "gram_fold") tuning().gram_fold = value;
     else if (k == "gram_l2_promotion") tuning().gram_l2_promotion = value;

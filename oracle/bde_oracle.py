@@ -306,9 +306,12 @@ def philox_normal(count: int, seed: int, stream_id: int, elem0: int = 0) -> np.n
     r = philox4x32_10(np.arange(nq, dtype=np.uint64) + np.uint64(elem0 // 4), seed, stream_id)
 
     def bm(r0, r1):
-        u = (r0 >> np.uint32(8)).astype(np.float64) * 2.0 ** -24 + 2.0 ** -25
-        u = u.astype(np.float32).astype(np.float64)  # the kernel forms u with one fp32 FMA
-        ang = (r1 >> np.uint32(8)).astype(np.float64) * (2.0 * np.pi * 2.0 ** -24) - np.pi  # uniform on [-pi, pi)
+        # the kernel's uniforms (common.cuh:box_muller): the low 23 bits x of a Philox word as the float 2^23 + x, one fp32 FMA each
+        x0 = (r0 & np.uint32(0x7FFFFF)).astype(np.float64)
+        x1 = (r1 & np.uint32(0x7FFFFF)).astype(np.float64)
+        u = (2.0 * x0 + 1.0) * 2.0 ** -24                                   # exact in fp32, in (0, 1)
+        k = float(np.float32(2.0 * np.pi * 2.0 ** -23))
+        ang = ((2.0 ** 23 + x1) * k + float(np.float32(-3.0 * np.pi))).astype(np.float32).astype(np.float64)   # [-pi, pi)
         rad = np.sqrt(-2.0 * np.log(u))
         return rad * np.cos(ang), rad * np.sin(ang)
 
