@@ -207,7 +207,9 @@ swag_sample_batch_kernel(const float* __restrict__ mean, const float* __restrict
 // runs as packed FFMA2 (IEEE per lane, same k order), the epilogue as packed add / mul without contraction — but none of
 // the per-draw predicates, guarded loads and 64-bit address recomputation of the general form: measured 0.99 -> see
 // profiles/r02_bench_n1.json (16 draws at ResNet-50 size).
-template <int SB, bool INJ>
+// (KU = deviation rows in flight per thread; 5 measured best against 2 / 3 / 4 with the L2 prefetch in place: 0.64 / 0.70 /
+// 0.67 / 0.71 ms, profiles/r02_batch_samplers.jsonl)
+template <int SB, bool INJ, int KU = 5>
 __global__ void __launch_bounds__(kEwThreads, SB >= 16 ? 2 : 3)
 swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __restrict__ sq, const float* __restrict__ dev, int K,
                               int head, int64_t nquads, int64_t ld, const float* __restrict__ eps_k,
@@ -257,7 +259,6 @@ swag_sample_batch_fast_kernel(const float* __restrict__ mean, const float* __res
         f32x2 lo[SB], hi[SB];
 #pragma unroll
         for (int sidx = 0; sidx < SB; ++sidx) lo[sidx] = hi[sidx] = 0ull;
-        constexpr int KU = 5;
         for (int k0 = 0; k0 < K; k0 += KU) {
             V4 d[KU];
 #pragma unroll

@@ -49,8 +49,11 @@ const char* bde_error_string(int code);
  * "apply_ctas_per_sm", "ew_ctas_per_sm", or "pairdist_variant" / "apply_variant" /
  * "ew_variant" (1 = direct-LDG kernels, 2 = TMA-staged kernels), "apply_tile_sets" (the
  * alternative consumer geometry of the staged K2: 3 or 4 tile sets at n > 12, 1 set x 512 or
- * 3 sets x 256 columns at n <= 12) or "swag_batch" (draws per pass of bde_swag_sample_batch:
- * 2, 4, 8 or 16); value 0 restores the automatic choice.
+ * 3 sets x 256 columns at n <= 12), "swag_batch" (draws per pass of bde_swag_sample_batch:
+ * 2, 4, 8 or 16; 1 = the general kernels of both batched samplers instead of the fast ones),
+ * "batch_prefetch" (fast batched samplers: L2 prefetch distance in grid-stride iterations,
+ * 9 = off) or "batch_splits" (partner CTAs per pass of the fast batched SWAG sampler: 2, 4);
+ * value 0 restores the automatic choice.
  */
 int bde_tune(const char* key, int value);
 /* number of SMs of the current device (grid sizing is done inside the library) */
