@@ -500,6 +500,78 @@ def other_paths(ops, peak_gbs, dev):
     return res
 
 
+def sharded_elementwise(ops, bdist, dist, world, rank, dev, iters=10):
+    """N > 1: the elementwise family D-sharded (second bullet) — every rank holds one slice of the SWAG and iVON
+    state at the C3 / C4b sizes (weak: the slice IS a whole ResNet-50 / DistilBERT vector), placed in the job-wide Philox
+    stream by dist.column_shard (the collective the host classes run at construction).  No data-path collective; timed like
+    the headline step (barrier, CUDA events, max over ranks), aggregate = N x bytes / time."""
+    res = {}
+
+    def timed(fn, nbytes, name, cfg):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = {"ms": t.item(), "GBps_aggregate": world * nbytes / (t.item() * 1e-3) / 1e9, "config": cfg}
+
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    D, K = 23_880_960, 10
+    shard = bdist.column_shard(D, dist.group.WORLD)
+    theta = torch.randn(D, device=dev, generator=g) * 0.05
+    mean = theta + torch.randn(D, device=dev, generator=g) * 0.01
+    sq = mean * mean + 1e-4
+    ring = torch.randn(K, D, device=dev, generator=g) * 0.01
+    out = torch.empty(D, device=dev)
+    u = [0]
+
+    def upd():
+        u[0] += 1
+        ops.swag_update(theta, mean, sq, ring[(u[0] - 1) % K], u[0])
+
+    cfg = f"slice D={D} per GPU at elem0 = rank x D of {shard.total}, K={K}"
+    timed(upd, 24 * D, "swag_update", cfg)
+    timed(lambda: ops.swag_sample(mean, sq, ring, 3, out, seed=shard.seed, stream_id=2, elem0=shard.elem0), 4 * (K + 3) * D,
+          "swag_sample", cfg)
+    del theta, mean, sq, ring, out
+    D = 66_955_072
+    shard = bdist.column_shard(D, dist.group.WORLD)
+    mean = torch.randn(D, device=dev, generator=g) * 0.05
+    prec = torch.rand(D, device=dev, generator=g) * 1e-4 + 10.0 / 269038
+    mom = torch.randn(D, device=dev, generator=g) * 1e-4
+    dsum = torch.randn(D, device=dev, generator=g) * 0.3
+    acc = torch.randn(D, device=dev, generator=g) * 2e-5
+    theta = torch.zeros(D, device=dev)
+    cfg = f"slice D={D} per GPU at elem0 = rank x D of {shard.total}"
+    timed(lambda: ops.ivon_sample(mean, prec, dsum, theta, first=False, seed=shard.seed, stream_id=3, n_eff=269038.0,
+                                  elem0=shard.elem0), 20 * D, "ivon_sample", cfg)
+    dsum.normal_(0.0, 0.3, generator=g)
+    step = [0]
+
+    def ivon_upd():
+        step[0] += 1
+        ops.ivon_update(acc, dsum, mean, mom, prec, mc_samples=2, step=100 + step[0], lr=1e-5, beta1=0.9, beta2=0.999,
+                        prior_prec=10.0, n_eff=269038.0, tempering=1.0, damping=1e-3)
+
+    timed(ivon_upd, 32 * D, "ivon_update", cfg)
+    res["elem0_of_this_rank"] = shard.elem0
+    res["what"] = ("elementwise family D-sharded over the ranks: no collective on the data path; the group only places each "
+                   "slice in the Philox stream (dist.column_shard)")
+    del mean, prec, mom, dsum, acc, theta
+    torch.cuda.empty_cache()
+    if rank == 0:
+        log(f"[bench] sharded elementwise family: {res}")
+    return res
+
+
 def strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel, steps):
     """D_total = 1e8 and 1e9 columns x n particles split over the `world` ranks (every rank [n, D_total / world]),
     timed like the headline step (barrier, CUDA events, max over ranks); rank 0 then runs the SAME total problem alone
@@ -736,6 +808,14 @@ def main():
         out = torch.empty_like(X)
         step()   # K / A of the headline problem back in the scratch, `out` refilled (the e2e leg compares against it)
 
+    sharded_ew = None
+    if world > 1 and not args.skip_extras:
+        try:
+            sharded_ew = sharded_elementwise(ops, bdist, dist, world, rank, dev)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] sharded elementwise family failed: {e}")
+            sharded_ew = {"error": str(e)}
+
     # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
     e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
     paths, cpu_base, eager = None, None, None
@@ -825,7 +905,7 @@ def main():
             },
             "step_frac_of_measured_peak": value / world / peak_gbs,
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
-            "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong,
+            "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong, "sharded_elementwise": sharded_ew,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
         try:
