@@ -305,6 +305,23 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// Build-time instrumentation (-DBDE_TAIL_TIMING, tools/exp_tail_timing.py; never in the shipped library): %globaltimer stamps
+// in the unused bytes 192.. of the workspace header — where K1's fixed cost goes at small D.
+#ifdef BDE_TAIL_TIMING
+#define BDE_TS_SLOT(ws_, i) (reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(ws_) + 192) + (i))
+#define BDE_TS(ws_, i)                                                                       \
+    do {                                                                                     \
+        if (threadIdx.x == 0 && threadIdx.y == 0) *BDE_TS_SLOT(ws_, i) = globaltimer_ns();   \
+    } while (0)
+#define BDE_TS_MAX(ws_, i)                                                                             \
+    do {                                                                                               \
+        if (threadIdx.x == 0 && threadIdx.y == 0) atomicMax(BDE_TS_SLOT(ws_, i), globaltimer_ns());    \
+    } while (0)
+#else
+#define BDE_TS(ws_, i) do { } while (0)
+#define BDE_TS_MAX(ws_, i) do { } while (0)
+#endif
+
 // Called by every thread of the last CTA with the local sums in total[0..count): on return total holds
 // the sums over all ranks (same bits on every rank).  No-op for an unattached workspace.
 __device__ __forceinline__ void peer_allreduce_fp64(WsHeader* h, double* total, int count) {
@@ -383,8 +400,8 @@ __device__ __forceinline__ bool peer_exchange_failed(const void* ws) { return re
 // Returns true in every thread of the LAST CTA to arrive, after which total[k] = sum over all
 // CTAs (and, for a workspace attached to a peer set, over all ranks) is available in `total`
 // (shared, count doubles).  The order of the additions depends only
-// on (gridDim, count): every warp of the last CTA owns groups of 4 consecutive values k (one 32-byte
-// sector per CTA), its lanes walk the CTA list with stride 32 keeping 4 x 8 independent loads in
+// on (gridDim, count): every warp of the last CTA owns groups of 4 consecutive values k, its lanes
+// walk the CTA list with stride 32 (coalesced: the partials are stored value-major) keeping 4 x 8 independent loads in
 // flight, and the 32 lane sums are combined by the fixed xor-shuffle tree.  The ticket is reset so
 // the workspace can be reused by the next launch.
 __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int count, void* ws, double* total) {
@@ -393,7 +410,11 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     const int tid = threadIdx.x + threadIdx.y * blockDim.x;
     const int nthreads = blockDim.x * blockDim.y;
     __shared__ bool is_last;
-    for (int k = tid; k < count; k += nthreads) parts[(size_t)blockIdx.x * count + k] = cta_vals[k];
+    // value-major layout parts[k][cta]: the last CTA's lanes walk the CTA list, so consecutive lanes read consecutive
+    // doubles — one 256-byte request per warp load.  (CTA-major, every lane touched its own 32-byte sector with four
+    // separate 8-byte loads: 128 sector transactions per warp and group, 18.6 us for 148 x 190 values at n = 20 —
+    // measured with the stamps below, profiles/r02_tail_timing.jsonl.  Same addends in the same order: same bits.)
+    for (int k = tid; k < count; k += nthreads) parts[(size_t)k * gridDim.x + blockIdx.x] = cta_vals[k];
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -403,6 +424,7 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
+    BDE_TS(ws, 2);
     constexpr int KU = 4, BU = 8;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;  // CTA sizes are multiples of 32
     const unsigned int G = gridDim.x;
@@ -417,7 +439,7 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
                 const unsigned int b = b0 + 32u * r;
 #pragma unroll
                 for (int u = 0; u < KU; ++u)
-                    v[r][u] = (b < G && k0 + u < count) ? __ldcg(&parts[(size_t)b * count + k0 + u]) : 0.0;
+                    v[r][u] = (b < G && k0 + u < count) ? __ldcg(&parts[(size_t)(k0 + u) * G + b]) : 0.0;
             }
 #pragma unroll
             for (int r = 0; r < BU; ++r)
@@ -432,6 +454,7 @@ __device__ __forceinline__ bool grid_reduce_fp64(const double* cta_vals, int cou
     }
     if (tid == 0) *ticket = 0u;
     __syncthreads();
+    BDE_TS(ws, 3);
     if (count <= kPeerMaxVals) peer_allreduce_fp64(reinterpret_cast<WsHeader*>(ws), total, count);
     return true;
 }

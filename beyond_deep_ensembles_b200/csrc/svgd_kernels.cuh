@@ -324,7 +324,16 @@ __device__ __forceinline__ void bandwidth_device(const double* dist, int n, cons
                     s_ord[l] = ia;
                 }
             }
-            __syncthreads();
+            // A 32-aligned block of compare-exchange indices t belongs to ONE warp in every pass (nthreads is a multiple of
+            // 32), and with j <= 32 such a block only touches its own 64 elements: as long as this pass and the next both
+            // have j <= 32, the hand-over is warp-local: 10 block-wide barriers instead of 45 at n = 20 (512 padded
+            // entries), 3 instead of 28 at n = 10.  (Worth ~0.5 us only: K1b's 9 / 5 us at n = 20 / 10 are dependent fp64
+            // chains — sqrt, log, exp, the division — not barriers and not instruction fetch: profiles/r02_tail_timing.jsonl.)
+            const int j_next = j > 1 ? (j >> 1) : k;   // first pass of the next k runs with j = k
+            if (j <= 32 && j_next <= 32 && !(k == npad && j == 1))
+                __syncwarp();
+            else
+                __syncthreads();
         }
     }
     const int pos_lo = (nn - 1) / 2;
@@ -565,6 +574,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
 
     const int tid = threadIdx.x;
     const int nthreads = kPdConsumers + 32;
+    if (blockIdx.x == 0) BDE_TS(ws, 0);
     for (int k = tid; k < CWARPS * PG; k += nthreads) (&wacc[0][0])[k] = 0.0;
     if (tid == 0) {
 #pragma unroll
@@ -602,6 +612,7 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
         pairdist_tma_dispatch<N, 0>(g, X, D, ld, tiles, full_bar, empty_bar, wacc[wid], qi);
     }
     __syncthreads();
+    BDE_TS_MAX(ws, 1);
     griddep_launch();   // streaming done: a dependent K2 may become resident during the tail
 
     // pair p of group grp is accumulated by that group's warps only
@@ -621,10 +632,21 @@ svgd_pairdist_tma_kernel(const float* __restrict__ X, int64_t D, int64_t ld, dou
         if (accumulate) v += dist[e];
         dist[e] = v;
     }
+    BDE_TS(ws, 4);
     if (fuse_bandwidth && !peer_exchange_failed(ws)) {
         __syncthreads();
         bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
     }
+    __syncthreads();
+    BDE_TS(ws, 5);
+#ifdef BDE_TAIL_TIMING
+    if (fuse_bandwidth && !peer_exchange_failed(ws)) {   // the same code again, now warm: what of K1b's time is instruction fetch?
+        __syncthreads();
+        bandwidth_device<pow2_ceil(N * N)>(dist, N, bp, sd, sk);
+    }
+    __syncthreads();
+    BDE_TS(ws, 6);
+#endif
 }
 
 // ---------------------------------------------------------------------------------
