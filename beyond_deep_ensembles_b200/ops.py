@@ -532,21 +532,27 @@ def multi_tensor_copy(flat_row: torch.Tensor, tensors, offsets, mode: int, table
     count = len(tensors)
     if count == 0:
         return
-    require_cuda(flat_row, *tensors)
+    require_cuda(flat_row)
     _lib.require_f32(flat_row)
     if table is None:
         table = CopyTable(offsets, [t.numel() for t in tensors])
     elif table.count != count:
         raise ValueError("multi_tensor_copy: tensor list does not match the copy table")
-    f32, ptrs = torch.float32, []
+    # one pass over the tensors (this runs once per particle / MC sample over up to a few hundred gradients): the common
+    # case costs four attribute reads per tensor, the error branch says which check failed
+    f32, dev, ptrs = torch.float32, flat_row.device, []
     for t, numel in zip(tensors, table.numels):
+        if t.dtype is f32 and t.device == dev and t.numel() == numel and t.is_contiguous():
+            ptrs.append(t.data_ptr())
+            continue
         if t.dtype is not f32:
             raise TypeError(f"expected float32 tensor, got {t.dtype}")
+        if t.device != dev:
+            require_cuda(flat_row, t)   # raises: not a CUDA tensor / tensors span devices
+            raise _lib.BdeError(f"tensors of one kernel call span devices ({dev} and {t.device})")
         if not t.is_contiguous():
             raise ValueError("multi_tensor_copy needs contiguous tensors")
-        if t.numel() != numel:
-            raise ValueError("multi_tensor_copy: tensor size does not match the copy table")
-        ptrs.append(t.data_ptr())
+        raise ValueError("multi_tensor_copy: tensor size does not match the copy table")
     cptrs = (C.c_uint64 * count)(*ptrs)
     if inv_scale is None:
         _lib.call("bde_multi_tensor_copy", flat_row.data_ptr(), C.cast(cptrs, C.c_void_p), table.offs_p, table.sizes_p,

@@ -130,6 +130,12 @@ class SVGDOptimizer(BayesianOptimizer):
                 for param, xview, gview in zip(plist, xviews, gviews):
                     param.data = xview           # _use_particle (svgd.py:120-127): alias, no copy
                     param.grad = gview           # what base.zero_grad() + the gather of svgd.py:74,129-133 amount to
+            elif self._base_owns_exactly(base, plist):
+                # base.zero_grad() (svgd.py:74) over exactly these parameters is "grad = None" for each of them; folded into
+                # the rebinding loop it saves torch's per-call bookkeeping (~0.1 ms per particle at 96 tensors)
+                for param, xview in zip(plist, xviews):
+                    param.data = xview
+                    param.grad = None
             else:
                 for param, xview in zip(plist, xviews):
                     param.data = xview
@@ -212,6 +218,19 @@ class SVGDOptimizer(BayesianOptimizer):
         if plan is None or plan.base is not base or not plan.still_valid():
             plan = self._fused_plan = FusedBasePlan.build(base, plist, self._layout, self._X.device)
         return plan
+
+    def _base_owns_exactly(self, base, plist) -> bool:
+        """True when the base optimizer holds exactly this optimizer's parameters, zero_grad defaults to
+        set_to_none and nobody hooked or overrode it (checked once per base optimizer object)."""
+        cached = getattr(self, "_base_zero_fast", None)
+        if cached is None or cached[0] is not base:
+            import inspect
+            ids = {id(p) for g in base.param_groups for p in g["params"]}
+            plain = type(base).zero_grad is torch.optim.Optimizer.zero_grad and "zero_grad" not in vars(base)
+            default = inspect.signature(torch.optim.Optimizer.zero_grad).parameters["set_to_none"].default is True
+            cached = (base, plain and default and ids == {id(p) for p in plist})
+            self._base_zero_fast = cached
+        return cached[1]
 
     def _write_versions(self, plist):
         """Autograd version counters that every tracked in-place write to a particle bumps: the X arena's (shared

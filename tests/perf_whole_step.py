@@ -33,6 +33,9 @@ import standin_models as S  # noqa: E402
 from golden_models import make_mlp  # noqa: E402
 
 
+PROFILE = 0
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -213,6 +216,17 @@ def bench_config(name, build, steps, warmup):
         l0 = _lib.launch_count
         s_ms = wall_ms(step_fn, steps, warmup)
         launches = (_lib.launch_count - l0) / (3 * steps + warmup)
+        if PROFILE and kind == "b200":   # where the host time of step() goes (cumulative, top entries) -> stderr
+            import cProfile, io, pstats
+            pr = cProfile.Profile()
+            pr.enable()
+            for _ in range(steps):
+                step_fn()
+            _sync()
+            pr.disable()
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(PROFILE)
+            log(f"[whole_step] cProfile of {steps} x step() at {name}:\n" + buf.getvalue()[:6000])
         pre = "" if kind == "b200" else "eager_"
         res[pre + "closures_ms"] = c_ms
         res[pre + "step_ms"] = s_ms
@@ -238,8 +252,10 @@ def main():
     ap.add_argument("--eager-only-cpu", action="store_true", help="debug: run only the eager port, on the CPU")
     ap.add_argument("--prebind", default="auto", choices=["auto", "on", "off"],
                     help="zero-copy gradient capture of SVGD / iVON (BayesianOptimizer.prebind_grads): A/B runs")
+    ap.add_argument("--cprofile", type=int, default=0, help="print the top N cumulative cProfile entries of step() per config")
     args = ap.parse_args()
-    global KINDS
+    global KINDS, PROFILE
+    PROFILE = args.cprofile
     if args.eager_only_cpu:
         KINDS = ("eager",)
     import beyond_deep_ensembles_b200 as bde

@@ -108,6 +108,36 @@ def build_svgd(env, g, base_cls=torch.optim.Adam, **base_kw):
     return model, opt
 
 
+def test_svgd_zero_grad_shortcut_only_when_base_owns_exactly_these_params(env, golden):
+    """svgd.py:74 calls base_optimizer.zero_grad() per particle.  The gather path folds it into the rebinding loop
+    (grad = None) only when the base optimizer holds exactly the SVGD parameters and its zero_grad is torch's own;
+    a base optimizer with an extra parameter group, or an overridden zero_grad, is called as the reference calls it."""
+    g = golden("svgd_steps.npz")
+    model, opt = build_svgd(env, g)
+    plist = list(model.parameters())
+    base = opt.get_base_optimizer()
+    assert opt._base_owns_exactly(base, plist)
+    extra = torch.nn.Parameter(torch.zeros(3, device=env.dev))
+    base.add_param_group({"params": [extra]})
+    opt._base_zero_fast = None
+    assert not opt._base_owns_exactly(base, plist)
+    opt.prebind_grads = False
+    extra.grad = torch.ones_like(extra)
+    fwd, bwd = gm.mse_closures(model, env.t(g["xs"][0]), env.t(g["ys"][0]))
+    opt.step(fwd, bwd)
+    assert extra.grad is None            # base.zero_grad() ran (the shortcut would have left it alone)
+
+    class Hooked(torch.optim.SGD):
+        def zero_grad(self, set_to_none=True):
+            self.calls = getattr(self, "calls", 0) + 1
+            super().zero_grad(set_to_none)
+    model2, opt2 = build_svgd(env, g, base_cls=Hooked)
+    opt2.prebind_grads = False
+    fwd, bwd = gm.mse_closures(model2, env.t(g["xs"][0]), env.t(g["ys"][0]))
+    opt2.step(fwd, bwd)
+    assert opt2.get_base_optimizer().calls == g["init"].shape[0]
+
+
 @pytest.mark.parametrize("capture", ["prebound", "gather", "closure-zeroes-grads"])
 def test_svgd_gradient_capture_forms_match_reference(env, golden, capture):
     """the particles' gradients reach the G arena through pre-bound `.grad` views (autograd accumulates
