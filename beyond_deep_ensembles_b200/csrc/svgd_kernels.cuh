@@ -1314,9 +1314,13 @@ int launch_apply_opt(const float* X, const float* G, float* out, const float* K,
     const int64_t d4 = D & ~static_cast<int64_t>(3);
     const int64_t ntiles = (d4 + TC - 1) / TC;
     int variant = tuning().apply_variant;
-    // auto: the staged kernel wins once every SM has a few tiles per tile set
+    // auto: the staged kernel wins once every SM has a few tiles per tile set — and, for K2 / K2f, already from 64 K columns on:
+    // the direct kernel at n = 20 loads its 40 row quads one j at a time (rolled loop, ~20 exposed latencies per thread), the
+    // ring keeps them all in flight.  Measured with a flushed L2 (profiles/r02_apply_small.jsonl): n = 20, D = 273,664: K2 27.0 ->
+    // 21.7 us, K2f 30.7 -> 23.9 us; n = 10, D = 65,536: 11.3 -> 8.9 us; never slower from 65,536 columns up at n = 5 ... 20.
+    // (The training-step form keeps its own rule: it was not part of that measurement.)
     if (variant == 0) {
-        variant = (ntiles >= 2 * TS0 * static_cast<int64_t>(sm_count_cached())) ? 2 : 1;
+        variant = (ntiles >= 2 * TS0 * static_cast<int64_t>(sm_count_cached()) || (!NEXT && d4 >= 65536)) ? 2 : 1;
     }
     if (d4 == 0 || d4 > 0x7fffffffLL) variant = 1;   // the tensor maps need >= 1 column quad and int32 coordinates
     if (variant == 2) {
