@@ -42,6 +42,25 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert lib.bde_error_string(-3) == b"bde: workspace missing or too small"
 
 
+def test_tuning_keys_documented_in_the_header_are_accepted(built_lib):
+    """bde_tune is host-only code: every key the header's comment names is accepted (value 0 = automatic choice),
+    anything else and negative values are BDE_ERR_INVALID_ARG, and no key is left without a word in the header."""
+    lib = ctypes.CDLL(str(built_lib))
+    lib.bde_tune.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.bde_tune.restype = ctypes.c_int
+    comment = HEADER.read_text().split("int bde_tune(")[0].rsplit("/*", 1)[1]
+    documented = set(re.findall(r'"([a-z_0-9]+)"', comment))
+    assert {"pairdist_ctas_per_sm", "apply_variant", "swag_batch", "batch_prefetch", "batch_splits"} <= documented
+    for key in documented:
+        assert lib.bde_tune(key.encode(), 0) == 0, key
+    assert lib.bde_tune(b"no_such_knob", 0) != 0
+    assert lib.bde_tune(b"swag_batch", -1) != 0
+    src = (ROOT / "beyond_deep_ensembles_b200" / "csrc" / "util.cu").read_text()
+    implemented = set(re.findall(r'k == "([a-z_0-9]+)"', src))
+    internal = {"gram_pairing", "gram_fold", "gram_l2_promotion", "ring_kb", "gram_guard_x1000"}   # csrc/common.cuh:Tuning only
+    assert implemented - internal == documented
+
+
 def test_python_binding_covers_the_header(built_lib):
     from beyond_deep_ensembles_b200 import _lib
     bound = set(_lib.SIGNATURES) | {"bde_error_string"}
