@@ -10,6 +10,7 @@ from .algo import BayesianOptimizer, LastLayerBayesianOptimizer
 from .bbb import BBBOptimizer, GaussianPrior, MixturePrior
 from .ensemble import DeepEnsemble
 from .install import install
+from .sharded_closure import ColumnShardedModel
 from .ivorn import iVONOptimizer
 from .svgd import SVGDOptimizer, rbf
 from .swag import SwagOptimizer
@@ -17,5 +18,5 @@ from .util import GaussianParameter
 
 __all__ = [
     "BayesianOptimizer", "LastLayerBayesianOptimizer", "BBBOptimizer", "GaussianPrior", "MixturePrior",
-    "DeepEnsemble", "install", "iVONOptimizer", "SVGDOptimizer", "rbf", "SwagOptimizer", "GaussianParameter",
+    "DeepEnsemble", "install", "ColumnShardedModel", "iVONOptimizer", "SVGDOptimizer", "rbf", "SwagOptimizer", "GaussianParameter",
 ]

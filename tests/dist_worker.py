@@ -198,3 +198,28 @@ def run_elementwise(rank: int, world: int, port: int, out_path: str, backend: st
     torch.save(res, f"{out_path}.{rank}")
     dist.barrier()
     dist.destroy_process_group()
+
+
+def run_sharded_closure(rank: int, world: int, port: int, out_path: str, backend: str = "gloo", split_batch: bool = True):
+    """D-sharded optimizers over ColumnShardedModel closures (all-gather weights / reduce-scatter gradients): every
+    rank runs tests/sharded_closure_script.py; the test compares with the plain classes on the whole model."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        torch.set_num_threads(1)
+        import fake_abi
+        fake_abi.install(_Patch())
+    import sharded_closure_script
+    from beyond_deep_ensembles_b200 import dist as bdist
+    res = sharded_closure_script.run(dev, world, rank, dist.group.WORLD, split_batch)
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+    torch.save(res, f"{out_path}.{rank}")
+    dist.barrier()
+    bdist.shutdown_peer_exchange()
+    dist.destroy_process_group()
