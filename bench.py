@@ -572,6 +572,78 @@ def sharded_elementwise(ops, bdist, dist, world, rank, dev, iters=10):
     return res
 
 
+def sharded_closure(bde, dist, world, rank, dev, D=23_880_960, K=10, iters=10):
+    """N > 1: a whole optimizer step on D-sharded state with a MODEL-shaped closure (SURVEY §8e last note, §8 f4):
+    `ColumnShardedModel` all-gathers the ranks' weight slices before the forward and reduce-scatters the gradients after the
+    backward (two single-buffer NCCL collectives over NVLink), `SwagOptimizer(process_group=...)` over a sharded SGD then
+    updates 1 / N of the columns.  The model itself is left out (forward = a constant, backward = one accumulate pass into
+    the pre-bound gradient views), so the lines show what sharding costs (the collectives) and saves (the update on 1 / N
+    of the state) at ResNet-50 size; the unsharded class runs the same closure on every rank for comparison.  Strong
+    scaling of a fixed D; barrier, CUDA events, max over ranks."""
+    res = {}
+
+    def timed(fn, name):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = {"ms": t.item()}
+        return t.item()
+
+    def make(group):
+        g = torch.Generator(device=dev).manual_seed(5)
+        w = torch.nn.Parameter(torch.randn(D, device=dev, generator=g) * 0.05)
+        gsyn = torch.randn(D, device=dev, generator=g) * 1e-3
+        zero = torch.zeros((), device=dev)
+        sm = bde.ColumnShardedModel([w], group) if group is not None else None
+        params = [sm.param] if sm is not None else [w]
+        base = torch.optim.SGD(params, lr=0.01, momentum=0.9)
+        opt = bde.SwagOptimizer(params, base, update_interval=1, deviation_samples=K, process_group=group)
+
+        def fwd():
+            return zero
+
+        def bwd(loss):
+            if w.grad is None:
+                w.grad = gsyn.clone()
+            else:
+                w.grad.add_(gsyn)          # what autograd's AccumulateGrad does with a bound .grad
+        return w, sm, opt, (sm.closures(fwd, bwd) if sm is not None else (fwd, bwd))
+
+    w, sm, opt, (fwd, bwd) = make(dist.group.WORLD)
+    wire = 4.0 * sm.shard * (world - 1)     # bytes every GPU receives (all-gather) / sends (reduce-scatter) per call
+    ms = timed(sm.gather, "all_gather_weights")
+    res["all_gather_weights"].update(GBps_per_gpu_on_the_wire=wire / (ms * 1e-3) / 1e9)
+    ms = timed(sm.reduce_grads, "reduce_scatter_grads")
+    res["reduce_scatter_grads"].update(GBps_per_gpu_on_the_wire=wire / (ms * 1e-3) / 1e9)
+    timed(lambda: opt.step(fwd, bwd), "swag_step_sharded")
+    res["swag_step_sharded"]["what"] = "gather + closure + reduce-scatter + SGD(momentum) and SWAG update on this rank's columns"
+    res["state_bytes_per_gpu_sharded"] = 4 * sm.shard * (K + 4 + 1) + 8 * world * sm.shard
+    shard_cols = sm.shard
+    del w, sm, opt, fwd, bwd
+    torch.cuda.empty_cache()
+    w, _, opt, (fwd, bwd) = make(None)
+    timed(lambda: opt.step(fwd, bwd), "swag_step_unsharded")
+    res["swag_step_unsharded"]["what"] = "the plain class on the whole vector (every rank its own copy), same closure"
+    res["state_bytes_per_gpu_unsharded"] = 4 * D * (K + 4 + 1) + 4 * D
+    res["config"] = (f"flat weight vector D={D} (ResNet-50 size), K={K} deviations, {world} ranks x {shard_cols} columns; "
+                     "model forward / backward left out")
+    del w, opt, fwd, bwd
+    torch.cuda.empty_cache()
+    if rank == 0:
+        log(f"[bench] sharded closure: {res}")
+    return res
+
+
 def strong_scaling(ops, bdist, dist, sc, n, world, rank, dev, in_kernel, steps):
     """D_total = 1e8 and 1e9 columns x n particles split over the `world` ranks (every rank [n, D_total / world]),
     timed like the headline step (barrier, CUDA events, max over ranks); rank 0 then runs the SAME total problem alone
@@ -816,6 +888,15 @@ def main():
             log(f"[bench] sharded elementwise family failed: {e}")
             sharded_ew = {"error": str(e)}
 
+    sharded_cl = None
+    if world > 1 and not args.skip_extras:
+        try:
+            import beyond_deep_ensembles_b200 as bde
+            sharded_cl = sharded_closure(bde, dist, world, rank, dev)
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] sharded closure failed: {e}")
+            sharded_cl = {"error": str(e)}
+
     # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
     e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
     paths, cpu_base, eager = None, None, None
@@ -905,7 +986,7 @@ def main():
             },
             "step_frac_of_measured_peak": value / world / peak_gbs,
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
-            "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong, "sharded_elementwise": sharded_ew,
+            "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong, "sharded_elementwise": sharded_ew, "sharded_closure": sharded_cl,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
         try:
