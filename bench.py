@@ -500,6 +500,29 @@ def other_paths(ops, peak_gbs, dev):
     return res
 
 
+def whole_step_configs(dev):
+    """Whole `optimizer.step(forward_closure, backward_closure)` of the drop-in classes with REAL model closures at the
+    small BASELINE configs (SURVEY §8d item ii: C1 = UCI MLP, SVGD n = 10, Adam; C2 = CIFAR ResNet-20-FRN, SVGD n = 20,
+    SGD-Nesterov): wall clock per step, the model's forward + backward passes alone, and the difference — what the posterior
+    update costs on top of the model, host-side Python included.  tests/perf_whole_step.py with kinds = ("b200",): only
+    this package's classes run.  BDE_BENCH_WHOLE_STEP=C1,C2,C3,C4a,C4b widens it (C3 needs torchvision, C4 transformers)."""
+    configs = [c for c in os.environ.get("BDE_BENCH_WHOLE_STEP", "C1,C2").split(",") if c]
+    if not configs:
+        return None
+    try:
+        tests_dir = os.path.join(ROOT, "tests")
+        if tests_dir not in sys.path:
+            sys.path.insert(0, tests_dir)
+        import perf_whole_step
+        res = perf_whole_step.run(configs, steps=3, warmup=2, kinds=("b200",), dev=dev)
+        torch.cuda.empty_cache()
+        log(f"[bench] whole step with model closures: { {k: v for k, v in res.items() if k != '_meta'} }")
+        return res
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] whole-step configs failed: {e}")
+        return {"error": str(e)}
+
+
 def sharded_elementwise(ops, bdist, dist, world, rank, dev, iters=10):
     """N > 1: the elementwise family D-sharded (second bullet) — every rank holds one slice of the SWAG and iVON
     state at the C3 / C4b sizes (weak: the slice IS a whole ResNet-50 / DistilBERT vector), placed in the job-wide Philox
@@ -899,7 +922,7 @@ def main():
 
     # ---- end-to-end through the host-buffer API (pinned host memory, H2D + D2H inside the timing) ----
     e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 8 * n * D * world, "d2h_bytes_per_step": 4 * n * D * world}
-    paths, cpu_base, eager = None, None, None
+    paths, cpu_base, eager, whole = None, None, None, None
     if not args.skip_extras:
         try:
             import psutil
@@ -951,6 +974,7 @@ def main():
             except Exception as e:  # noqa: BLE001
                 log(f"[bench] other paths failed: {e}")
                 paths = {"error": str(e)}
+            whole = whole_step_configs(dev)
             eager = eager_cuda_reference(dev)
             gbs, ms, threads, kind, Dc = cpu_reference_run(3, 1)
             cpu_base = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "cores": threads, "kind": kind,
@@ -987,6 +1011,7 @@ def main():
             "step_frac_of_measured_peak": value / world / peak_gbs,
             "step_frac_of_nominal_8TBps": value / world / 8000.0,
             "cpu_baseline": cpu_base, "eager_cuda": eager, "paths": paths, "exchange": exchange, "strong": strong, "sharded_elementwise": sharded_ew, "sharded_closure": sharded_cl,
+            "whole_step": whole,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
         try:

@@ -253,18 +253,30 @@ def main():
     ap.add_argument("--prebind", default="auto", choices=["auto", "on", "off"],
                     help="zero-copy gradient capture of SVGD / iVON (BayesianOptimizer.prebind_grads): A/B runs")
     ap.add_argument("--cprofile", type=int, default=0, help="print the top N cumulative cProfile entries of step() per config")
+    ap.add_argument("--kinds", default="b200,eager", help="b200 = this package, eager = the reference's op sequence (tests-only port)")
     args = ap.parse_args()
-    global KINDS, PROFILE
+    global PROFILE
     PROFILE = args.cprofile
-    if args.eager_only_cpu:
-        KINDS = ("eager",)
-    import beyond_deep_ensembles_b200 as bde
-    from beyond_deep_ensembles_b200 import util as butil
     from beyond_deep_ensembles_b200.algo import BayesianOptimizer
     BayesianOptimizer.prebind_grads = {"auto": "auto", "on": True, "off": False}[args.prebind]
     dev = torch.device("cpu") if args.eager_only_cpu else torch.device("cuda", 0)
+    kinds = ("eager",) if args.eager_only_cpu else tuple(args.kinds.split(","))
+    out = run(args.configs.split(","), args.steps, args.warmup, kinds, dev)
+    out["_meta"]["prebind_grads"] = args.prebind
+    print(json.dumps(out, indent=1))
+
+
+def run(configs, steps=5, warmup=2, kinds=("b200", "eager"), dev=None):
+    """The configs' whole-step numbers as a dict (bench.py calls this with kinds=("b200",): only the package's own
+    classes run then, nothing under oracle/ is imported)."""
+    global KINDS
+    KINDS = tuple(kinds)
+    import beyond_deep_ensembles_b200 as bde
+    from beyond_deep_ensembles_b200 import util as butil
+    dev = torch.device("cuda", 0) if dev is None else dev
+    args = argparse.Namespace(steps=steps, warmup=warmup)
     out = {}
-    want = set(args.configs.split(","))
+    want = set(configs)
 
     def closures_of(model, x, y, loss_fn):
         def fwd():
@@ -406,10 +418,12 @@ def main():
             torch.cuda.empty_cache()
         out["C5_svgd_update_only_n10"] = res5
 
-    out["_meta"] = {"prebind_grads": args.prebind, "gpu": torch.cuda.get_device_name(0) if torch.cuda.is_available() else "cpu", "torch": torch.__version__,
+    out["_meta"] = {"gpu": torch.cuda.get_device_name(0) if torch.cuda.is_available() else "cpu", "torch": torch.__version__,
                     "timing": "wall clock per step, best of 3 timed loops, synchronised before and after each loop",
-                    "eager": "reference op sequence in eager PyTorch on the same GPU (tests-only port)"}
-    print(json.dumps(out, indent=1))
+                    "kinds": list(KINDS)}
+    if "eager" in KINDS:
+        out["_meta"]["eager"] = "reference op sequence in eager PyTorch on the same GPU (tests-only port)"
+    return out
 
 
 if __name__ == "__main__":
