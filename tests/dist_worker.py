@@ -200,9 +200,11 @@ def run_elementwise(rank: int, world: int, port: int, out_path: str, backend: st
     dist.destroy_process_group()
 
 
-def run_sharded_closure(rank: int, world: int, port: int, out_path: str, backend: str = "gloo", split_batch: bool = True):
+def run_sharded_closure(rank: int, world: int, port: int, out_path: str, backend: str = "gloo", split_batch: bool = True,
+                        subgroup: bool = False):
     """D-sharded optimizers over ColumnShardedModel closures (all-gather weights / reduce-scatter gradients): every
-    rank runs tests/sharded_closure_script.py; the test compares with the plain classes on the whole model."""
+    rank runs tests/sharded_closure_script.py; the test compares with the plain classes on the whole model.
+    subgroup: the column slices live on ranks 1 .. world-1 only (a sub-group of the job; rank 0 stays out)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     if backend == "nccl":
         torch.cuda.set_device(rank)
@@ -216,7 +218,11 @@ def run_sharded_closure(rank: int, world: int, port: int, out_path: str, backend
         fake_abi.install(_Patch())
     import sharded_closure_script
     from beyond_deep_ensembles_b200 import dist as bdist
-    res = sharded_closure_script.run(dev, world, rank, dist.group.WORLD, split_batch)
+    if subgroup:
+        grp = dist.new_group(list(range(1, world)))      # collective over the whole job
+        res = sharded_closure_script.run(dev, world - 1, rank - 1, grp, split_batch) if rank > 0 else None
+    else:
+        res = sharded_closure_script.run(dev, world, rank, dist.group.WORLD, split_batch)
     if dev.type == "cuda":
         torch.cuda.synchronize()
     torch.save(res, f"{out_path}.{rank}")

@@ -66,6 +66,19 @@ def test_sharded_closure_gloo(tmp_path, monkeypatch, world, split_batch):
     run_case(tmp_path, world, "gloo", full, split_batch)
 
 
+def test_sharded_closure_on_a_subgroup_gloo(tmp_path, monkeypatch):
+    """The column slices live on ranks 1 and 2 of a 3-rank job (process_group = a sub-group, not WORLD): group ranks,
+    the broadcast source and every collective must be the sub-group's."""
+    import dist_worker
+    torch.set_num_threads(1)
+    fake_abi.install(monkeypatch)
+    full = script.run(torch.device("cpu"), 1, 0, None, True)
+    out_path = str(tmp_path / "sub")
+    mp.spawn(dist_worker.run_sharded_closure, args=(3, free_port(), out_path, "gloo", True, True), nprocs=3, join=True)
+    assert torch.load(f"{out_path}.0") is None
+    compare([torch.load(f"{out_path}.{r}") for r in (1, 2)], full, 2, True)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,split_batch", [(2, False), (2, True), (4, True)])
 def test_sharded_closure_nccl(tmp_path, world, split_batch):
