@@ -33,8 +33,10 @@ def _data(dev, world, rank, split_batch):
     return x.to(dev), y.to(dev)
 
 
-def run(dev, world: int, rank: int, group, split_batch: bool):
-    """Returns full-length vectors on every rank (the sharded run all-gathers its slices for the comparison)."""
+def run(dev, world: int, rank: int, group, split_batch: bool, wrap_single: bool = False):
+    """Returns full-length vectors on every rank (the sharded run all-gathers its slices for the comparison).
+    wrap_single (with group None): the optimizers still run over ColumnShardedModel's one flat parameter and its
+    closures, as a one-rank "group" — no collective, everything else as in a sharded job."""
     import beyond_deep_ensembles_b200 as bde
     from beyond_deep_ensembles_b200 import noise
 
@@ -45,7 +47,7 @@ def run(dev, world: int, rank: int, group, split_batch: bool):
     def build():
         torch.manual_seed(3 + (0 if group is None else 17 * rank))  # rank 0's init is what the job uses (broadcast)
         model = gm.make_mlp().to(dev)
-        if group is None:
+        if group is None and not wrap_single:
             return model, None, list(model.parameters())
         sm = bde.ColumnShardedModel(model, group)
         return model, sm, [sm.param]

@@ -88,6 +88,33 @@ def test_sharded_closure_nccl(tmp_path, world, split_batch):
     run_case(tmp_path, world, "nccl", full, split_batch)
 
 
+@pytest.mark.parametrize("backend", [pytest.param("cpu", id="oracle-abi"), pytest.param("cuda", id="cuda", marks=pytest.mark.gpu)])
+def test_one_rank_group_equals_the_plain_classes(monkeypatch, backend):
+    """ONE device, no torch.distributed: SWAG / iVON / SVGD over ColumnShardedModel's flat parameter and closures
+    (world = 1) against the plain classes over the model's own tensors — same arena layout, same Philox counters,
+    so the elementwise family agrees bit for bit and SVGD to rounding (one [n, 640] tensor instead of four)."""
+    if backend == "cuda":
+        if not torch.cuda.is_available():
+            pytest.skip("no CUDA device")
+        from beyond_deep_ensembles_b200 import _lib
+        _lib.get()
+        dev = torch.device("cuda", 0)
+    else:
+        torch.set_num_threads(1)
+        fake_abi.install(monkeypatch)
+        dev = torch.device("cpu")
+    full = script.run(dev, 1, 0, None, False)
+    wrapped = script.run(dev, 1, 0, None, False, wrap_single=True)
+    for key in VECTORS:
+        if key in ("init", "svgd_init") or (backend == "cpu" and not key.startswith("svgd")):
+            assert torch.equal(wrapped[key], full[key]), key
+        else:   # fp32 rtol 1e-5 / atol 1e-6 (north star); on the GPU also for the elementwise family (library GEMMs in the closures)
+            np.testing.assert_allclose(wrapped[key].numpy(), full[key].numpy(), rtol=1e-5, atol=1e-6, err_msg=key)
+    np.testing.assert_allclose(wrapped["swag_losses"], full["swag_losses"], rtol=1e-6)
+    np.testing.assert_allclose(wrapped["svgd_losses"], full["svgd_losses"], rtol=1e-5)
+    assert wrapped["collectives"] == [0, 0, 0]
+
+
 def test_single_rank_closure_is_the_plain_model(monkeypatch):
     """world = 1 (process_group=None): no collective; the closures still run the model on `full`, hand the gradient
     to `param.grad` with autograd's accumulate semantics, and survive a closure that replaces the .grad tensors."""
