@@ -69,6 +69,7 @@ def build(verbose: bool = True, force: bool = False) -> Path:
     if force:
         for old in OBJDIR.glob("*.o"):
             old.unlink()
+        (LIBDIR / "link.stamp").unlink(missing_ok=True)   # fresh objects are linked again even if their names did not change
     sources = sorted(CSRC.glob("*.cu"))
     headers = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
