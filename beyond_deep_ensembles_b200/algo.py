@@ -83,6 +83,13 @@ class BayesianOptimizer(Optimizer):
             key = id(optimizer if optimizer is not None else self)
             grad_scaler._per_optimizer_states[key]["stage"] = stage
 
+    def _refuse_scaler_if_sharded(self, grad_scaler, world: int) -> None:
+        """D-sharded optimizers (process_group=...) see one rank's columns only: the non-finite check of an active
+        GradScaler would be taken per rank and the ranks could disagree about skipping a step — refuse loudly."""
+        if world > 1 and _scaler_active(grad_scaler):
+            raise ValueError("a D-sharded optimizer (process_group=...) does not support an active GradScaler: the "
+                             "non-finite check would have to be agreed over the group")
+
     #: with an active GradScaler, fold unscale_ + the non-finite check into the gradient gather (SURVEY §8 f2)
     fuse_unscale_into_gather = True
 

@@ -107,6 +107,8 @@ class BBBOptimizer(BayesianOptimizer):
             owner.noise_seed = int(rows[0][1])
 
     def step(self, forward_closure, backward_closure, grad_scaler=None):
+        if grad_scaler is not None:
+            self._refuse_scaler_if_sharded(grad_scaler, bdist.world(self._group))
         base = self.state["__base_optimizer"]
         base.zero_grad()
 

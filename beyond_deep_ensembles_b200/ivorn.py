@@ -75,6 +75,7 @@ class iVONOptimizer(BayesianOptimizer):
 
     # ------------------------------------------------------------------ step
     def step(self, forward_closure, backward_closure, grad_scaler=None):
+        self._refuse_scaler_if_sharded(grad_scaler, self._arenas[0]["shard"].world)
         self._reset_state()
         self._drop_presampled(release=True)   # training does not keep the prediction-time sample buffers
 

@@ -26,7 +26,7 @@ closure equals the unsharded run on the same layout: bit for bit for the element
 the same batch, to rounding for SVGD (the n x n distance sums are added in a different order).
 
 Not covered: an active GradScaler (each rank would run the non-finite check on its own columns only and the ranks
-could disagree about skipping a step — the flag would have to be agreed over the group first), BBB / Rank-1 layers (their variational parameters live inside the modules and the layers sample in
+could disagree about skipping a step; the D-sharded optimizers raise in step()), BBB / Rank-1 layers (their variational parameters live inside the modules and the layers sample in
 `forward`; `BBBOptimizer(process_group=...)` shards them per tensor), module buffers (rank-local, as under DDP
 without buffer broadcast), non-fp32 parameters.
 """

@@ -119,6 +119,8 @@ class SVGDOptimizer(BayesianOptimizer):
         losses = []
         prebind = self._prebind_active(grad_scaler, self._layout.size, len(plist))
         scaler_on = grad_scaler is not None and grad_scaler.is_enabled()
+        if scaler_on:
+            self._refuse_scaler_if_sharded(grad_scaler, bdist.world(self._group))
         if prebind:
             self._G.zero_()   # ONE memset for all particles; autograd then accumulates straight into the arena rows
         for particle_idx in range(n):

@@ -155,3 +155,35 @@ def test_single_rank_closure_is_the_plain_model(monkeypatch):
     assert sm.collectives == 0
     with pytest.raises(TypeError):
         bde.ColumnShardedModel(gm.make_mlp().double())
+
+
+def test_sharded_optimizers_refuse_an_active_grad_scaler(monkeypatch):
+    """A D-sharded optimizer sees one rank's columns: the scaler's non-finite check would be taken per rank and the
+    ranks could disagree about skipping a step — step() raises instead (single-rank jobs keep their AMP path)."""
+    import beyond_deep_ensembles_b200 as bde
+    from beyond_deep_ensembles_b200 import dist as bdist
+    fake_abi.install(monkeypatch)
+
+    class Scaler:
+        def is_enabled(self):
+            return True
+
+    w = torch.nn.Parameter(torch.randn(64))
+    fwd, bwd = (lambda: (w ** 2).sum()), (lambda loss: loss.backward())
+    swag = bde.SwagOptimizer([w], torch.optim.SGD([w], lr=0.1), update_interval=1, deviation_samples=2)
+    ivon = bde.iVONOptimizer([torch.nn.Parameter(torch.randn(64))], lr=0.01, prior_prec=1.0, dataset_size=10, mc_samples=1)
+    swag._shard.world = 2
+    ivon._arenas[0]["shard"].world = 2
+    for opt in (swag, ivon):
+        with pytest.raises(ValueError, match="GradScaler"):
+            opt.step(fwd, bwd, grad_scaler=Scaler())
+    monkeypatch.setattr(bdist, "world", lambda group=None: 2)
+    v = torch.nn.Parameter(torch.randn(64))
+    svgd = bde.SVGDOptimizer.__new__(bde.SVGDOptimizer)        # the guard sits in front of everything step() does
+    torch.optim.Optimizer.__init__(svgd, [v], {})
+    svgd.state["__particle_count"], svgd.state["__base_optimizer"] = 2, torch.optim.SGD([v], lr=0.1)
+    svgd._group = object()
+    from beyond_deep_ensembles_b200.layout import ParamLayout
+    svgd._layout = ParamLayout([v])
+    with pytest.raises(ValueError, match="GradScaler"):
+        svgd.step(fwd, bwd, grad_scaler=Scaler())
