@@ -500,6 +500,19 @@ def other_paths(ops, peak_gbs, dev):
     return res
 
 
+def k2_traffic(n, D):
+    """DRAM bytes of one K2 launch from the committed ncu capture of this kernel (profiles/r02_k2_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum at n = 10, D = 1e8), scaled to D; None for another n or without the file."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_k2_traffic.json")) as f:
+            cap = json.load(f)
+        if n != cap["n"]:
+            return None
+        return (cap["dram__bytes_read.sum"] + cap["dram__bytes_write.sum"]) * (D / cap["D"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def whole_step_configs(dev):
     """Whole `optimizer.step(forward_closure, backward_closure)` of the drop-in classes with REAL model closures at the
     small BASELINE configs (SURVEY §8d item ii: C1 = UCI MLP, SVGD n = 10, Adam; C2 = CIFAR ResNet-20-FRN, SVGD n = 20,
@@ -998,8 +1011,9 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
                          # at n=10, D=1e8 (profiles/r02_ncu_summary.md, tensor-map kernel): 8.000 GB + 3.970 GB per launch.
                          # A citation of that capture, not a live counter: ncu cannot run inside the timed region.
-                         "traffic": 11.970e9 * (D / 1e8) if n == 10 else None,
-                         "traffic_source": "profiles/r02_ncu_summary.md (r02_prof_n10.ncu-rep, tools/sessions/r02_s11.sh)"},
+                         "traffic": k2_traffic(n, D),
+                         "traffic_source": "profiles/r02_k2_traffic.json (ncu --set full capture r02_prof_n10.ncu-rep, "
+                                           "tools/sessions/r02_s11.sh; read in profiles/r02_ncu_summary.md)"},
             "kernels": {
                 "svgd_pairdist(+bandwidth)": {"ms": k1_ms, "GBps": k1_bytes / (k1_ms * 1e-3) / 1e9,
                                                "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / peak_gbs,
