@@ -110,3 +110,39 @@ def test_reserved_stream_ids_are_the_ids_single_calls_would_take(chunks):
         got.extend(range(first, first + c))
     noise.set_seed(None)
     assert got == singles and len(set(singles)) == len(singles)
+
+
+@given(shapes=shapes, seed=st.integers(0, 2**16))
+@settings(max_examples=40, deadline=None)
+def test_column_sharded_model_closures_on_any_parameter_list(shapes, seed):
+    """ColumnShardedModel over arbitrary tensor lists (one-rank group, no collective): the flat parameter holds the
+    layout's padded vector, a write to it reaches the tensors at the next forward, the backward hands exactly the
+    tensors' gradients (padding zero) to param.grad, and accumulates like autograd."""
+    from beyond_deep_ensembles_b200 import ColumnShardedModel
+    g = torch.Generator().manual_seed(seed)
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    coeff = [torch.randn(s, generator=g) for s in shapes]
+    start = [p.detach().clone() for p in params]
+    sm = ColumnShardedModel(params)
+    L = sm.layout
+    assert sm.world == 1 and sm.shard == L.size == sm.param.numel() and (sm.lo, sm.hi) == (0, L.size)
+    assert torch.equal(L.to_logical(sm.param.detach()), torch.cat([p.reshape(-1) for p in start]))
+    assert float(sm.param.detach().abs().sum()) == float(L.from_logical(L.to_logical(sm.param.detach())).abs().sum())
+
+    def fwd():
+        return sum((c * p * p).sum() for c, p in zip(coeff, params))
+
+    def bwd(loss):
+        loss.backward()
+    f, b = sm.closures(fwd, bwd)
+    with torch.no_grad():
+        sm.param.mul_(0.5)
+    loss = f()
+    for p, s0 in zip(params, start):
+        assert torch.equal(p.detach(), 0.5 * s0)
+    b(loss)
+    want = L.from_logical(torch.cat([(2 * c * 0.5 * s0).reshape(-1) for c, s0 in zip(coeff, start)]))
+    assert torch.allclose(sm.param.grad, want, rtol=1e-6, atol=1e-7)
+    b(f())
+    assert torch.allclose(sm.param.grad, 2 * want, rtol=1e-6, atol=1e-7)
+    assert sm.collectives == 0
